@@ -1,0 +1,173 @@
+/*
+ * raystrack_b200.h -- C ABI of librsk_b200.so: the B200 (sm_100a) implementation of Raystrack's
+ * Monte-Carlo view-factor hot path.
+ *
+ * This is the drop-in boundary.  The reference (philip-ba/raystrack v1.0.2) is pure Python: its host
+ * orchestrator (src/raystrack/main.py) calls Numba kernels with flat C-contiguous NumPy arrays.  The entry
+ * points below are what a ctypes binding for that kernel boundary binds; each one names the reference
+ * interface it replaces (paths relative to /root/reference/src/raystrack/).  INTEGRATION.md shows the
+ * reference-side stub.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.  Host pointers unless a parameter says "device".
+ *   - every function returns 0 on success, a negative rsk_status otherwise; rsk_last_error() returns the
+ *     message of the last failure on the calling thread.  No exceptions cross the boundary.
+ *   - objects are opaque handles owned by the library; destroy in reverse order of creation.
+ *   - all work of a context is ordered on one CUDA stream (its own, or one supplied by the caller, e.g.
+ *     torch.cuda.current_stream().cuda_stream).  Calls that return host data synchronise that stream.
+ *   - float arrays of shape [n,3] are row-major float32 exactly as the reference passes them.
+ */
+#ifndef RAYSTRACK_B200_H
+#define RAYSTRACK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSK_ABI_VERSION 1
+
+typedef enum rsk_status {
+    RSK_OK = 0,
+    RSK_ERR_INVALID = -1,   /* bad argument */
+    RSK_ERR_CUDA = -2,      /* CUDA runtime failure (message in rsk_last_error) */
+    RSK_ERR_NO_DEVICE = -3, /* no CUDA device / wrong architecture */
+    RSK_ERR_OOM = -4
+} rsk_status;
+
+typedef struct rsk_ctx rsk_ctx;
+typedef struct rsk_scene rsk_scene;
+typedef struct rsk_emitters rsk_emitters;
+typedef struct rsk_solve rsk_solve;
+
+/* ------------------------------------------------------------------------------------------- library */
+
+const char *rsk_last_error(void);
+int rsk_abi_version(void);
+/* Number of visible CUDA devices (0 without a driver); replaces numba.cuda.is_available() (main.py:136-147). */
+int rsk_device_count(int *count);
+
+/* ------------------------------------------------------------------------------------------- context */
+
+/* One context per (process, GPU).  `stream` is a cudaStream_t to order all work on, or NULL for a private
+ * non-blocking stream.  Replaces cuda.get_current_device()/cuda.stream() (main.py:109, 419-495). */
+int rsk_ctx_create(int device_ordinal, void *stream, rsk_ctx **out);
+int rsk_ctx_destroy(rsk_ctx *ctx);
+int rsk_ctx_synchronize(rsk_ctx *ctx);
+/* CUDA-event stopwatch on the context stream (bench.py times the kernels with it). */
+int rsk_ctx_timer_start(rsk_ctx *ctx);
+int rsk_ctx_timer_stop(rsk_ctx *ctx, float *elapsed_ms);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int rsk_ctx_launch_count(rsk_ctx *ctx, int64_t *count);
+/* name[256]; info: [0]=SM count, [1]=cc major, [2]=cc minor, [3]=total global memory bytes. */
+int rsk_ctx_device_info(rsk_ctx *ctx, char *name, int64_t *info);
+
+/* ------------------------------------------------------------------------------------------- scene
+ * Replaces prepare_scene + build_bvh + PreparedSolver.get_device_scene
+ * (utils/prepared.py:170-243, 381-403; utils/bvh.py:14-72).
+ * Input is the reference's flattened scene in mesh order: v0,e1,e2,normals float32[n_tri,3], sid int32[n_tri]
+ * (mesh index of each triangle, 0 <= sid < n_surf).  With use_bvh != 0 the library builds, on the GPU, a
+ * Morton-code LBVH and collapses it into 80-byte 8-wide quantised nodes; otherwise rays test every triangle
+ * in input order (the reference's bvh="off" path, same tie order). */
+int rsk_scene_create(rsk_ctx *ctx, const float *v0, const float *e1, const float *e2, const float *normals,
+                     const int32_t *sid, int64_t n_tri, int32_t n_surf, int32_t use_bvh, rsk_scene **out);
+int rsk_scene_destroy(rsk_scene *scene);
+/* info: [0]=n_tri, [1]=n_surf, [2]=use_bvh, [3]=wide nodes, [4]=node bytes, [5]=triangle bytes,
+ *       [6]=wide-tree depth, [7]=build time in microseconds (device). */
+int rsk_scene_info(rsk_scene *scene, int64_t *info);
+/* Test hook: copy the wide BVH back.  nodes: n_nodes*80 bytes; tri_index: int32[n_tri] = input index of the
+ * triangle stored at each slot of the traversal-order triangle array.  Either pointer may be NULL. */
+int rsk_scene_download_bvh(rsk_scene *scene, void *nodes, int32_t *tri_index);
+
+/* ------------------------------------------------------------------------------------------- emitters
+ * Replaces prepare_emitters' per-mesh arrays + PreparedSolver.get_device_emitter + the Halton tables
+ * (utils/prepared.py:246-321, 405-431; utils/halton.py:9-58).  Triangles of all emitters are concatenated;
+ * emitter i owns rows [tri_offset[i], tri_offset[i+1]).  g[i] is the Halton grid side (helpers.py:8-11),
+ * rays_per_cell the `rays` parameter: emitter i shoots g[i]^2 * rays_per_cell rays per iteration.
+ * The five per-ray Halton dimensions (bases 5,2,3,7,11) and the per-cell jitter grids are generated on the
+ * device with the reference's exact float64 operation order and cached in the context. */
+int rsk_emitters_create(rsk_ctx *ctx, int32_t n_emit, const int64_t *tri_offset,
+                        const float *tri_a, const float *tri_e1, const float *tri_e2,
+                        const float *tri_u, const float *tri_v, const float *tri_n,
+                        const float *tri_eps, const float *cdf,
+                        const int32_t *g, int32_t rays_per_cell, rsk_emitters **out);
+int rsk_emitters_destroy(rsk_emitters *em);
+/* Test hook: the cached tables.  dims: float32[5][n] (rows: bases 5,2,3,7,11), n <= max rays/iteration;
+ * grid_u/grid_v: float32[g*g] for a grid side used by one of the emitters. */
+int rsk_emitters_download_tables(rsk_emitters *em, int64_t n, float *dims, int32_t g, float *grid_u, float *grid_v);
+
+/* ------------------------------------------------------------------------------------------- per-ray hook
+ * Replaces build_rays + trace_cpu_[bvh_]firsthit / trace_cpu_[bvh_]hitmask called back to back
+ * (utils/ray_builder.py:25-94; utils/cpu_trace.py:54-277, 540-732) for ONE emitter and ONE iteration, writing
+ * per-ray outputs.  cp = [cp_grid[0..1], cp_dims[0..4]] (main.py:1810-1812).  mode 0: closest hit
+ * (hit_sid = mesh index or -1, hit_front = 1 if front side); mode 1: any hit (hit_sid = 0/1 hit mask,
+ * hit_front = Tregenza patch id of a miss with dz>0, else 255).  Any output pointer may be NULL.
+ * first_ray/n_rays select a sub-range of the iteration's rays. */
+int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int32_t emitter,
+                   const uint8_t *surf_active, int32_t emit_sid, int32_t min_sid, const float *cp,
+                   int32_t mode, int64_t first_ray, int64_t n_rays,
+                   float *orig, float *dirs, int32_t *hit_sid, uint8_t *hit_front);
+
+/* ------------------------------------------------------------------------------------------- matrix solve
+ * Replaces the emitter/iteration loops of view_factor_matrix (main.py:1757-1945): per iteration and emitter
+ * build_rays -> trace -> reduce_first_hits -> Welford update -> convergence test, for a SET of emitters at once.
+ *
+ *   emit_ids[n_local]             emitters handled by this solve (this GPU's shard)
+ *   surf_active[n_local][n_surf]  main.py:167-204 mask per emitter; emit_sid/min_sid[n_local]: main.py:1181-1182
+ *   cp_table[n_rot][7]            rotations; iteration `it` of local emitter k uses row rot_base[k] + it
+ *   tol_mode: 0 = "stderr", 1 = "delta";  interval: convergence_interval (1 = the reference's CPU behaviour)
+ *
+ * rsk_matrix_step enqueues `n_iters` further iterations for every unconverged emitter: one fused
+ * raygen+closest-hit+tally kernel and one statistics/convergence kernel per iteration, no host round trip in
+ * between; emitters that converge are skipped on the device.  It then returns how many emitters are still
+ * running.  rsk_matrix_read copies the integer tallies back. */
+typedef struct rsk_solve_params {
+    int32_t max_iters;
+    int32_t min_iters;
+    int32_t interval;
+    int32_t tol_mode;
+    double tol;
+} rsk_solve_params;
+
+int rsk_matrix_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em,
+                     const int32_t *emit_ids, int32_t n_local,
+                     const uint8_t *surf_active, const int32_t *emit_sid, const int32_t *min_sid,
+                     const float *cp_table, int32_t n_rot, const int32_t *rot_base,
+                     const rsk_solve_params *params, rsk_solve **out);
+int rsk_matrix_step(rsk_solve *solve, int32_t n_iters, int32_t *n_active);
+/* hits_front/hits_back: int64[n_local][n_surf]; iters: int32[n_local]; total_rays: int64[n_local];
+ * stderr_front/back: float64[n_local][n_surf] replicate standard errors (may be NULL). */
+int rsk_matrix_read(rsk_solve *solve, int64_t *hits_front, int64_t *hits_back, int32_t *iters,
+                    int64_t *total_rays, double *stderr_front, double *stderr_back);
+/* Device pointer + element count of the int64 tally block [n_local][2][n_surf] (front rows then back rows per
+ * emitter) for collectives issued by the caller (torch.distributed / NCCL). */
+int rsk_matrix_device_tallies(rsk_solve *solve, void **device_ptr, int64_t *n_elements);
+
+/* ------------------------------------------------------------------------------------------- sky solve
+ * Replaces the loops of view_factor_to_tregenza_sky (main.py:1997-2185): any-hit trace against every active
+ * non-emitter mesh (emit_sid = emitter index, min_sid = 0), misses with dz>0 binned into the 145 Tregenza
+ * patches (utils/cpu_trace.py:735-798) when discrete != 0, else counted. */
+int rsk_sky_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em,
+                  const int32_t *emit_ids, int32_t n_local, const uint8_t *surf_active,
+                  const float *cp_table, int32_t n_rot, const int32_t *rot_base,
+                  const rsk_solve_params *params, int32_t discrete, rsk_solve **out);
+int rsk_sky_step(rsk_solve *solve, int32_t n_iters, int32_t *n_active);
+/* counts: int64[n_local][145] (discrete) or int64[n_local][1]. */
+int rsk_sky_read(rsk_solve *solve, int64_t *counts, int32_t *iters, int64_t *total_rays);
+
+int rsk_solve_destroy(rsk_solve *solve);
+/* Rays traced so far by this solve (all emitters, all iterations). */
+int rsk_solve_rays_traced(rsk_solve *solve, int64_t *rays);
+
+/* ------------------------------------------------------------------------------------------- reciprocity
+ * Replaces the dense core of enforce_reciprocity_and_rowsum (utils/helpers.py:70-96): G = 0.5*(A F + (A F)^T),
+ * symmetric diagonal scaling d <- d*sqrt(target/(d .* G d)) until max|d_new - d| < tol (<= max_iter sweeps),
+ * F' = D G D / A.  F is float64[n][n] row-major, overwritten with F'.  target may be NULL (= area). */
+int rsk_reciprocity_rowsum(rsk_ctx *ctx, int32_t n, const double *area, const double *target,
+                           double *F, double tol, int32_t max_iter, int32_t *sweeps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYSTRACK_B200_H */

@@ -1,0 +1,294 @@
+"""ctypes binding of librsk_b200.so (include/raystrack_b200.h) -- the only bridge between the Python host
+code and the CUDA implementation.  There is no CPU fallback: every entry point raises if the library or a
+B200 is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "_lib" / "librsk_b200.so"
+_lib: Optional[C.CDLL] = None
+
+
+class SolveParams(C.Structure):
+    _fields_ = [("max_iters", C.c_int32), ("min_iters", C.c_int32), ("interval", C.c_int32),
+                ("tol_mode", C.c_int32), ("tol", C.c_double)]
+
+
+EXPORTS = (
+    "rsk_last_error", "rsk_abi_version", "rsk_device_count",
+    "rsk_ctx_create", "rsk_ctx_destroy", "rsk_ctx_synchronize", "rsk_ctx_timer_start", "rsk_ctx_timer_stop",
+    "rsk_ctx_launch_count", "rsk_ctx_device_info",
+    "rsk_scene_create", "rsk_scene_destroy", "rsk_scene_info", "rsk_scene_download_bvh",
+    "rsk_emitters_create", "rsk_emitters_destroy", "rsk_emitters_download_tables",
+    "rsk_trace_rays",
+    "rsk_matrix_begin", "rsk_matrix_step", "rsk_matrix_read", "rsk_matrix_device_tallies",
+    "rsk_sky_begin", "rsk_sky_step", "rsk_sky_read",
+    "rsk_solve_destroy", "rsk_solve_rays_traced", "rsk_reciprocity_rowsum",
+)
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the in-tree library, building it with nvcc when it is missing (never falls back to anything else)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists() or os.environ.get("RSK_REBUILD"):
+        from . import _build
+        _build.build(force=bool(os.environ.get("RSK_REBUILD")))
+    lib = C.CDLL(str(LIB_PATH))
+    lib.rsk_last_error.restype = C.c_char_p
+    for name in EXPORTS:
+        if name != "rsk_last_error":
+            getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().rsk_last_error().decode("utf-8", "replace")
+        raise NativeError(f"{what or 'librsk_b200'} failed (status {rc}): {msg}")
+
+
+def ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(load().rsk_device_count(C.byref(n)), "rsk_device_count")
+    return int(n.value)
+
+
+class Context:
+    """One CUDA context/stream per (process, GPU) -- wraps ``rsk_ctx``."""
+
+    _by_device: dict = {}
+
+    def __init__(self, device: int = 0, stream: int = 0):
+        self.lib = load()
+        self.handle = C.c_void_p()
+        check(self.lib.rsk_ctx_create(C.c_int(device), C.c_void_p(stream or None), C.byref(self.handle)), "rsk_ctx_create")
+        self.device = device
+
+    @classmethod
+    def for_device(cls, device: Optional[int] = None) -> "Context":
+        if device is None:
+            device = int(os.environ.get("RSK_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            n = device_count()
+            if n > 0:
+                device %= n
+        ctx = cls._by_device.get(device)
+        if ctx is None:
+            ctx = cls(device)
+            cls._by_device[device] = ctx
+        return ctx
+
+    def synchronize(self) -> None:
+        check(self.lib.rsk_ctx_synchronize(self.handle))
+
+    def timer_start(self) -> None:
+        check(self.lib.rsk_ctx_timer_start(self.handle))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        check(self.lib.rsk_ctx_timer_stop(self.handle, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        n = C.c_int64(0)
+        check(self.lib.rsk_ctx_launch_count(self.handle, C.byref(n)))
+        return int(n.value)
+
+    def device_info(self) -> dict:
+        name = C.create_string_buffer(256)
+        info = (C.c_int64 * 4)()
+        check(self.lib.rsk_ctx_device_info(self.handle, name, info))
+        return {"name": name.value.decode(), "sm_count": int(info[0]), "cc": (int(info[1]), int(info[2])), "mem": int(info[3])}
+
+    def reciprocity_rowsum(self, area: np.ndarray, F: np.ndarray, target: Optional[np.ndarray] = None,
+                           tol: float = 1e-10, max_iter: int = 500) -> int:
+        area = np.ascontiguousarray(area, np.float64)
+        assert F.dtype == np.float64 and F.flags.c_contiguous
+        tgt = None if target is None else np.ascontiguousarray(target, np.float64)
+        sweeps = C.c_int32(0)
+        check(self.lib.rsk_reciprocity_rowsum(self.handle, C.c_int32(area.shape[0]), ptr(area), ptr(tgt), ptr(F),
+                                              C.c_double(tol), C.c_int32(max_iter), C.byref(sweeps)), "rsk_reciprocity_rowsum")
+        return int(sweeps.value)
+
+
+class DeviceScene:
+    """Wraps ``rsk_scene`` (triangles + GPU-built wide BVH)."""
+
+    def __init__(self, ctx: Context, v0, e1, e2, normals, sid, n_surf: int, use_bvh: bool):
+        self.ctx = ctx
+        self.handle = C.c_void_p()
+        self.n_tri = int(v0.shape[0])
+        self.n_surf = int(n_surf)
+        self.use_bvh = bool(use_bvh and self.n_tri > 0)
+        arrs = [np.ascontiguousarray(a, np.float32) for a in (v0, e1, e2, normals)]
+        sid = np.ascontiguousarray(sid, np.int32)
+        check(ctx.lib.rsk_scene_create(ctx.handle, *(ptr(a) for a in arrs), ptr(sid), C.c_int64(self.n_tri),
+                                       C.c_int32(n_surf), C.c_int32(1 if use_bvh else 0), C.byref(self.handle)), "rsk_scene_create")
+
+    def info(self) -> dict:
+        info = (C.c_int64 * 8)()
+        check(self.ctx.lib.rsk_scene_info(self.handle, info))
+        keys = ("n_tri", "n_surf", "use_bvh", "n_nodes", "node_bytes", "tri_bytes", "depth", "build_us")
+        return dict(zip(keys, (int(x) for x in info)))
+
+    def download_bvh(self):
+        inf = self.info()
+        nodes = np.empty((inf["n_nodes"], 80), np.uint8)
+        order = np.empty(inf["n_tri"], np.int32)
+        check(self.ctx.lib.rsk_scene_download_bvh(self.handle, ptr(nodes), ptr(order)))
+        return nodes, order
+
+    def close(self) -> None:
+        if self.handle:
+            self.ctx.lib.rsk_scene_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceEmitters:
+    """Wraps ``rsk_emitters``: all emitter meshes of one (samples, rays, flip_faces) configuration."""
+
+    def __init__(self, ctx: Context, tri_offset, tri_a, tri_e1, tri_e2, tri_u, tri_v, tri_n, tri_eps, cdf, g, rays: int):
+        self.ctx = ctx
+        self.handle = C.c_void_p()
+        off = np.ascontiguousarray(tri_offset, np.int64)
+        gs = np.ascontiguousarray(g, np.int32)
+        f = [np.ascontiguousarray(a, np.float32) for a in (tri_a, tri_e1, tri_e2, tri_u, tri_v, tri_n, tri_eps, cdf)]
+        self.n_emit = int(gs.shape[0])
+        self.g = gs
+        self.rays = int(rays)
+        check(ctx.lib.rsk_emitters_create(ctx.handle, C.c_int32(self.n_emit), ptr(off), *(ptr(a) for a in f), ptr(gs),
+                                          C.c_int32(rays), C.byref(self.handle)), "rsk_emitters_create")
+
+    def download_tables(self, n: int, g: int):
+        dims = np.empty((5, n), np.float32)
+        gu = np.empty(g * g, np.float32)
+        gv = np.empty(g * g, np.float32)
+        check(self.ctx.lib.rsk_emitters_download_tables(self.handle, C.c_int64(n), ptr(dims), C.c_int32(g), ptr(gu), ptr(gv)))
+        return dims, gu, gv
+
+    def close(self) -> None:
+        if self.handle:
+            self.ctx.lib.rsk_emitters_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def trace_rays(ctx: Context, scene: DeviceScene, em: DeviceEmitters, emitter: int, surf_active: np.ndarray,
+               emit_sid: int, min_sid: int, cp: np.ndarray, mode: int = 0, first_ray: int = 0,
+               n_rays: Optional[int] = None, want_rays: bool = True):
+    """Per-ray hook (``rsk_trace_rays``): returns (orig, dirs, hit_sid, hit_front) for one emitter iteration."""
+    n_once = int(em.g[emitter]) ** 2 * em.rays
+    n = n_once - first_ray if n_rays is None else int(n_rays)
+    orig = np.empty((n, 3), np.float32) if want_rays else None
+    dirs = np.empty((n, 3), np.float32) if want_rays else None
+    hit = np.empty(n, np.int32)
+    front = np.empty(n, np.uint8)
+    act = np.ascontiguousarray(surf_active, np.uint8)
+    cpv = np.ascontiguousarray(cp, np.float32)
+    check(ctx.lib.rsk_trace_rays(ctx.handle, scene.handle, em.handle, C.c_int32(emitter), ptr(act), C.c_int32(emit_sid),
+                                 C.c_int32(min_sid), ptr(cpv), C.c_int32(mode), C.c_int64(first_ray), C.c_int64(n),
+                                 ptr(orig), ptr(dirs), ptr(hit), ptr(front)), "rsk_trace_rays")
+    return orig, dirs, hit, front
+
+
+class Solve:
+    """Wraps ``rsk_solve`` for the matrix (``sky=False``) or sky variant."""
+
+    def __init__(self, ctx: Context, scene: DeviceScene, em: DeviceEmitters, emit_ids, surf_active, cp_table, rot_base,
+                 *, max_iters: int, min_iters: int, interval: int, tol_mode: str, tol: float,
+                 emit_sid=None, min_sid=None, sky: bool = False, discrete: bool = False):
+        if tol_mode not in ("stderr", "delta"):
+            raise ValueError(f"Unknown tol_mode: {tol_mode}")
+        self.ctx, self.scene, self.em = ctx, scene, em
+        self.sky, self.discrete = bool(sky), bool(discrete)
+        self.handle = C.c_void_p()
+        self.emit_ids = np.ascontiguousarray(emit_ids, np.int32)
+        self.n_local = int(self.emit_ids.shape[0])
+        act = np.ascontiguousarray(surf_active, np.uint8).reshape(self.n_local, scene.n_surf)
+        cpt = np.ascontiguousarray(cp_table, np.float32).reshape(-1, 7)
+        rb = np.ascontiguousarray(rot_base, np.int32)
+        p = SolveParams(int(max_iters), int(min_iters), int(interval), 0 if tol_mode == "stderr" else 1, float(tol))
+        if sky:
+            check(ctx.lib.rsk_sky_begin(ctx.handle, scene.handle, em.handle, ptr(self.emit_ids), C.c_int32(self.n_local),
+                                        ptr(act), ptr(cpt), C.c_int32(cpt.shape[0]), ptr(rb), C.byref(p),
+                                        C.c_int32(1 if discrete else 0), C.byref(self.handle)), "rsk_sky_begin")
+        else:
+            es = np.ascontiguousarray(emit_sid, np.int32)
+            ms = np.ascontiguousarray(min_sid, np.int32)
+            check(ctx.lib.rsk_matrix_begin(ctx.handle, scene.handle, em.handle, ptr(self.emit_ids), C.c_int32(self.n_local),
+                                           ptr(act), ptr(es), ptr(ms), ptr(cpt), C.c_int32(cpt.shape[0]), ptr(rb),
+                                           C.byref(p), C.byref(self.handle)), "rsk_matrix_begin")
+
+    def step(self, n_iters: int) -> int:
+        n_active = C.c_int32(0)
+        fn = self.ctx.lib.rsk_sky_step if self.sky else self.ctx.lib.rsk_matrix_step
+        check(fn(self.handle, C.c_int32(n_iters), C.byref(n_active)), "solve step")
+        return int(n_active.value)
+
+    def read_matrix(self, want_stderr: bool = False):
+        ns = self.scene.n_surf
+        hf = np.zeros((self.n_local, ns), np.int64)
+        hb = np.zeros((self.n_local, ns), np.int64)
+        iters = np.zeros(self.n_local, np.int32)
+        total = np.zeros(self.n_local, np.int64)
+        sf = np.zeros((self.n_local, ns), np.float64) if want_stderr else None
+        sb = np.zeros((self.n_local, ns), np.float64) if want_stderr else None
+        check(self.ctx.lib.rsk_matrix_read(self.handle, ptr(hf), ptr(hb), ptr(iters), ptr(total), ptr(sf), ptr(sb)), "rsk_matrix_read")
+        return hf, hb, iters, total, sf, sb
+
+    def read_sky(self):
+        nb = 145 if self.discrete else 1
+        counts = np.zeros((self.n_local, nb), np.int64)
+        iters = np.zeros(self.n_local, np.int32)
+        total = np.zeros(self.n_local, np.int64)
+        check(self.ctx.lib.rsk_sky_read(self.handle, ptr(counts), ptr(iters), ptr(total)), "rsk_sky_read")
+        return counts, iters, total
+
+    def device_tallies(self):
+        p = C.c_void_p()
+        n = C.c_int64(0)
+        check(self.ctx.lib.rsk_matrix_device_tallies(self.handle, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def rays_traced(self) -> int:
+        n = C.c_int64(0)
+        check(self.ctx.lib.rsk_solve_rays_traced(self.handle, C.byref(n)))
+        return int(n.value)
+
+    def close(self) -> None:
+        if self.handle:
+            self.ctx.lib.rsk_solve_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,606 @@
+// rsk_api.cu -- the extern "C" boundary of librsk_b200 (include/raystrack_b200.h).
+#include <cstdarg>
+
+#include "rsk_stats.cuh"
+
+static thread_local char g_error[1024] = "";
+
+void rsk_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *rsk_last_error(void) { return g_error; }
+extern "C" int rsk_abi_version(void) { return RSK_ABI_VERSION; }
+
+extern "C" int rsk_device_count(int *count) {
+    RSK_REQUIRE(count, "rsk_device_count: null output");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *count = n;
+    return RSK_OK;
+}
+
+// ----------------------------------------------------------------------------- context
+
+extern "C" int rsk_ctx_create(int device, void *stream, rsk_ctx **out) {
+    RSK_REQUIRE(out, "rsk_ctx_create: null output");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        rsk_set_error("no CUDA device available: librsk_b200 has no CPU fallback");
+        return RSK_ERR_NO_DEVICE;
+    }
+    RSK_REQUIRE(device >= 0 && device < n, "rsk_ctx_create: device ordinal out of range");
+    RSK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RSK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        rsk_set_error("device %d is sm_%d%d; librsk_b200 is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return RSK_ERR_NO_DEVICE;
+    }
+    rsk_ctx *ctx = new rsk_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete ctx; rsk_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return RSK_ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    *out = ctx;
+    return RSK_OK;
+}
+
+extern "C" int rsk_ctx_destroy(rsk_ctx *ctx) {
+    if (!ctx) return RSK_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->halton);
+    cudaFree(ctx->grid);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RSK_OK;
+}
+
+extern "C" int rsk_ctx_synchronize(rsk_ctx *ctx) {
+    RSK_REQUIRE(ctx, "null context");
+    RSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RSK_OK;
+}
+
+extern "C" int rsk_ctx_timer_start(rsk_ctx *ctx) {
+    RSK_REQUIRE(ctx, "null context");
+    RSK_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    return RSK_OK;
+}
+
+extern "C" int rsk_ctx_timer_stop(rsk_ctx *ctx, float *ms) {
+    RSK_REQUIRE(ctx && ms, "rsk_ctx_timer_stop: bad arguments");
+    RSK_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    RSK_CUDA(cudaEventSynchronize(ctx->ev1));
+    RSK_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return RSK_OK;
+}
+
+extern "C" int rsk_ctx_launch_count(rsk_ctx *ctx, int64_t *count) {
+    RSK_REQUIRE(ctx && count, "rsk_ctx_launch_count: bad arguments");
+    *count = ctx->launches;
+    return RSK_OK;
+}
+
+extern "C" int rsk_ctx_device_info(rsk_ctx *ctx, char *name, int64_t *info) {
+    RSK_REQUIRE(ctx, "null context");
+    cudaDeviceProp prop;
+    RSK_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+    if (name) { strncpy(name, prop.name, 255); name[255] = 0; }
+    if (info) { info[0] = prop.multiProcessorCount; info[1] = prop.major; info[2] = prop.minor; info[3] = (int64_t)prop.totalGlobalMem; }
+    return RSK_OK;
+}
+
+// ----------------------------------------------------------------------------- scene
+
+extern "C" int rsk_scene_create(rsk_ctx *ctx, const float *v0, const float *e1, const float *e2, const float *normals,
+                                const int32_t *sid, int64_t n_tri, int32_t n_surf, int32_t use_bvh, rsk_scene **out) {
+    RSK_REQUIRE(ctx && out, "rsk_scene_create: null context/output");
+    RSK_REQUIRE(n_tri >= 0 && n_surf >= 0, "rsk_scene_create: negative sizes");
+    RSK_REQUIRE(n_tri == 0 || (v0 && e1 && e2 && normals && sid), "rsk_scene_create: null arrays");
+    RSK_REQUIRE(n_tri < (1ll << 30), "rsk_scene_create: too many triangles");
+    *out = nullptr;
+    RSK_CUDA(cudaSetDevice(ctx->device));
+    // pack (v0,sid) (e1,0) (e2,0) and (normal,sid) records in input order
+    std::vector<float4> tri((size_t)n_tri * 3), nrm((size_t)n_tri);
+    for (int64_t i = 0; i < n_tri; ++i) {
+        RSK_REQUIRE(sid[i] >= 0 && sid[i] < n_surf, "rsk_scene_create: sid out of range");
+        float sbits;
+        memcpy(&sbits, &sid[i], 4);
+        tri[3 * i] = make_float4(v0[3 * i], v0[3 * i + 1], v0[3 * i + 2], sbits);
+        tri[3 * i + 1] = make_float4(e1[3 * i], e1[3 * i + 1], e1[3 * i + 2], 0.f);
+        tri[3 * i + 2] = make_float4(e2[3 * i], e2[3 * i + 1], e2[3 * i + 2], 0.f);
+        nrm[i] = make_float4(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2], sbits);
+    }
+    rsk_scene *sc = new rsk_scene();
+    sc->ctx = ctx;
+    sc->n_tri = n_tri;
+    sc->n_surf = n_surf;
+    sc->use_bvh = (use_bvh && n_tri > 0) ? 1 : 0;
+    float4 *d_tri = nullptr, *d_nrm = nullptr;
+    int rc = rsk_dev_alloc(&d_tri, (size_t)n_tri * 3);
+    if (rc == RSK_OK) rc = rsk_dev_alloc(&d_nrm, (size_t)n_tri);
+    if (rc != RSK_OK) { cudaFree(d_tri); cudaFree(d_nrm); delete sc; return rc; }
+    cudaError_t e = cudaSuccess;
+    if (n_tri > 0) {
+        e = cudaMemcpyAsync(d_tri, tri.data(), tri.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_nrm, nrm.data(), nrm.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    if (e != cudaSuccess) {
+        rsk_set_error("scene upload failed: %s", cudaGetErrorString(e));
+        cudaFree(d_tri); cudaFree(d_nrm); delete sc;
+        return RSK_ERR_CUDA;
+    }
+    if (sc->use_bvh) {
+        rc = rsk_bvh_build(sc, d_tri, d_nrm);
+        cudaFree(d_tri);
+        cudaFree(d_nrm);
+        if (rc != RSK_OK) { rsk_scene_destroy(sc); return rc; }
+    } else {
+        sc->tri = d_tri;
+        sc->nrm = d_nrm;
+    }
+    *out = sc;
+    return RSK_OK;
+}
+
+extern "C" int rsk_scene_destroy(rsk_scene *sc) {
+    if (!sc) return RSK_OK;
+    cudaSetDevice(sc->ctx->device);
+    cudaStreamSynchronize(sc->ctx->stream);
+    cudaFree(sc->tri);
+    cudaFree(sc->nrm);
+    cudaFree(sc->nodes);
+    cudaFree(sc->tri_index);
+    delete sc;
+    return RSK_OK;
+}
+
+extern "C" int rsk_scene_info(rsk_scene *sc, int64_t *info) {
+    RSK_REQUIRE(sc && info, "rsk_scene_info: bad arguments");
+    info[0] = sc->n_tri; info[1] = sc->n_surf; info[2] = sc->use_bvh; info[3] = sc->n_nodes;
+    info[4] = sc->n_nodes * (int64_t)sizeof(WideNode); info[5] = sc->n_tri * 64; info[6] = sc->depth; info[7] = sc->build_us;
+    return RSK_OK;
+}
+
+extern "C" int rsk_scene_download_bvh(rsk_scene *sc, void *nodes, int32_t *tri_index) {
+    RSK_REQUIRE(sc && sc->use_bvh, "rsk_scene_download_bvh: scene has no BVH");
+    RSK_CUDA(cudaSetDevice(sc->ctx->device));
+    RSK_CUDA(cudaStreamSynchronize(sc->ctx->stream));
+    if (nodes) RSK_CUDA(cudaMemcpy(nodes, sc->nodes, sc->n_nodes * sizeof(WideNode), cudaMemcpyDeviceToHost));
+    if (tri_index) RSK_CUDA(cudaMemcpy(tri_index, sc->tri_index, sc->n_tri * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return RSK_OK;
+}
+
+// ----------------------------------------------------------------------------- emitters
+
+extern "C" int rsk_emitters_create(rsk_ctx *ctx, int32_t n_emit, const int64_t *tri_offset,
+                                   const float *tri_a, const float *tri_e1, const float *tri_e2,
+                                   const float *tri_u, const float *tri_v, const float *tri_n,
+                                   const float *tri_eps, const float *cdf,
+                                   const int32_t *g, int32_t rays_per_cell, rsk_emitters **out) {
+    RSK_REQUIRE(ctx && out && n_emit >= 0 && rays_per_cell > 0, "rsk_emitters_create: bad arguments");
+    RSK_REQUIRE(n_emit == 0 || (tri_offset && g), "rsk_emitters_create: null tables");
+    *out = nullptr;
+    RSK_CUDA(cudaSetDevice(ctx->device));
+    const int64_t total = n_emit ? tri_offset[n_emit] : 0;
+    RSK_REQUIRE(total < (1ll << 31), "rsk_emitters_create: too many emitter triangles");
+    RSK_REQUIRE(total == 0 || (tri_a && tri_e1 && tri_e2 && tri_u && tri_v && tri_n && tri_eps && cdf), "rsk_emitters_create: null arrays");
+    rsk_emitters *em = new rsk_emitters();
+    em->ctx = ctx;
+    em->n_emit = n_emit;
+    em->rays_per_cell = rays_per_cell;
+    em->n_tri_total = total;
+    em->h_desc.resize(n_emit);
+    int rc = RSK_OK;
+    for (int i = 0; i < n_emit && rc == RSK_OK; ++i) {
+        EmitterDesc &d = em->h_desc[i];
+        d.tri_off = (int32_t)tri_offset[i];
+        d.n_tri = (int32_t)(tri_offset[i + 1] - tri_offset[i]);
+        d.g = g[i];
+        if (d.g < 1 || d.n_tri < 0) { rsk_set_error("rsk_emitters_create: bad grid/triangle count for emitter %d", i); rc = RSK_ERR_INVALID; break; }
+        d.n_rays_once = (int64_t)d.g * d.g * rays_per_cell;
+        em->max_rays_once = std::max(em->max_rays_once, d.n_rays_once);
+        int64_t off = 0;
+        rc = rsk_qmc_ensure_grid(ctx, d.g, &off);
+        d.grid_off = (int32_t)off;
+    }
+    if (rc == RSK_OK) rc = rsk_qmc_ensure_halton(ctx, em->max_rays_once);
+    std::vector<float4> rec((size_t)total * 5);
+    for (int64_t t = 0; t < total; ++t) {
+        rec[5 * t + 0] = make_float4(tri_a[3 * t], tri_a[3 * t + 1], tri_a[3 * t + 2], tri_eps[t]);
+        rec[5 * t + 1] = make_float4(tri_e1[3 * t], tri_e1[3 * t + 1], tri_e1[3 * t + 2], tri_n[3 * t]);
+        rec[5 * t + 2] = make_float4(tri_e2[3 * t], tri_e2[3 * t + 1], tri_e2[3 * t + 2], tri_n[3 * t + 1]);
+        rec[5 * t + 3] = make_float4(tri_u[3 * t], tri_u[3 * t + 1], tri_u[3 * t + 2], tri_n[3 * t + 2]);
+        rec[5 * t + 4] = make_float4(tri_v[3 * t], tri_v[3 * t + 1], tri_v[3 * t + 2], 0.f);
+    }
+    if (rc == RSK_OK) rc = rsk_dev_alloc(&em->tri, rec.size());
+    if (rc == RSK_OK) rc = rsk_dev_alloc(&em->cdf, (size_t)total);
+    if (rc == RSK_OK) rc = rsk_dev_alloc(&em->desc, (size_t)n_emit);
+    if (rc == RSK_OK) {
+        cudaError_t e = cudaSuccess;
+        if (total > 0) {
+            e = cudaMemcpyAsync(em->tri, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(em->cdf, cdf, total * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+        }
+        if (e == cudaSuccess && n_emit > 0)
+            e = cudaMemcpyAsync(em->desc, em->h_desc.data(), n_emit * sizeof(EmitterDesc), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { rsk_set_error("emitter upload failed: %s", cudaGetErrorString(e)); rc = RSK_ERR_CUDA; }
+    }
+    if (rc != RSK_OK) { rsk_emitters_destroy(em); return rc; }
+    *out = em;
+    return RSK_OK;
+}
+
+extern "C" int rsk_emitters_destroy(rsk_emitters *em) {
+    if (!em) return RSK_OK;
+    cudaSetDevice(em->ctx->device);
+    cudaStreamSynchronize(em->ctx->stream);
+    cudaFree(em->tri);
+    cudaFree(em->cdf);
+    cudaFree(em->desc);
+    delete em;
+    return RSK_OK;
+}
+
+extern "C" int rsk_emitters_download_tables(rsk_emitters *em, int64_t n, float *dims, int32_t g, float *grid_u, float *grid_v) {
+    RSK_REQUIRE(em, "null emitters");
+    rsk_ctx *ctx = em->ctx;
+    RSK_CUDA(cudaSetDevice(ctx->device));
+    RSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (dims) {
+        RSK_REQUIRE(n <= ctx->halton_cap, "rsk_emitters_download_tables: n exceeds the cached table");
+        for (int r = 0; r < 5; ++r)
+            RSK_CUDA(cudaMemcpy(dims + r * n, ctx->halton + r * ctx->halton_cap, n * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    if (grid_u || grid_v) {
+        auto it = ctx->grid_index.find(g);
+        RSK_REQUIRE(it != ctx->grid_index.end(), "rsk_emitters_download_tables: grid size not cached");
+        std::vector<float2> tmp((size_t)it->second.second);
+        RSK_CUDA(cudaMemcpy(tmp.data(), ctx->grid + it->second.first, tmp.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+        for (size_t c = 0; c < tmp.size(); ++c) {
+            if (grid_u) grid_u[c] = tmp[c].x;
+            if (grid_v) grid_v[c] = tmp[c].y;
+        }
+    }
+    return RSK_OK;
+}
+
+// ----------------------------------------------------------------------------- helpers for masks / uploads
+
+static void rsk_pack_mask(const uint8_t *active, int n_surf, int emit_sid, int min_sid, uint32_t *words) {
+    // utils/cpu_trace.py:45-51 `_skip_surface` folded into one bit per surface (bit set = NOT skipped)
+    const int nw = (n_surf + 31) / 32;
+    for (int w = 0; w < nw; ++w) words[w] = 0;
+    for (int s = 0; s < n_surf; ++s)
+        if (active[s] != 0 && s >= min_sid && s != emit_sid) words[s >> 5] |= 1u << (s & 31);
+}
+
+template <typename T>
+static int rsk_upload(rsk_ctx *ctx, T **dst, const T *src, size_t count) {
+    RSK_TRY(rsk_dev_alloc(dst, count));
+    if (count) RSK_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return RSK_OK;
+}
+
+// ----------------------------------------------------------------------------- per-ray hook
+
+extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int32_t emitter,
+                              const uint8_t *surf_active, int32_t emit_sid, int32_t min_sid, const float *cp,
+                              int32_t mode, int64_t first_ray, int64_t n_rays,
+                              float *orig, float *dirs, int32_t *hit_sid, uint8_t *hit_front) {
+    RSK_REQUIRE(ctx && scene && em && surf_active && cp, "rsk_trace_rays: null argument");
+    RSK_REQUIRE(emitter >= 0 && emitter < em->n_emit, "rsk_trace_rays: emitter out of range");
+    RSK_REQUIRE(mode == 0 || mode == 1, "rsk_trace_rays: mode must be 0 or 1");
+    const int64_t n_once = em->h_desc[emitter].n_rays_once;
+    RSK_REQUIRE(first_ray >= 0 && n_rays >= 0 && first_ray + n_rays <= n_once, "rsk_trace_rays: ray range out of bounds");
+    if (n_rays == 0) return RSK_OK;
+    RSK_CUDA(cudaSetDevice(ctx->device));
+    const int nw = (scene->n_surf + 31) / 32;
+    std::vector<uint32_t> mask(std::max(nw, 1));
+    rsk_pack_mask(surf_active, scene->n_surf, emit_sid, min_sid, mask.data());
+    const int64_t n_tiles = (n_rays + RSK_TILE_RAYS - 1) / RSK_TILE_RAYS;
+    const int64_t tiles[2] = {0, n_tiles};
+    const int32_t zero = 0;
+
+    uint32_t *d_mask = nullptr; float *d_cp = nullptr; int32_t *d_ids = nullptr, *d_zero = nullptr; int64_t *d_tiles = nullptr;
+    float *d_orig = nullptr, *d_dirs = nullptr; int32_t *d_hit = nullptr; uint8_t *d_front = nullptr;
+    auto cleanup = [&]() { cudaFree(d_mask); cudaFree(d_cp); cudaFree(d_ids); cudaFree(d_zero); cudaFree(d_tiles);
+                           cudaFree(d_orig); cudaFree(d_dirs); cudaFree(d_hit); cudaFree(d_front); };
+    int rc = RSK_OK;
+#define T_TRY(expr) do { rc = (expr); if (rc != RSK_OK) { cleanup(); return rc; } } while (0)
+#define T_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rsk_set_error("%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); return RSK_ERR_CUDA; } } while (0)
+    T_TRY(rsk_upload(ctx, &d_mask, mask.data(), mask.size()));
+    T_TRY(rsk_upload(ctx, &d_cp, cp, 7));
+    T_TRY(rsk_upload(ctx, &d_ids, &emitter, 1));
+    T_TRY(rsk_upload(ctx, &d_zero, &zero, 1));
+    T_TRY(rsk_upload(ctx, &d_tiles, tiles, 2));
+    if (orig) T_TRY(rsk_dev_alloc(&d_orig, (size_t)n_rays * 3));
+    if (dirs) T_TRY(rsk_dev_alloc(&d_dirs, (size_t)n_rays * 3));
+    if (hit_sid) T_TRY(rsk_dev_alloc(&d_hit, (size_t)n_rays));
+    if (hit_front) T_TRY(rsk_dev_alloc(&d_front, (size_t)n_rays));
+
+    TraceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sc = scene->view();
+    a.ev = em->view();
+    a.emit_ids = d_ids; a.tile_start = d_tiles; a.n_local = 1; a.surf_mask = d_mask;
+    a.cp_table = d_cp; a.rot_base = d_zero; a.iters_done = d_zero; a.done = nullptr; a.tally = nullptr;
+    a.n_hist = mode == MODE_MATRIX ? 2 * scene->n_surf : RSK_TREGENZA_BINS;
+    a.ray_first = first_ray; a.ray_count = n_rays;
+    a.dbg_orig = d_orig; a.dbg_dirs = d_dirs; a.dbg_hit = d_hit; a.dbg_front = d_front;
+    T_TRY(rsk_launch_trace(ctx, a, mode, n_tiles));
+    if (orig) T_CUDA(cudaMemcpyAsync(orig, d_orig, (size_t)n_rays * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (dirs) T_CUDA(cudaMemcpyAsync(dirs, d_dirs, (size_t)n_rays * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (hit_sid) T_CUDA(cudaMemcpyAsync(hit_sid, d_hit, (size_t)n_rays * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (hit_front) T_CUDA(cudaMemcpyAsync(hit_front, d_front, (size_t)n_rays, cudaMemcpyDeviceToHost, ctx->stream));
+    T_CUDA(cudaStreamSynchronize(ctx->stream));
+    T_CUDA(cudaGetLastError());
+    cleanup();
+#undef T_TRY
+#undef T_CUDA
+    return RSK_OK;
+}
+
+// ----------------------------------------------------------------------------- solves
+
+struct rsk_solve {
+    rsk_ctx *ctx = nullptr;
+    rsk_scene *scene = nullptr;
+    rsk_emitters *em = nullptr;
+    int mode = MODE_MATRIX;
+    int32_t n_local = 0, n_hist = 0, discrete = 0;
+    rsk_solve_params p{};
+    int64_t n_tiles = 0;
+    // device state
+    int32_t *emit_ids = nullptr, *rot_base = nullptr, *iters_done = nullptr, *done = nullptr, *not_conv = nullptr, *have_prev = nullptr;
+    int64_t *tile_start = nullptr, *n_rays_once = nullptr, *total_rays = nullptr;
+    uint32_t *mask = nullptr;
+    float *cp_table = nullptr;
+    unsigned long long *iter_tally = nullptr, *rays_traced = nullptr;
+    long long *total = nullptr;
+    double *mean = nullptr, *m2 = nullptr, *prev = nullptr;
+    int32_t *n_active = nullptr;
+    int32_t *h_pinned = nullptr;     // [0] n_active
+    int32_t last_active = 0;
+};
+
+static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int mode, int discrete,
+                           const int32_t *emit_ids, int32_t n_local, const uint8_t *surf_active,
+                           const int32_t *emit_sid, const int32_t *min_sid,
+                           const float *cp_table, int32_t n_rot, const int32_t *rot_base,
+                           const rsk_solve_params *params, rsk_solve **out) {
+    RSK_REQUIRE(ctx && scene && em && params && out, "solve begin: null argument");
+    RSK_REQUIRE(n_local >= 0 && n_rot >= 0, "solve begin: negative sizes");
+    RSK_REQUIRE(n_local == 0 || (emit_ids && surf_active && cp_table && rot_base), "solve begin: null arrays");
+    RSK_REQUIRE(params->tol_mode == 0 || params->tol_mode == 1, "solve begin: tol_mode must be 0 (stderr) or 1 (delta)");
+    *out = nullptr;
+    RSK_CUDA(cudaSetDevice(ctx->device));
+    rsk_solve *s = new rsk_solve();
+    s->ctx = ctx; s->scene = scene; s->em = em; s->mode = mode; s->n_local = n_local; s->discrete = discrete;
+    s->p = *params;
+    s->n_hist = mode == MODE_MATRIX ? 2 * scene->n_surf : (discrete ? RSK_TREGENZA_BINS : 1);
+    const int nw = std::max((scene->n_surf + 31) / 32, 1);
+    std::vector<uint32_t> mask((size_t)n_local * nw);
+    std::vector<int64_t> tiles(n_local + 1, 0), once(n_local);
+    int rc = RSK_OK;
+    for (int k = 0; k < n_local; ++k) {
+        if (emit_ids[k] < 0 || emit_ids[k] >= em->n_emit) { rsk_set_error("solve begin: emitter id out of range"); rc = RSK_ERR_INVALID; break; }
+        if (rot_base[k] < 0 || (int64_t)rot_base[k] + std::max(params->max_iters, 0) > n_rot) { rsk_set_error("solve begin: rotation table too short"); rc = RSK_ERR_INVALID; break; }
+        const int es = emit_sid ? emit_sid[k] : emit_ids[k], ms = min_sid ? min_sid[k] : 0;
+        rsk_pack_mask(surf_active + (size_t)k * scene->n_surf, scene->n_surf, es, ms, mask.data() + (size_t)k * nw);
+        once[k] = em->h_desc[emit_ids[k]].n_rays_once;
+        tiles[k + 1] = tiles[k] + (once[k] + RSK_TILE_RAYS - 1) / RSK_TILE_RAYS;
+    }
+    s->n_tiles = tiles[n_local];
+    const size_t nh = (size_t)n_local * s->n_hist;
+    auto fail = [&](int code) { rsk_solve_destroy(s); return code; };
+    if (rc != RSK_OK) return fail(rc);
+#define S_TRY(expr) do { rc = (expr); if (rc != RSK_OK) return fail(rc); } while (0)
+#define S_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rsk_set_error("%s failed: %s", #call, cudaGetErrorString(e__)); return fail(e__ == cudaErrorMemoryAllocation ? RSK_ERR_OOM : RSK_ERR_CUDA); } } while (0)
+    S_TRY(rsk_upload(ctx, &s->emit_ids, emit_ids, n_local));
+    S_TRY(rsk_upload(ctx, &s->rot_base, rot_base, n_local));
+    S_TRY(rsk_upload(ctx, &s->tile_start, tiles.data(), tiles.size()));
+    S_TRY(rsk_upload(ctx, &s->n_rays_once, once.data(), once.size()));
+    S_TRY(rsk_upload(ctx, &s->mask, mask.data(), mask.size()));
+    S_TRY(rsk_upload(ctx, &s->cp_table, cp_table, (size_t)n_rot * 7));
+    S_TRY(rsk_dev_alloc(&s->iters_done, n_local)); S_TRY(rsk_dev_alloc(&s->done, n_local));
+    S_TRY(rsk_dev_alloc(&s->not_conv, n_local)); S_TRY(rsk_dev_alloc(&s->have_prev, n_local));
+    S_TRY(rsk_dev_alloc(&s->total_rays, n_local));
+    S_TRY(rsk_dev_alloc(&s->iter_tally, nh)); S_TRY(rsk_dev_alloc(&s->total, nh));
+    S_TRY(rsk_dev_alloc(&s->mean, nh)); S_TRY(rsk_dev_alloc(&s->m2, nh));
+    if (params->tol_mode == 1) S_TRY(rsk_dev_alloc(&s->prev, nh));
+    S_TRY(rsk_dev_alloc(&s->n_active, 1)); S_TRY(rsk_dev_alloc(&s->rays_traced, 1));
+    S_CUDA(cudaMallocHost((void **)&s->h_pinned, 4 * sizeof(int32_t)));
+    cudaStream_t st = ctx->stream;
+    const size_t nl = std::max(n_local, 1);
+    S_CUDA(cudaMemsetAsync(s->iters_done, 0, nl * sizeof(int32_t), st));
+    S_CUDA(cudaMemsetAsync(s->done, 0, nl * sizeof(int32_t), st));
+    S_CUDA(cudaMemsetAsync(s->not_conv, 0, nl * sizeof(int32_t), st));
+    S_CUDA(cudaMemsetAsync(s->have_prev, 0, nl * sizeof(int32_t), st));
+    S_CUDA(cudaMemsetAsync(s->total_rays, 0, nl * sizeof(int64_t), st));
+    const size_t nh1 = std::max(nh, (size_t)1);
+    S_CUDA(cudaMemsetAsync(s->iter_tally, 0, nh1 * 8, st));
+    S_CUDA(cudaMemsetAsync(s->total, 0, nh1 * 8, st));
+    S_CUDA(cudaMemsetAsync(s->mean, 0, nh1 * 8, st));
+    S_CUDA(cudaMemsetAsync(s->m2, 0, nh1 * 8, st));
+    if (s->prev) S_CUDA(cudaMemsetAsync(s->prev, 0, nh1 * 8, st));
+    S_CUDA(cudaMemsetAsync(s->rays_traced, 0, 8, st));
+    S_CUDA(cudaStreamSynchronize(st));
+#undef S_TRY
+#undef S_CUDA
+    s->last_active = (params->max_iters > 0) ? n_local : 0;
+    *out = s;
+    return RSK_OK;
+}
+
+static int rsk_solve_step(rsk_solve *s, int32_t n_iters, int32_t *n_active) {
+    RSK_REQUIRE(s && n_iters >= 0, "solve step: bad arguments");
+    rsk_ctx *ctx = s->ctx;
+    RSK_CUDA(cudaSetDevice(ctx->device));
+    if (s->n_local == 0 || s->p.max_iters <= 0 || s->last_active == 0 || n_iters == 0) {
+        if (n_active) *n_active = s->last_active;
+        return RSK_OK;
+    }
+    TraceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sc = s->scene->view();
+    a.ev = s->em->view();
+    a.emit_ids = s->emit_ids; a.tile_start = s->tile_start; a.n_local = s->n_local; a.surf_mask = s->mask;
+    a.cp_table = s->cp_table; a.rot_base = s->rot_base; a.iters_done = s->iters_done; a.done = s->done;
+    a.tally = s->iter_tally; a.n_hist = s->n_hist; a.ray_first = 0; a.ray_count = -1;
+
+    FoldArgs f;
+    memset(&f, 0, sizeof(f));
+    f.iter_tally = s->iter_tally; f.total = s->total; f.mean = s->mean; f.m2 = s->m2; f.prev = s->prev;
+    f.surf_mask = s->mode == MODE_MATRIX ? s->mask : nullptr;
+    f.n_rays_once = s->n_rays_once; f.iters_done = s->iters_done; f.total_rays = s->total_rays; f.done = s->done;
+    f.not_converged = s->not_conv; f.n_local = s->n_local; f.n_hist = s->n_hist; f.n_surf = s->scene->n_surf;
+    f.mask_words = (s->scene->n_surf + 31) / 32;
+    f.max_iters = s->p.max_iters; f.min_iters = s->p.min_iters; f.interval = s->p.interval; f.tol_mode = s->p.tol_mode;
+    f.scalar_sky = (s->mode == MODE_SKY && !s->discrete) ? 1 : 0;
+    f.tol = s->p.tol;
+
+    DecideArgs d;
+    memset(&d, 0, sizeof(d));
+    d.iters_done = s->iters_done; d.total_rays = s->total_rays; d.done = s->done; d.not_converged = s->not_conv;
+    d.have_prev = s->have_prev; d.n_rays_once = s->n_rays_once; d.n_active = s->n_active; d.rays_traced = s->rays_traced;
+    d.n_local = s->n_local; d.max_iters = s->p.max_iters; d.min_iters = s->p.min_iters; d.interval = s->p.interval;
+    d.tol_mode = s->p.tol_mode;
+
+    for (int it = 0; it < n_iters; ++it) {
+        RSK_TRY(rsk_launch_trace(ctx, a, s->mode, s->n_tiles));
+        RSK_TRY(rsk_launch_fold(ctx, f));
+        RSK_CUDA(cudaMemsetAsync(s->n_active, 0, sizeof(int32_t), ctx->stream));
+        RSK_TRY(rsk_launch_decide(ctx, d));
+    }
+    RSK_CUDA(cudaMemcpyAsync(s->h_pinned, s->n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    RSK_CUDA(cudaGetLastError());
+    s->last_active = s->h_pinned[0];
+    if (n_active) *n_active = s->last_active;
+    return RSK_OK;
+}
+
+extern "C" int rsk_matrix_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, const int32_t *emit_ids, int32_t n_local,
+                                const uint8_t *surf_active, const int32_t *emit_sid, const int32_t *min_sid,
+                                const float *cp_table, int32_t n_rot, const int32_t *rot_base,
+                                const rsk_solve_params *params, rsk_solve **out) {
+    RSK_REQUIRE(n_local == 0 || (emit_sid && min_sid), "rsk_matrix_begin: null emit_sid/min_sid");
+    return rsk_solve_begin(ctx, scene, em, MODE_MATRIX, 0, emit_ids, n_local, surf_active, emit_sid, min_sid, cp_table, n_rot, rot_base, params, out);
+}
+
+extern "C" int rsk_matrix_step(rsk_solve *s, int32_t n_iters, int32_t *n_active) {
+    RSK_REQUIRE(s && s->mode == MODE_MATRIX, "rsk_matrix_step: not a matrix solve");
+    return rsk_solve_step(s, n_iters, n_active);
+}
+
+static int rsk_read_common(rsk_solve *s, int32_t *iters, int64_t *total_rays) {
+    if (iters && s->n_local) RSK_CUDA(cudaMemcpyAsync(iters, s->iters_done, s->n_local * sizeof(int32_t), cudaMemcpyDeviceToHost, s->ctx->stream));
+    if (total_rays && s->n_local) RSK_CUDA(cudaMemcpyAsync(total_rays, s->total_rays, s->n_local * sizeof(int64_t), cudaMemcpyDeviceToHost, s->ctx->stream));
+    return RSK_OK;
+}
+
+extern "C" int rsk_matrix_read(rsk_solve *s, int64_t *hits_front, int64_t *hits_back, int32_t *iters, int64_t *total_rays,
+                               double *stderr_front, double *stderr_back) {
+    RSK_REQUIRE(s && s->mode == MODE_MATRIX, "rsk_matrix_read: not a matrix solve");
+    RSK_CUDA(cudaSetDevice(s->ctx->device));
+    const int ns = s->scene->n_surf;
+    const size_t nh = (size_t)s->n_local * s->n_hist;
+    std::vector<int32_t> h_iters(std::max(s->n_local, 1));
+    RSK_TRY(rsk_read_common(s, h_iters.data(), total_rays));
+    std::vector<long long> tot(nh);
+    std::vector<double> m2;
+    if (nh) RSK_CUDA(cudaMemcpyAsync(tot.data(), s->total, nh * 8, cudaMemcpyDeviceToHost, s->ctx->stream));
+    if ((stderr_front || stderr_back) && nh) {
+        m2.resize(nh);
+        RSK_CUDA(cudaMemcpyAsync(m2.data(), s->m2, nh * 8, cudaMemcpyDeviceToHost, s->ctx->stream));
+    }
+    RSK_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    for (int k = 0; k < s->n_local; ++k) {
+        if (iters) iters[k] = h_iters[k];
+        for (int j = 0; j < ns; ++j) {
+            if (hits_front) hits_front[(size_t)k * ns + j] = tot[(size_t)k * s->n_hist + j];
+            if (hits_back) hits_back[(size_t)k * ns + j] = tot[(size_t)k * s->n_hist + ns + j];
+            if (!m2.empty()) {
+                const int n = h_iters[k];
+                for (int side = 0; side < 2; ++side) {
+                    double *dst = side ? stderr_back : stderr_front;
+                    if (!dst) continue;
+                    const double v = m2[(size_t)k * s->n_hist + side * ns + j];
+                    dst[(size_t)k * ns + j] = n > 1 ? sqrt(std::max(v / (n - 1), 0.0) / n) : INFINITY;   // main.py:1911-1916
+                }
+            }
+        }
+    }
+    return RSK_OK;
+}
+
+extern "C" int rsk_matrix_device_tallies(rsk_solve *s, void **device_ptr, int64_t *n_elements) {
+    RSK_REQUIRE(s && device_ptr && n_elements, "rsk_matrix_device_tallies: bad arguments");
+    *device_ptr = s->total;
+    *n_elements = (int64_t)s->n_local * s->n_hist;
+    return RSK_OK;
+}
+
+extern "C" int rsk_sky_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, const int32_t *emit_ids, int32_t n_local,
+                             const uint8_t *surf_active, const float *cp_table, int32_t n_rot, const int32_t *rot_base,
+                             const rsk_solve_params *params, int32_t discrete, rsk_solve **out) {
+    // main.py:2112: emit_sid = emitter index, min_sid = 0
+    return rsk_solve_begin(ctx, scene, em, MODE_SKY, discrete ? 1 : 0, emit_ids, n_local, surf_active, nullptr, nullptr, cp_table, n_rot, rot_base, params, out);
+}
+
+extern "C" int rsk_sky_step(rsk_solve *s, int32_t n_iters, int32_t *n_active) {
+    RSK_REQUIRE(s && s->mode == MODE_SKY, "rsk_sky_step: not a sky solve");
+    return rsk_solve_step(s, n_iters, n_active);
+}
+
+extern "C" int rsk_sky_read(rsk_solve *s, int64_t *counts, int32_t *iters, int64_t *total_rays) {
+    RSK_REQUIRE(s && s->mode == MODE_SKY, "rsk_sky_read: not a sky solve");
+    RSK_CUDA(cudaSetDevice(s->ctx->device));
+    RSK_TRY(rsk_read_common(s, iters, total_rays));
+    const size_t nh = (size_t)s->n_local * s->n_hist;
+    if (counts && nh) RSK_CUDA(cudaMemcpyAsync(counts, s->total, nh * 8, cudaMemcpyDeviceToHost, s->ctx->stream));
+    RSK_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    return RSK_OK;
+}
+
+extern "C" int rsk_solve_rays_traced(rsk_solve *s, int64_t *rays) {
+    RSK_REQUIRE(s && rays, "rsk_solve_rays_traced: bad arguments");
+    RSK_CUDA(cudaSetDevice(s->ctx->device));
+    unsigned long long v = 0;
+    RSK_CUDA(cudaMemcpyAsync(&v, s->rays_traced, 8, cudaMemcpyDeviceToHost, s->ctx->stream));
+    RSK_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    *rays = (int64_t)v;
+    return RSK_OK;
+}
+
+extern "C" int rsk_solve_destroy(rsk_solve *s) {
+    if (!s) return RSK_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    cudaFree(s->emit_ids); cudaFree(s->rot_base); cudaFree(s->iters_done); cudaFree(s->done); cudaFree(s->not_conv);
+    cudaFree(s->have_prev); cudaFree(s->tile_start); cudaFree(s->n_rays_once); cudaFree(s->total_rays); cudaFree(s->mask);
+    cudaFree(s->cp_table); cudaFree(s->iter_tally); cudaFree(s->rays_traced); cudaFree(s->total); cudaFree(s->mean);
+    cudaFree(s->m2); cudaFree(s->prev); cudaFree(s->n_active);
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    delete s;
+    return RSK_OK;
+}

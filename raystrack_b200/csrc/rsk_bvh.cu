@@ -1,0 +1,464 @@
+// rsk_bvh.cu -- GPU BVH builder: Morton-code LBVH (Karras 2012) collapsed into 80-byte 8-wide quantised nodes.
+//
+// Replaces utils/bvh.py:14-72 (`build_bvh`, a recursive median split in Python: 20 s for 1M triangles) and the
+// permutation step of utils/prepared.py:223-228.  The tree is a different one (closest hits do not depend on
+// the tree except at exact t ties); what is kept is the contract: every triangle of the scene is
+// reachable, in a traversal-order triangle array, with its mesh id.
+//
+// Pipeline (all on the device, one stream):
+//   1. triangle boxes + centroids, scene bounds (block reduce + ordered-int atomics)
+//   2. 63-bit Morton codes, cub radix sort of (code, triangle) pairs
+//   3. Karras' binary radix tree over the sorted codes (one thread per internal node)
+//   4. bottom-up box refit with per-node arrival counters
+//   5. level-by-level collapse: a wide node adopts the binary subtree roots obtained by repeatedly opening the
+//      child with the largest surface area until 8 children (sub-trees of <= 3 triangles become leaf children),
+//      assigns children to octant slots, quantises their boxes conservatively to 8 bits and emits its triangles
+//   6. gather of the triangle / normal records into traversal order
+#include <cub/cub.cuh>
+
+#include "rsk_common.cuh"
+
+namespace {
+
+struct Box {
+    float3 lo, hi;
+};
+
+__device__ __forceinline__ unsigned ord_from_float(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_ord(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// ---- 1. boxes, centroids, scene bounds.  bounds[0..2] = min (ordered uint), bounds[3..5] = max
+__global__ void k_tri_boxes(const float4 *__restrict__ tri, int n, float4 *blo, float4 *bhi, unsigned *bounds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 lo = make_float3(3e38f, 3e38f, 3e38f), hi = make_float3(-3e38f, -3e38f, -3e38f);
+    if (i < n) {
+        const float4 a = tri[3 * (int64_t)i], e1 = tri[3 * (int64_t)i + 1], e2 = tri[3 * (int64_t)i + 2];
+        const float3 p1 = make_float3(a.x + e1.x, a.y + e1.y, a.z + e1.z);
+        const float3 p2 = make_float3(a.x + e2.x, a.y + e2.y, a.z + e2.z);
+        lo = make_float3(fminf(a.x, fminf(p1.x, p2.x)), fminf(a.y, fminf(p1.y, p2.y)), fminf(a.z, fminf(p1.z, p2.z)));
+        hi = make_float3(fmaxf(a.x, fmaxf(p1.x, p2.x)), fmaxf(a.y, fmaxf(p1.y, p2.y)), fmaxf(a.z, fmaxf(p1.z, p2.z)));
+        blo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
+        bhi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
+    }
+    typedef cub::BlockReduce<float, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    float v[6] = {lo.x, lo.y, lo.z, hi.x, hi.y, hi.z};
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        float r = c < 3 ? BR(tmp).Reduce(v[c], cub::Min()) : BR(tmp).Reduce(v[c], cub::Max());
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (c < 3) atomicMin(&bounds[c], ord_from_float(r));
+            else atomicMax(&bounds[c], ord_from_float(r));
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long x) {
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+// ---- 2. Morton codes of the box centres
+__global__ void k_morton(const float4 *blo, const float4 *bhi, int n, const unsigned *bounds,
+                         unsigned long long *codes, unsigned *ids) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float3 smin = make_float3(float_from_ord(bounds[0]), float_from_ord(bounds[1]), float_from_ord(bounds[2]));
+    const float3 smax = make_float3(float_from_ord(bounds[3]), float_from_ord(bounds[4]), float_from_ord(bounds[5]));
+    const float4 lo = blo[i], hi = bhi[i];
+    const float ex = fmaxf(smax.x - smin.x, 1e-30f), ey = fmaxf(smax.y - smin.y, 1e-30f), ez = fmaxf(smax.z - smin.z, 1e-30f);
+    const float cx = (0.5f * (lo.x + hi.x) - smin.x) / ex, cy = (0.5f * (lo.y + hi.y) - smin.y) / ey, cz = (0.5f * (lo.z + hi.z) - smin.z) / ez;
+    const float s = 2097151.0f;
+    const unsigned long long qx = (unsigned long long)fminf(fmaxf(cx * s, 0.f), s);
+    const unsigned long long qy = (unsigned long long)fminf(fmaxf(cy * s, 0.f), s);
+    const unsigned long long qz = (unsigned long long)fminf(fmaxf(cz * s, 0.f), s);
+    codes[i] = spread21(qx) | (spread21(qy) << 1) | (spread21(qz) << 2);
+    ids[i] = (unsigned)i;
+}
+
+// ---- 3. Karras' radix tree.  Node ids: internal i in [0,n-1); leaf j (sorted position) = (n-1)+j.
+__device__ __forceinline__ int delta(const unsigned long long *codes, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const unsigned long long x = codes[i] ^ codes[j];
+    return x == 0ull ? 64 + __clz(i ^ j) : __clzll((long long)x);
+}
+
+__global__ void k_radix_tree(const unsigned long long *codes, int n, int *left, int *right, int *parent, int *first, int *last) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = delta(codes, n, i, i + 1) - delta(codes, n, i, i - 1) >= 0 ? 1 : -1;
+    const int dmin = delta(codes, n, i, i - d);
+    int lmax = 2;
+    while (delta(codes, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(codes, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(codes, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(codes, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int lc = (lo == gamma) ? (n - 1) + gamma : gamma;
+    const int rc = (hi == gamma + 1) ? (n - 1) + gamma + 1 : gamma + 1;
+    left[i] = lc;
+    right[i] = rc;
+    parent[lc] = i;
+    parent[rc] = i;
+    first[i] = lo;
+    last[i] = hi;
+    if (i == 0) parent[0] = -1;
+}
+
+// ---- 4. refit: leaf boxes from the sorted triangles, internal boxes bottom-up
+__global__ void k_refit(const unsigned *ids, const float4 *tlo, const float4 *thi, int n, const int *left, const int *right,
+                        const int *parent, float4 *nlo, float4 *nhi, int *arrivals) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int node = (n - 1) + j;
+    nlo[node] = tlo[ids[j]];
+    nhi[node] = thi[ids[j]];
+    __threadfence();
+    int p = parent[node];
+    while (p >= 0) {
+        if (atomicAdd(&arrivals[p], 1) == 0) return;     // the sibling finishes this node
+        __threadfence();
+        const int l = left[p], r = right[p];
+        const float4 a = __ldcg(nlo + l), b = __ldcg(nlo + r), c = __ldcg(nhi + l), e = __ldcg(nhi + r);
+        nlo[p] = make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z), 0.f);
+        nhi[p] = make_float4(fmaxf(c.x, e.x), fmaxf(c.y, e.y), fmaxf(c.z, e.z), 0.f);
+        __threadfence();
+        p = parent[p];
+    }
+}
+
+// ---- 5. collapse one level of wide nodes
+struct CollapseArgs {
+    const int *left, *right, *first, *last;
+    const float4 *nlo, *nhi;
+    const unsigned *ids;          // sorted position -> input triangle
+    int n;                        // triangles
+    const int2 *queue_in;         // (binary node, wide index)
+    int n_in;
+    int2 *queue_out;
+    int *n_out;
+    int *node_counter;            // next free wide-node index
+    int *tri_counter;             // next free traversal-order triangle slot
+    WideNode *nodes;
+    int *tri_order;               // traversal slot -> input triangle
+    float pad;                    // conservative padding in world units
+    int min_exp;                  // lower bound of the (unbiased) quantisation exponent
+};
+
+__device__ __forceinline__ int sub_count(const CollapseArgs &a, int node) {
+    return node >= a.n - 1 ? 1 : a.last[node] - a.first[node] + 1;
+}
+__device__ __forceinline__ float half_area(const float4 &lo, const float4 &hi) {
+    const float x = hi.x - lo.x, y = hi.y - lo.y, z = hi.z - lo.z;
+    return x * y + y * z + z * x;
+}
+
+__device__ __forceinline__ int quant_exp(float ext, int min_exp) {
+    int e = min_exp;
+    if (ext > 0.f) {
+        int k;
+        frexpf(ext / 255.0f, &k);     // ext/255 = m * 2^k, m in [0.5,1)  =>  2^k >= ext/255
+        e = max(k, min_exp);
+    }
+    return min(max(e, -126), 127);
+}
+
+__global__ void k_collapse(const CollapseArgs a) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.n_in) return;
+    const int bnode = a.queue_in[q].x, widx = a.queue_in[q].y;
+
+    int cand[RSK_WIDE];
+    int nc = 2;
+    cand[0] = a.left[bnode];
+    cand[1] = a.right[bnode];
+    while (nc < RSK_WIDE) {
+        int best = -1;
+        float best_area = -1.f;
+        for (int c = 0; c < nc; ++c) {
+            if (sub_count(a, cand[c]) <= RSK_LEAF_MAX) continue;
+            const float ar = half_area(a.nlo[cand[c]], a.nhi[cand[c]]);
+            if (ar > best_area) { best_area = ar; best = c; }
+        }
+        if (best < 0) break;
+        const int open = cand[best];
+        cand[best] = a.left[open];
+        cand[nc++] = a.right[open];
+    }
+
+    // padded child boxes, node box
+    float3 clo[RSK_WIDE], chi[RSK_WIDE];
+    float3 lo = make_float3(3e38f, 3e38f, 3e38f), hi = make_float3(-3e38f, -3e38f, -3e38f);
+    for (int c = 0; c < nc; ++c) {
+        const float4 l = a.nlo[cand[c]], h = a.nhi[cand[c]];
+        clo[c] = make_float3(l.x - a.pad, l.y - a.pad, l.z - a.pad);
+        chi[c] = make_float3(h.x + a.pad, h.y + a.pad, h.z + a.pad);
+        lo = make_float3(fminf(lo.x, clo[c].x), fminf(lo.y, clo[c].y), fminf(lo.z, clo[c].z));
+        hi = make_float3(fmaxf(hi.x, chi[c].x), fmaxf(hi.y, chi[c].y), fmaxf(hi.z, chi[c].z));
+    }
+    const float3 ctr = make_float3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
+
+    // octant slots: greedy maximum of  (child centre - node centre) . (+-1,+-1,+-1)
+    int slot_of[RSK_WIDE], child_in[RSK_WIDE];
+    for (int s = 0; s < RSK_WIDE; ++s) { slot_of[s] = -1; child_in[s] = -1; }
+    for (int round = 0; round < nc; ++round) {
+        float bestv = -3e38f;
+        int bc = -1, bs = -1;
+        for (int c = 0; c < nc; ++c) {
+            if (slot_of[c] >= 0) continue;
+            const float vx = 0.5f * (clo[c].x + chi[c].x) - ctr.x, vy = 0.5f * (clo[c].y + chi[c].y) - ctr.y, vz = 0.5f * (clo[c].z + chi[c].z) - ctr.z;
+            for (int s = 0; s < RSK_WIDE; ++s) {
+                if (child_in[s] >= 0) continue;
+                const float v = ((s & 1) ? vx : -vx) + ((s & 2) ? vy : -vy) + ((s & 4) ? vz : -vz);
+                if (v > bestv) { bestv = v; bc = c; bs = s; }
+            }
+        }
+        slot_of[bc] = bs;
+        child_in[bs] = bc;
+    }
+
+    int n_inner = 0, n_leaf_tris = 0;
+    for (int s = 0; s < RSK_WIDE; ++s) {
+        if (child_in[s] < 0) continue;
+        const int cnt = sub_count(a, cand[child_in[s]]);
+        if (cnt <= RSK_LEAF_MAX) n_leaf_tris += cnt; else n_inner++;
+    }
+    const int child_base = n_inner ? atomicAdd(a.node_counter, n_inner) : 0;
+    const int tri_base = n_leaf_tris ? atomicAdd(a.tri_counter, n_leaf_tris) : 0;
+    int out_base = n_inner ? atomicAdd(a.n_out, n_inner) : 0;
+
+    WideNode node;
+    node.ox = lo.x; node.oy = lo.y; node.oz = lo.z;
+    const int ex = quant_exp(hi.x - lo.x, a.min_exp), ey = quant_exp(hi.y - lo.y, a.min_exp), ez = quant_exp(hi.z - lo.z, a.min_exp);
+    node.ex = (uint8_t)(ex + 127); node.ey = (uint8_t)(ey + 127); node.ez = (uint8_t)(ez + 127);
+    const float ix = exp2f((float)-ex), iy = exp2f((float)-ey), iz = exp2f((float)-ez);
+    node.imask = 0;
+    node.child_base = (uint32_t)child_base;
+    node.tri_base = (uint32_t)tri_base;
+    int inner_rank = 0, tri_off = 0;
+    for (int s = 0; s < RSK_WIDE; ++s) {
+        const int c = child_in[s];
+        if (c < 0) {
+            node.meta[s] = 0;
+            for (int ax = 0; ax < 3; ++ax) { node.qlo[ax][s] = 255; node.qhi[ax][s] = 0; }
+            continue;
+        }
+        node.qlo[0][s] = (uint8_t)fminf(fmaxf(floorf((clo[c].x - lo.x) * ix), 0.f), 255.f);
+        node.qlo[1][s] = (uint8_t)fminf(fmaxf(floorf((clo[c].y - lo.y) * iy), 0.f), 255.f);
+        node.qlo[2][s] = (uint8_t)fminf(fmaxf(floorf((clo[c].z - lo.z) * iz), 0.f), 255.f);
+        node.qhi[0][s] = (uint8_t)fminf(fmaxf(ceilf((chi[c].x - lo.x) * ix), 0.f), 255.f);
+        node.qhi[1][s] = (uint8_t)fminf(fmaxf(ceilf((chi[c].y - lo.y) * iy), 0.f), 255.f);
+        node.qhi[2][s] = (uint8_t)fminf(fmaxf(ceilf((chi[c].z - lo.z) * iz), 0.f), 255.f);
+        const int bn = cand[c];
+        const int cnt = sub_count(a, bn);
+        if (cnt <= RSK_LEAF_MAX) {
+            const int f = bn >= a.n - 1 ? bn - (a.n - 1) : a.first[bn];
+            for (int t = 0; t < cnt; ++t) a.tri_order[tri_base + tri_off + t] = (int)a.ids[f + t];
+            node.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | (unsigned)tri_off);
+            tri_off += cnt;
+        } else {
+            node.imask |= (uint8_t)(1u << s);
+            node.meta[s] = (uint8_t)(0x20u | (24u + s));
+            a.queue_out[out_base + inner_rank] = make_int2(bn, child_base + inner_rank);
+            inner_rank++;
+        }
+    }
+    a.nodes[widx] = node;
+}
+
+// ---- 6. gather triangle records into traversal order
+__global__ void k_gather(const float4 *tri_in, const float4 *nrm_in, const int *order, int n, float4 *tri_out, float4 *nrm_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t s = order[i];
+    tri_out[3 * (int64_t)i] = tri_in[3 * s];
+    tri_out[3 * (int64_t)i + 1] = tri_in[3 * s + 1];
+    tri_out[3 * (int64_t)i + 2] = tri_in[3 * s + 2];
+    nrm_out[i] = nrm_in[s];
+}
+
+__global__ void k_iota(int *p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+// tiny scenes (<= RSK_LEAF_MAX triangles): a root whose only child is a leaf with every triangle
+__global__ void k_tiny_root(const float4 *tlo, const float4 *thi, int n, WideNode *nodes, float pad, int min_exp) {
+    float3 lo = make_float3(3e38f, 3e38f, 3e38f), hi = make_float3(-3e38f, -3e38f, -3e38f);
+    for (int i = 0; i < n; ++i) {
+        lo = make_float3(fminf(lo.x, tlo[i].x - pad), fminf(lo.y, tlo[i].y - pad), fminf(lo.z, tlo[i].z - pad));
+        hi = make_float3(fmaxf(hi.x, thi[i].x + pad), fmaxf(hi.y, thi[i].y + pad), fmaxf(hi.z, thi[i].z + pad));
+    }
+    WideNode node;
+    memset(&node, 0, sizeof(node));
+    node.ox = lo.x; node.oy = lo.y; node.oz = lo.z;
+    const int e[3] = {quant_exp(hi.x - lo.x, min_exp), quant_exp(hi.y - lo.y, min_exp), quant_exp(hi.z - lo.z, min_exp)};
+    node.ex = (uint8_t)(e[0] + 127); node.ey = (uint8_t)(e[1] + 127); node.ez = (uint8_t)(e[2] + 127);
+    for (int s = 0; s < RSK_WIDE; ++s)
+        for (int ax = 0; ax < 3; ++ax) { node.qlo[ax][s] = 255; node.qhi[ax][s] = 0; }
+    for (int ax = 0; ax < 3; ++ax) { node.qlo[ax][0] = 0; node.qhi[ax][0] = 255; }
+    node.meta[0] = (uint8_t)((((1u << n) - 1u) << 5) | 0u);
+    nodes[0] = node;
+}
+
+}  // namespace
+
+int rsk_bvh_build(rsk_scene *sc, const float4 *tri_in, const float4 *nrm_in) {
+    rsk_ctx *ctx = sc->ctx;
+    cudaStream_t s = ctx->stream;
+    const int n = (int)sc->n_tri;
+    RSK_REQUIRE(n >= 1, "rsk_bvh_build: empty scene");
+    RSK_REQUIRE(sc->n_tri < (1ll << 30), "rsk_bvh_build: too many triangles");
+
+    cudaEvent_t t0, t1;
+    RSK_CUDA(cudaEventCreate(&t0));
+    RSK_CUDA(cudaEventCreate(&t1));
+    RSK_CUDA(cudaEventRecord(t0, s));
+
+    float4 *tlo = nullptr, *thi = nullptr, *nlo = nullptr, *nhi = nullptr;
+    unsigned *bounds = nullptr, *ids = nullptr, *ids_sorted = nullptr;
+    unsigned long long *codes = nullptr, *codes_sorted = nullptr;
+    int *left = nullptr, *right = nullptr, *parent = nullptr, *first = nullptr, *last = nullptr, *arrivals = nullptr;
+    int2 *queue[2] = {nullptr, nullptr};
+    int *counters = nullptr;      // [0] node counter, [1] tri counter, [2] queue out count
+    void *sort_tmp = nullptr;
+    WideNode *nodes = nullptr;
+    int rc = RSK_OK;
+    auto cleanup = [&]() {
+        cudaFree(tlo); cudaFree(thi); cudaFree(nlo); cudaFree(nhi); cudaFree(bounds); cudaFree(ids); cudaFree(ids_sorted);
+        cudaFree(codes); cudaFree(codes_sorted); cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(first); cudaFree(last);
+        cudaFree(arrivals); cudaFree(queue[0]); cudaFree(queue[1]); cudaFree(counters); cudaFree(sort_tmp);
+        cudaEventDestroy(t0); cudaEventDestroy(t1);
+    };
+#define B_TRY(expr) do { rc = (expr); if (rc != RSK_OK) { cleanup(); cudaFree(nodes); return rc; } } while (0)
+#define B_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rsk_set_error("%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); cudaFree(nodes); return RSK_ERR_CUDA; } } while (0)
+
+    B_TRY(rsk_dev_alloc(&tlo, n)); B_TRY(rsk_dev_alloc(&thi, n));
+    B_TRY(rsk_dev_alloc(&bounds, 6));
+    {
+        const unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+        B_CUDA(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    }
+    k_tri_boxes<<<rsk_blocks(n, 256), 256, 0, s>>>(tri_in, n, tlo, thi, bounds);
+    ctx->launches++;
+    unsigned hb[6];
+    B_CUDA(cudaMemcpyAsync(hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost, s));
+    B_CUDA(cudaStreamSynchronize(s));
+    float max_abs = 0.f;
+    for (int c = 0; c < 6; ++c) {
+        unsigned u = hb[c];
+        unsigned bits = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+        float f;
+        memcpy(&f, &bits, 4);
+        max_abs = fmaxf(max_abs, fabsf(f));
+    }
+    if (!(max_abs > 0.f)) max_abs = 1.f;
+    const float pad = max_abs * 4.76837158e-7f;                 // 2^-21 of the largest coordinate: several ulps
+    int me;
+    frexpf(max_abs, &me);
+    const int min_exp = me - 20;                                // grid step never below ~2^-20 of the coordinates
+
+    B_TRY(rsk_dev_alloc(&sc->tri_index, n));
+    const int max_nodes = n > RSK_LEAF_MAX ? n : 1;
+    B_TRY(rsk_dev_alloc(&nodes, max_nodes));
+
+    int depth = 1, n_nodes = 1;
+    if (n <= RSK_LEAF_MAX) {
+        k_tiny_root<<<1, 1, 0, s>>>(tlo, thi, n, nodes, pad, min_exp);
+        k_iota<<<1, 32, 0, s>>>(sc->tri_index, n);
+        ctx->launches += 2;
+    } else {
+        B_TRY(rsk_dev_alloc(&codes, n)); B_TRY(rsk_dev_alloc(&codes_sorted, n));
+        B_TRY(rsk_dev_alloc(&ids, n)); B_TRY(rsk_dev_alloc(&ids_sorted, n));
+        k_morton<<<rsk_blocks(n, 256), 256, 0, s>>>(tlo, thi, n, bounds, codes, ids);
+        ctx->launches++;
+        size_t tmp_bytes = 0;
+        B_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, codes, codes_sorted, ids, ids_sorted, n, 0, 63, s));
+        B_CUDA(cudaMalloc(&sort_tmp, tmp_bytes));
+        B_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, tmp_bytes, codes, codes_sorted, ids, ids_sorted, n, 0, 63, s));
+        ctx->launches += 8;
+
+        B_TRY(rsk_dev_alloc(&left, n - 1)); B_TRY(rsk_dev_alloc(&right, n - 1));
+        B_TRY(rsk_dev_alloc(&first, n - 1)); B_TRY(rsk_dev_alloc(&last, n - 1));
+        B_TRY(rsk_dev_alloc(&parent, 2 * (size_t)n - 1)); B_TRY(rsk_dev_alloc(&arrivals, n - 1));
+        B_TRY(rsk_dev_alloc(&nlo, 2 * (size_t)n - 1)); B_TRY(rsk_dev_alloc(&nhi, 2 * (size_t)n - 1));
+        B_CUDA(cudaMemsetAsync(arrivals, 0, (size_t)(n - 1) * sizeof(int), s));
+        k_radix_tree<<<rsk_blocks(n - 1, 256), 256, 0, s>>>(codes_sorted, n, left, right, parent, first, last);
+        k_refit<<<rsk_blocks(n, 256), 256, 0, s>>>(ids_sorted, tlo, thi, n, left, right, parent, nlo, nhi, arrivals);
+        ctx->launches += 2;
+
+        B_TRY(rsk_dev_alloc(&queue[0], n)); B_TRY(rsk_dev_alloc(&queue[1], n));
+        B_TRY(rsk_dev_alloc(&counters, 4));
+        const int init_counters[4] = {1, 0, 0, 0};
+        B_CUDA(cudaMemcpyAsync(counters, init_counters, sizeof(init_counters), cudaMemcpyHostToDevice, s));
+        const int2 root = make_int2(0, 0);
+        B_CUDA(cudaMemcpyAsync(queue[0], &root, sizeof(root), cudaMemcpyHostToDevice, s));
+        int n_in = 1, cur = 0;
+        depth = 0;
+        while (n_in > 0) {
+            depth++;
+            B_CUDA(cudaMemsetAsync(counters + 2, 0, sizeof(int), s));
+            CollapseArgs a;
+            a.left = left; a.right = right; a.first = first; a.last = last; a.nlo = nlo; a.nhi = nhi; a.ids = ids_sorted; a.n = n;
+            a.queue_in = queue[cur]; a.n_in = n_in; a.queue_out = queue[cur ^ 1]; a.n_out = counters + 2;
+            a.node_counter = counters; a.tri_counter = counters + 1; a.nodes = nodes; a.tri_order = sc->tri_index;
+            a.pad = pad; a.min_exp = min_exp;
+            k_collapse<<<rsk_blocks(n_in, 128), 128, 0, s>>>(a);
+            ctx->launches++;
+            int h[3];
+            B_CUDA(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, s));
+            B_CUDA(cudaStreamSynchronize(s));
+            n_nodes = h[0];
+            n_in = h[2];
+            cur ^= 1;
+            if (depth > 4 * RSK_MAX_DEPTH_HOST) break;
+        }
+        if (depth > RSK_MAX_DEPTH_HOST) {
+            rsk_set_error("rsk_bvh_build: wide tree depth %d exceeds the traversal stack (%d)", depth, RSK_MAX_DEPTH_HOST);
+            cleanup(); cudaFree(nodes);
+            return RSK_ERR_INVALID;
+        }
+    }
+
+    // gather triangles, shrink the node array
+    B_TRY(rsk_dev_alloc(&sc->tri, 3 * (size_t)n));
+    B_TRY(rsk_dev_alloc(&sc->nrm, n));
+    k_gather<<<rsk_blocks(n, 256), 256, 0, s>>>(tri_in, nrm_in, sc->tri_index, n, sc->tri, sc->nrm);
+    ctx->launches++;
+    uint4 *packed = nullptr;
+    B_TRY(rsk_dev_alloc(&packed, (size_t)n_nodes * 5));
+    B_CUDA(cudaMemcpyAsync(packed, nodes, (size_t)n_nodes * sizeof(WideNode), cudaMemcpyDeviceToDevice, s));
+    B_CUDA(cudaEventRecord(t1, s));
+    B_CUDA(cudaStreamSynchronize(s));
+    B_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    sc->nodes = packed;
+    sc->n_nodes = n_nodes;
+    sc->depth = depth;
+    sc->build_us = (int64_t)(ms * 1000.f);
+    cudaFree(nodes);
+    cleanup();
+#undef B_TRY
+#undef B_CUDA
+    return RSK_OK;
+}

@@ -1,0 +1,192 @@
+// rsk_common.cuh -- shared declarations of librsk_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/raystrack_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "librsk_b200 is written for sm_100a (B200) only"
+#endif
+
+// ----------------------------------------------------------------------------- error plumbing
+void rsk_set_error(const char *fmt, ...);
+
+#define RSK_CUDA(call)                                                                            \
+    do {                                                                                          \
+        cudaError_t err__ = (call);                                                               \
+        if (err__ != cudaSuccess) {                                                               \
+            rsk_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                    \
+                          cudaGetErrorString(err__));                                             \
+            return err__ == cudaErrorMemoryAllocation ? RSK_ERR_OOM : RSK_ERR_CUDA;               \
+        }                                                                                         \
+    } while (0)
+
+#define RSK_REQUIRE(cond, msg)                                          \
+    do {                                                                \
+        if (!(cond)) {                                                  \
+            rsk_set_error("%s (%s:%d)", msg, __FILE__, __LINE__);       \
+            return RSK_ERR_INVALID;                                     \
+        }                                                               \
+    } while (0)
+
+#define RSK_TRY(expr)                 \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != RSK_OK) return rc__; \
+    } while (0)
+
+// ----------------------------------------------------------------------------- device-side layouts
+
+constexpr int RSK_TILE_THREADS = 256;      // threads per CTA of the trace kernels
+constexpr int RSK_TILE_RAYS = 4096;        // rays per CTA (one tile = 16 rays per thread)
+constexpr int RSK_TREGENZA_BINS = 145;     // utils/cuda_trace.py:12
+constexpr float RSK_INF = 1.0e20f;         // utils/cpu_trace.py:8
+constexpr int RSK_WIDE = 8;                // fan-out of the wide BVH
+constexpr int RSK_LEAF_MAX = 3;            // triangles per leaf child (24 triangle bits per node)
+constexpr int RSK_MAX_DEPTH_HOST = 32;     // traversal stack entries per ray (wide-tree depth limit)
+
+// One emitter mesh.  Triangle rows live in EmitterSet::tri[5][*] starting at tri_off.
+struct EmitterDesc {
+    int32_t tri_off;
+    int32_t n_tri;
+    int32_t g;
+    int32_t grid_off;        // offset of this g's jitter table in EmitterSet::grid (float2 per cell)
+    int64_t n_rays_once;     // g*g*rays_per_cell
+};
+
+// 80-byte compressed 8-wide BVH node (five 16-byte words, 16-byte aligned).
+struct __align__(16) WideNode {
+    float ox, oy, oz;        // quantisation origin = node box minimum
+    uint8_t ex, ey, ez;      // biased float exponents: cell size = 2^(e-127) per axis
+    uint8_t imask;           // bit s: slot s holds an inner node
+    uint32_t child_base;     // index of the first inner child (inner children contiguous, slot order)
+    uint32_t tri_base;       // index of the first triangle referenced by this node's leaf children
+    uint8_t meta[8];         // inner: 0x20|(24+s); leaf: (unary tri count)<<5 | first tri bit; empty: 0
+    uint8_t qlo[3][8];       // quantised child boxes, [axis][slot]
+    uint8_t qhi[3][8];
+};
+static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
+
+// Scene as the trace kernels see it.
+struct SceneView {
+    const float4 *tri;       // 3 float4 per triangle: (v0, sid bits) (e1, -) (e2, -); traversal order
+    const float4 *nrm;       // (unit normal, -) per triangle, same order
+    const uint4 *nodes;      // WideNode array as 5 x uint4 (null without BVH)
+    int32_t n_tri;
+    int32_t n_surf;
+    int32_t use_bvh;
+    int32_t mask_words;      // ceil(n_surf/32)
+};
+
+struct EmitterView {
+    const EmitterDesc *desc;
+    const float4 *tri;       // 5 float4 per emitter triangle: (a,eps) (e1,n.x) (e2,n.y) (u,n.z) (v,0)
+    const float *cdf;
+    const float2 *grid;      // per-cell jitter (u,v)
+    const float *halton;     // 5 rows of `halton_stride` floats: bases 5,2,3,7,11
+    int64_t halton_stride;
+    int32_t rays_per_cell;
+};
+
+// ----------------------------------------------------------------------------- host objects
+
+struct rsk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    int sm_count = 0;
+    // QMC caches (device)
+    float *halton = nullptr;          // [5][halton_cap]
+    int64_t halton_cap = 0;
+    std::map<int, std::pair<int64_t, int64_t>> grid_index;   // g -> (offset, cells) inside grid
+    float2 *grid = nullptr;
+    int64_t grid_cap = 0, grid_used = 0;
+};
+
+struct rsk_scene {
+    rsk_ctx *ctx = nullptr;
+    int64_t n_tri = 0;
+    int32_t n_surf = 0;
+    int32_t use_bvh = 0;
+    float4 *tri = nullptr;
+    float4 *nrm = nullptr;
+    uint4 *nodes = nullptr;
+    int32_t *tri_index = nullptr;     // traversal slot -> input triangle
+    int64_t n_nodes = 0;
+    int32_t depth = 0;
+    int64_t build_us = 0;
+    SceneView view() const {
+        SceneView v;
+        v.tri = tri; v.nrm = nrm; v.nodes = nodes; v.n_tri = (int32_t)n_tri; v.n_surf = n_surf;
+        v.use_bvh = use_bvh; v.mask_words = (n_surf + 31) / 32;
+        return v;
+    }
+};
+
+struct rsk_emitters {
+    rsk_ctx *ctx = nullptr;
+    int32_t n_emit = 0;
+    int32_t rays_per_cell = 0;
+    int64_t n_tri_total = 0;
+    int64_t max_rays_once = 0;
+    std::vector<EmitterDesc> h_desc;
+    EmitterDesc *desc = nullptr;
+    float4 *tri = nullptr;
+    float *cdf = nullptr;
+    EmitterView view() const {
+        EmitterView v;
+        v.desc = desc; v.tri = tri; v.cdf = cdf; v.grid = ctx->grid; v.halton = ctx->halton;
+        v.halton_stride = ctx->halton_cap; v.rays_per_cell = rays_per_cell;
+        return v;
+    }
+};
+
+// Arguments of the fused trace kernels (rsk_trace.cu).
+struct TraceArgs {
+    SceneView sc;
+    EmitterView ev;
+    const int32_t *emit_ids;        // [n_local]
+    const int64_t *tile_start;      // [n_local+1] exclusive prefix of tiles per job
+    int32_t n_local;
+    const uint32_t *surf_mask;      // [n_local][mask_words], bit set = surface is a receiver/occluder
+    const float *cp_table;          // [n_rot][7]
+    const int32_t *rot_base;        // [n_local]
+    const int32_t *iters_done;      // [n_local] (device state)
+    const int32_t *done;            // [n_local] (device state), may be null
+    unsigned long long *tally;      // [n_local][n_hist]
+    int32_t n_hist;                 // matrix: 2*n_surf; sky: 145 or 1
+    int32_t hist_in_smem;
+    int64_t ray_first, ray_count;   // sub-range of each job's rays (ray_count < 0: all)
+    float *dbg_orig, *dbg_dirs;     // optional per-ray outputs (test hook)
+    int32_t *dbg_hit;
+    uint8_t *dbg_front;
+};
+
+enum { MODE_MATRIX = 0, MODE_SKY = 1 };
+
+// internal entry points shared between translation units
+int rsk_launch_trace(rsk_ctx *ctx, TraceArgs &a, int mode, int64_t n_tiles);
+int rsk_qmc_ensure_halton(rsk_ctx *ctx, int64_t n);
+int rsk_qmc_ensure_grid(rsk_ctx *ctx, int g, int64_t *offset);
+int rsk_bvh_build(rsk_scene *scene, const float4 *tri_in, const float4 *nrm_in);
+
+template <typename T>
+static inline int rsk_dev_alloc(T **ptr, size_t count) {
+    *ptr = nullptr;
+    if (count == 0) count = 1;
+    RSK_CUDA(cudaMalloc((void **)ptr, count * sizeof(T)));
+    return RSK_OK;
+}
+
+static inline unsigned rsk_blocks(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }

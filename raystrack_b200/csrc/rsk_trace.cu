@@ -1,0 +1,237 @@
+// rsk_trace.cu -- fused ray generation + closest-hit / any-hit traversal + tally kernels.
+//
+// One CTA processes one tile of RSK_TILE_RAYS consecutive rays of one (emitter, iteration) job.  Rays are
+// generated in registers (rsk_raygen.cuh), traced against the 8-wide quantised BVH (or, without BVH, against all
+// triangles in input order) and tallied into a per-CTA shared-memory histogram that is flushed with one global
+// atomic per touched bin.  Rays never touch HBM.
+//
+// Replaces, per iteration, the reference's launch sequence kernel_build_rays -> kernel_zero -> kernel_trace_* ->
+// kernel_reduce_hits (main.py:633-671) and kernel_trace_[bvh_]tregenza / _count_upward (main.py:2064-2088).
+#include "rsk_trace.cuh"
+
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int REFILL_BELOW = 20;     // leave the traversal loop to fetch new rays when fewer lanes are busy
+
+
+template <int MODE>
+__device__ __forceinline__ int rsk_result_key(const TraceArgs &a, const Walk &w, bool any_hit) {
+    if (MODE == MODE_MATRIX) {
+        if (w.best_tri < 0) return -1;
+        const float4 n = __ldg(a.sc.nrm + w.best_tri);
+        const int sid = __float_as_int(n.w);
+        const bool front = -(w.dx * n.x + w.dy * n.y + w.dz * n.z) > 0.0f;     // cpu_trace.py:114
+        return front ? sid : a.sc.n_surf + sid;
+    } else {
+        if (any_hit) return -1;
+        if (a.n_hist == 1) return w.dz > 0.0f ? 0 : -1;                       // cpu_trace.py:796
+        return rsk_tregenza_patch(w.dx, w.dy, w.dz);
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void rsk_debug_store(const TraceArgs &a, int64_t k, const Walk &w, int key, bool any_hit) {
+    const int64_t i = k - a.ray_first;
+    if (a.dbg_orig) { a.dbg_orig[3 * i] = w.ox; a.dbg_orig[3 * i + 1] = w.oy; a.dbg_orig[3 * i + 2] = w.oz; }
+    if (a.dbg_dirs) { a.dbg_dirs[3 * i] = w.dx; a.dbg_dirs[3 * i + 1] = w.dy; a.dbg_dirs[3 * i + 2] = w.dz; }
+    if (MODE == MODE_MATRIX) {
+        if (a.dbg_hit) a.dbg_hit[i] = key < 0 ? -1 : (key >= a.sc.n_surf ? key - a.sc.n_surf : key);
+        if (a.dbg_front) a.dbg_front[i] = (key >= 0 && key < a.sc.n_surf) ? 1 : 0;
+    } else {
+        if (a.dbg_hit) a.dbg_hit[i] = any_hit ? 1 : 0;
+        if (a.dbg_front) a.dbg_front[i] = key < 0 ? 255 : (uint8_t)key;
+    }
+}
+
+template <int MODE, bool BVH>
+__global__ void __launch_bounds__(RSK_TILE_THREADS) rsk_trace_kernel(const TraceArgs a) {
+    extern __shared__ uint32_t smem[];
+    __shared__ int s_job;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {           // job lookup: last k with tile_start[k] <= blockIdx.x
+        int lo = 0, hi = a.n_local - 1;
+        const int64_t b = blockIdx.x;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (a.tile_start[mid] <= b) lo = mid; else hi = mid - 1;
+        }
+        s_job = lo;
+    }
+    __syncthreads();
+    const int job = s_job;
+    if (a.done && a.done[job]) return;
+
+    const EmitterDesc e = a.ev.desc[a.emit_ids[job]];
+    const int64_t tile = (int64_t)blockIdx.x - a.tile_start[job];
+    const int64_t range_end = a.ray_count < 0 ? e.n_rays_once : a.ray_first + a.ray_count;
+    const int64_t begin = a.ray_first + tile * RSK_TILE_RAYS;
+    const int64_t end = min(begin + (int64_t)RSK_TILE_RAYS, range_end);
+
+    float cp[7];
+    {
+        const float *row = a.cp_table + 7 * (int64_t)(a.rot_base[job] + a.iters_done[job]);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) cp[i] = __ldg(row + i);
+    }
+
+    uint32_t *s_mask = smem;
+    uint32_t *s_hist = smem + a.sc.mask_words;
+    const int hist_words = a.hist_in_smem ? a.n_hist : 0;
+    uint2 *s_stack = reinterpret_cast<uint2 *>(smem + ((a.sc.mask_words + hist_words + 1) & ~1));
+    for (int i = tid; i < a.sc.mask_words; i += RSK_TILE_THREADS) s_mask[i] = a.surf_mask[(int64_t)job * a.sc.mask_words + i];
+    for (int i = tid; i < hist_words; i += RSK_TILE_THREADS) s_hist[i] = 0;
+    __syncthreads();
+
+    unsigned long long *g_tally = a.tally ? a.tally + (int64_t)job * a.n_hist : nullptr;
+
+    constexpr int WARP_RAYS = RSK_TILE_RAYS / (RSK_TILE_THREADS / 32);
+    int64_t next = begin + (int64_t)warp * WARP_RAYS;
+    const int64_t wend = min(next + WARP_RAYS, end);
+
+    Walk w;
+    bool active = false;
+    int key = -1;             // finished-ray result waiting to be tallied
+    int64_t my_k = 0;
+    uint2 spill[BVH ? RSK_LOCAL_STACK : 1];
+
+    for (;;) {
+        // ---- warp-aggregated tally of the rays finished since the last refill
+        const unsigned has = __ballot_sync(FULL, key >= 0);
+        if (key >= 0) {
+            const unsigned peers = __match_any_sync(has, key);
+            if ((__ffs(peers) - 1) == lane) {
+                if (a.hist_in_smem) atomicAdd(&s_hist[key], (uint32_t)__popc(peers));
+                else if (g_tally) atomicAdd(&g_tally[key], (unsigned long long)__popc(peers));
+            }
+            key = -1;
+        }
+        // ---- refill idle lanes with fresh rays
+        const unsigned need = __ballot_sync(FULL, !active);
+        if (need) {
+            const int64_t idx = next + __popc(need & ((1u << lane) - 1u));
+            if (!active && idx < wend) {
+                my_k = idx;
+                const Ray r = rsk_make_ray(a.ev, e, idx, cp);
+                rsk_walk_begin(w, r);
+                active = true;
+            }
+            next += __popc(need);
+        }
+        if (!__any_sync(FULL, active)) break;
+        const bool rays_left = next < wend;
+
+        if (BVH) {
+            // ---- 8-wide BVH walk
+            while (active) {
+                bool finished = false, any_hit = false;
+                if (w.ng.y <= 0x00ffffffu) {
+                    if (w.sp == 0) finished = true;
+                    else {
+                        --w.sp;
+                        w.ng = w.sp < RSK_SMEM_STACK ? s_stack[w.sp * RSK_TILE_THREADS + tid] : spill[w.sp - RSK_SMEM_STACK];
+                    }
+                }
+                if (!finished) {
+                    const int bit = 31 - __clz(w.ng.y);
+                    w.ng.y &= ~(1u << bit);
+                    const uint32_t imask = w.ng.y & 0xffu;
+                    if (w.ng.y > 0x00ffffffu) {
+                        if (w.sp < RSK_SMEM_STACK) s_stack[w.sp * RSK_TILE_THREADS + tid] = w.ng;
+                        else if (w.sp < RSK_MAX_DEPTH) spill[w.sp - RSK_SMEM_STACK] = w.ng;
+                        if (w.sp < RSK_MAX_DEPTH) ++w.sp;
+                    }
+                    const uint32_t slot = (uint32_t)(bit - 24) ^ w.octinv;
+                    const uint32_t rel = __popc(imask & ((1u << slot) - 1u));
+                    uint2 ng2, tg;
+                    rsk_test_node(a.sc.nodes, w.ng.x + rel, w, MODE == MODE_MATRIX ? w.best : RSK_INF, ng2, tg);
+                    while (tg.y) {
+                        const int b = __ffs(tg.y) - 1;
+                        tg.y &= tg.y - 1u;
+                        const int tri = (int)(tg.x + b);
+                        const float4 *tp = a.sc.tri + 3 * (int64_t)tri;
+                        const float4 V0 = __ldg(tp), E1 = __ldg(tp + 1), E2 = __ldg(tp + 2);
+                        if (!rsk_surface_on(s_mask, __float_as_int(V0.w))) continue;
+                        float t;
+                        if (!rsk_tri_hit(V0, E1, E2, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, t)) continue;
+                        if (MODE == MODE_MATRIX) {
+                            if (t > 1e-6f && t < w.best) { w.best = t; w.best_tri = tri; }
+                        } else if (t > 1e-6f) {
+                            any_hit = true;
+                            break;
+                        }
+                    }
+                    w.ng = ng2;
+                    if (any_hit) finished = true;
+                }
+                if (finished) {
+                    key = rsk_result_key<MODE>(a, w, any_hit);
+                    if (a.dbg_hit || a.dbg_orig || a.dbg_dirs || a.dbg_front) rsk_debug_store<MODE>(a, my_k, w, key, any_hit);
+                    active = false;
+                    break;
+                }
+                if (rays_left && __popc(__activemask()) < REFILL_BELOW) break;
+            }
+        } else {
+            // ---- no BVH: every triangle in input order, strict t<best (utils/cpu_trace.py:54-117, 540-583)
+            if (active) {
+                bool any_hit = false;
+                for (int tri = 0; tri < a.sc.n_tri; ++tri) {
+                    const float4 *tp = a.sc.tri + 3 * (int64_t)tri;
+                    const float4 V0 = __ldg(tp);
+                    if (!rsk_surface_on(s_mask, __float_as_int(V0.w))) continue;
+                    const float4 E1 = __ldg(tp + 1), E2 = __ldg(tp + 2);
+                    float t;
+                    if (!rsk_tri_hit(V0, E1, E2, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, t)) continue;
+                    if (MODE == MODE_MATRIX) {
+                        if (t > 1e-6f && t < w.best) { w.best = t; w.best_tri = tri; }
+                    } else if (t > 1e-6f) {
+                        any_hit = true;
+                        break;
+                    }
+                }
+                key = rsk_result_key<MODE>(a, w, any_hit);
+                if (a.dbg_hit || a.dbg_orig || a.dbg_dirs || a.dbg_front) rsk_debug_store<MODE>(a, my_k, w, key, any_hit);
+                active = false;
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- flush the CTA histogram: one global atomic per touched bin
+    if (a.hist_in_smem && g_tally) {
+        __syncthreads();
+        for (int i = tid; i < a.n_hist; i += RSK_TILE_THREADS) {
+            const uint32_t v = s_hist[i];
+            if (v) atomicAdd(&g_tally[i], (unsigned long long)v);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- host launcher
+
+static size_t rsk_trace_smem(const TraceArgs &a, bool bvh) {
+    size_t words = ((size_t)a.sc.mask_words + (a.hist_in_smem ? a.n_hist : 0) + 1) & ~(size_t)1;
+    return words * 4 + (bvh ? (size_t)RSK_SMEM_STACK * RSK_TILE_THREADS * sizeof(uint2) : 0);
+}
+
+template <int MODE, bool BVH>
+static int rsk_launch_one(rsk_ctx *ctx, const TraceArgs &a, int64_t n_tiles) {
+    const size_t smem = rsk_trace_smem(a, BVH);
+    if (smem > 48 * 1024)
+        RSK_CUDA(cudaFuncSetAttribute(rsk_trace_kernel<MODE, BVH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rsk_trace_kernel<MODE, BVH><<<(unsigned)n_tiles, RSK_TILE_THREADS, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    RSK_CUDA(cudaGetLastError());
+    return RSK_OK;
+}
+
+int rsk_launch_trace(rsk_ctx *ctx, TraceArgs &a, int mode, int64_t n_tiles) {
+    if (n_tiles <= 0) return RSK_OK;
+    RSK_REQUIRE(n_tiles < ((int64_t)1 << 31), "too many ray tiles in one launch");
+    // shared-memory histogram when it leaves room for >= 2 CTAs per SM, else warp-aggregated global atomics
+    a.hist_in_smem = ((size_t)a.n_hist * 4 <= 96 * 1024) ? 1 : 0;
+    const bool bvh = a.sc.use_bvh != 0;
+    if (mode == MODE_MATRIX) return bvh ? rsk_launch_one<MODE_MATRIX, true>(ctx, a, n_tiles) : rsk_launch_one<MODE_MATRIX, false>(ctx, a, n_tiles);
+    return bvh ? rsk_launch_one<MODE_SKY, true>(ctx, a, n_tiles) : rsk_launch_one<MODE_SKY, false>(ctx, a, n_tiles);
+}

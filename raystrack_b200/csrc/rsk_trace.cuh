@@ -1,0 +1,133 @@
+// rsk_trace.cuh -- ray/triangle and ray/wide-node device code shared by the trace kernels.
+#pragma once
+#include "rsk_common.cuh"
+#include "rsk_raygen.cuh"
+
+constexpr int RSK_SMEM_STACK = 8;      // stack entries per thread kept in shared memory
+constexpr int RSK_LOCAL_STACK = 24;    // spill entries per thread (local memory)
+constexpr int RSK_MAX_DEPTH = RSK_SMEM_STACK + RSK_LOCAL_STACK;
+static_assert(RSK_MAX_DEPTH == RSK_MAX_DEPTH_HOST, "stack size mismatch");
+
+// Moeller-Trumbore as the reference writes it (utils/cpu_trace.py:88-110): reject |det| < 1e-7, u in [0,1],
+// v >= 0, u+v <= 1; the caller applies the t window.  float32 throughout (the reference promotes
+// inv_det,u,v,t to float64; measured per-ray disagreement of the float32 form is ~3e-7).
+__device__ __forceinline__ bool rsk_tri_hit(const float4 &V0, const float4 &E1, const float4 &E2,
+                                            float ox, float oy, float oz, float dx, float dy, float dz, float &t) {
+    const float px = dy * E2.z - dz * E2.y;
+    const float py = dz * E2.x - dx * E2.z;
+    const float pz = dx * E2.y - dy * E2.x;
+    const float det = E1.x * px + E1.y * py + E1.z * pz;
+    if (fabsf(det) < 1e-7f) return false;
+    const float inv_det = 1.0f / det;
+    const float tx = ox - V0.x, ty = oy - V0.y, tz = oz - V0.z;
+    const float u = (tx * px + ty * py + tz * pz) * inv_det;
+    if (u < 0.0f || u > 1.0f) return false;
+    const float qx = ty * E1.z - tz * E1.y;
+    const float qy = tz * E1.x - tx * E1.z;
+    const float qz = tx * E1.y - ty * E1.x;
+    const float v = (dx * qx + dy * qy + dz * qz) * inv_det;
+    if (v < 0.0f || u + v > 1.0f) return false;
+    t = (E2.x * qx + E2.y * qy + E2.z * qz) * inv_det;
+    return true;
+}
+
+__device__ __forceinline__ bool rsk_surface_on(const uint32_t *mask, int sid) {
+    return (mask[sid >> 5] >> (sid & 31)) & 1u;
+}
+
+// Per-ray traversal state of the 8-wide BVH walk.
+struct Walk {
+    float ox, oy, oz, dx, dy, dz;
+    float ix, iy, iz;        // 1/d (clamped)
+    float best;              // closest accepted t so far (RSK_INF = none)
+    int best_tri;            // slot of the closest triangle, -1 = none
+    uint2 ng;                // current node group: x = first inner child, y = hit bits<<24 | imask
+    int sp;
+    uint32_t octinv;         // bit a set: direction component a >= 0
+};
+
+__device__ __forceinline__ float rsk_safe_inv(float d) {
+    const float lim = 1e-20f;
+    return 1.0f / (fabsf(d) > lim ? d : copysignf(lim, d));
+}
+
+__device__ __forceinline__ void rsk_walk_begin(Walk &w, const Ray &r) {
+    w.ox = r.ox; w.oy = r.oy; w.oz = r.oz; w.dx = r.dx; w.dy = r.dy; w.dz = r.dz;
+    w.ix = rsk_safe_inv(r.dx); w.iy = rsk_safe_inv(r.dy); w.iz = rsk_safe_inv(r.dz);
+    w.best = RSK_INF; w.best_tri = -1;
+    w.octinv = (r.dx >= 0.0f ? 1u : 0u) | (r.dy >= 0.0f ? 2u : 0u) | (r.dz >= 0.0f ? 4u : 0u);
+    w.ng = make_uint2(0u, 0x80000000u);     // pseudo group whose only child is the root
+    w.sp = 0;
+}
+
+__device__ __forceinline__ float rsk_byte(uint32_t word, int j) { return (float)((word >> (8 * j)) & 0xffu); }
+
+// Slab test of the 8 quantised child boxes of node `idx` against the ray over [0, tmax].
+// Returns the new node group (inner children hit, priority-permuted) and the 24-bit triangle mask.
+__device__ __forceinline__ void rsk_test_node(const uint4 *__restrict__ nodes, uint32_t idx, const Walk &w, float tmax,
+                                              uint2 &ng, uint2 &tg) {
+    const uint4 *p = nodes + 5 * (size_t)idx;
+    const uint4 n0 = __ldg(p), n1 = __ldg(p + 1), n2 = __ldg(p + 2), n3 = __ldg(p + 3), n4 = __ldg(p + 4);
+    const uint32_t imask = n0.w >> 24;
+    const float adx = __uint_as_float((n0.w & 0xffu) << 23) * w.ix;
+    const float ady = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * w.iy;
+    const float adz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * w.iz;
+    const float bx = (__uint_as_float(n0.x) - w.ox) * w.ix;
+    const float by = (__uint_as_float(n0.y) - w.oy) * w.iy;
+    const float bz = (__uint_as_float(n0.z) - w.oz) * w.iz;
+    // byte planes: n2 = qlo.x[0..7] qlo.y[0..7]; n3 = qlo.z[0..7] qhi.x[0..7]; n4 = qhi.y[0..7] qhi.z[0..7]
+    const bool px = w.octinv & 1u, py = w.octinv & 2u, pz = w.octinv & 4u;
+    uint32_t hits = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t meta = half ? n1.w : n1.z;
+        const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
+        const uint32_t hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
+        const uint32_t nxw = px ? lox : hix, fxw = px ? hix : lox;
+        const uint32_t nyw = py ? loy : hiy, fyw = py ? hiy : loy;
+        const uint32_t nzw = pz ? loz : hiz, fzw = pz ? hiz : loz;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t m = (meta >> (8 * j)) & 0xffu;
+            const float tnx = fmaf(rsk_byte(nxw, j), adx, bx), tfx = fmaf(rsk_byte(fxw, j), adx, bx);
+            const float tny = fmaf(rsk_byte(nyw, j), ady, by), tfy = fmaf(rsk_byte(fyw, j), ady, by);
+            const float tnz = fmaf(rsk_byte(nzw, j), adz, bz), tfz = fmaf(rsk_byte(fzw, j), adz, bz);
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+            if (m != 0u && tn <= tf) {
+                uint32_t shift = m & 31u;
+                if (shift >= 24u) shift ^= w.octinv;     // inner child: priority = slot ^ octinv
+                hits |= (m >> 5) << shift;
+            }
+        }
+    }
+    ng = make_uint2(n1.x, (hits & 0xff000000u) | imask);
+    tg = make_uint2(n1.y, hits & 0x00ffffffu);
+}
+
+// Tregenza patch of an upward direction (utils/cpu_trace.py:735-777, float32 arguments).  atan2 is evaluated
+// in float64 and rounded, which reproduces a correctly-rounded float32 atan2f; degrees() is a float32 multiply.
+__device__ __forceinline__ int rsk_tregenza_patch(float dx, float dy, float dz) {
+    if ((double)dz <= 0.0) return -1;
+    const double ring_hi[8] = {0.20791169081775934, 0.40673664307580015, 0.5877852522924731, 0.7431448254773942,
+                               0.8660254037844386,  0.9510565162951535,  0.9945218953682733, 1.0};
+    const int ring_n[8] = {30, 30, 24, 24, 18, 12, 6, 1};
+    const int ring_start[8] = {0, 30, 60, 84, 108, 126, 138, 144};
+    int ridx = 7;
+#pragma unroll
+    for (int j = 6; j >= 0; --j)
+        if ((double)dz < ring_hi[j]) ridx = j;
+    const int n_az = ring_n[ridx], base = ring_start[ridx];
+    if (n_az == 1) return base;
+    const float at = (float)atan2((double)dy, (double)dx);
+    double az = (double)__fmul_rn(at, 57.29577951308232f);
+    if (az < 0.0) az = __dadd_rn(az, 360.0);
+    const double width = __ddiv_rn(360.0, (double)n_az);
+    const double off = (ridx & 1) ? __ddiv_rn(180.0, (double)n_az) : 0.0;
+    double t = __dsub_rn(az, off);
+    if (t < 0.0) t = __dadd_rn(t, 360.0);
+    else if (t >= 360.0) t = __dsub_rn(t, 360.0);
+    int aidx = (int)floor(__ddiv_rn(t, width));
+    if (aidx >= n_az) aidx = n_az - 1;
+    return base + aidx;
+}

@@ -1,0 +1,65 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink on the B200 box, gloo in the
+CPU tests).  The path shards by emitter (matrix rows are independent, reference main.py:1758-1939): the BVH and
+triangles are replicated, each rank solves its emitters without any data-path collective, and the integer tally
+blocks are summed once at the end -- integer sums make the result independent of the GPU count."""
+from __future__ import annotations
+
+import os
+from typing import List, Sequence
+
+import numpy as np
+
+
+def init_from_env(backend: str | None = None) -> tuple[int, int]:
+    """Join the process group described by RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT (torchrun)."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    if not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group(backend=backend)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def allreduce_sum_(arrays: Sequence[np.ndarray], device: int = 0) -> None:
+    """In-place SUM all-reduce of int64 NumPy arrays over the default group (one flat NCCL all-reduce)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() <= 1:
+        return
+    flat = np.concatenate([np.ascontiguousarray(a, np.int64).reshape(-1) for a in arrays])
+    t = torch.from_numpy(flat)
+    if dist.get_backend() == "nccl":
+        t = t.cuda(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    out = t.cpu().numpy()
+    pos = 0
+    for a in arrays:
+        n = a.size
+        a[...] = out[pos:pos + n].reshape(a.shape)
+        pos += n
+
+
+def barrier() -> None:
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(value: float, device: int = 0) -> float:
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() <= 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64)
+    if dist.get_backend() == "nccl":
+        t = t.cuda(device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -1,0 +1,318 @@
+"""Host orchestrator of the view-factor solves -- the drop-in for the reference's ``raystrack.main``.
+
+Public functions keep the reference's names, arguments, return shapes, errors and log format
+(reference src/raystrack/main.py:1689-2185).  What changed underneath: instead of a Python loop that launches
+six Numba kernels per (emitter, iteration) and synchronises after each iteration, the solve is handed to
+librsk_b200 as ONE device-resident job set: every iteration of every unconverged emitter is a tile range of a
+single fused raygen+trace+tally kernel, followed by an on-device statistics/convergence kernel; the host only
+reads "how many emitters are still running".
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native
+from .params import MatrixParams, SkyParams
+from .prepared import PreparedEmitter, PreparedSolver
+
+Mesh = Tuple[str, np.ndarray, np.ndarray]
+_BVH_AUTO_THRESHOLD = 512      # reference main.py:48
+
+
+def _log(msg: str) -> None:
+    """Progress line sink.  A module attribute on purpose: the reference's validation harness and examples
+    replace ``raystrack.main._log`` to capture iteration counts (validation/common_validation.py:139-141)."""
+    print(msg)
+
+
+def _select_bvh(bvh: Optional[str], total_faces: int) -> bool:
+    """reference main.py:125-133."""
+    mode = (bvh or "auto").lower()
+    if mode not in ("auto", "off", "builtin"):
+        raise ValueError(f"bvh must be 'auto', 'off', or 'builtin' (got {bvh!r})")
+    if mode == "builtin":
+        return True
+    if mode == "off":
+        return False
+    return total_faces >= _BVH_AUTO_THRESHOLD
+
+
+def _resolve_device(device: Optional[str]) -> str:
+    """reference main.py:136-147.  Every value runs on the GPU (this package has no CPU path); the returned
+    label only selects the convergence schedule: "cpu" checks after every iteration like the reference's CPU
+    loop (main.py:1889), "gpu" honours ``convergence_interval``."""
+    dev = (device or "auto").lower()
+    if dev not in ("auto", "gpu", "cpu"):
+        raise ValueError(f"device must be 'auto', 'gpu', or 'cpu' (got {device!r})")
+    if _native.device_count() <= 0:
+        if dev == "gpu":
+            raise RuntimeError("device='gpu' requested but CUDA is not available")
+        raise RuntimeError("CUDA is not available: raystrack_b200 runs on a B200 only and has no CPU path")
+    return "cpu" if dev == "cpu" else "gpu"
+
+
+def _ensure_prepared(meshes: List[Mesh], prepared: Optional[PreparedSolver]) -> PreparedSolver:
+    if prepared is None:
+        return PreparedSolver(meshes)
+    if not isinstance(prepared, PreparedSolver):
+        raise TypeError("prepared must be a PreparedSolver instance")
+    return prepared
+
+
+def _surface_masks(emitters: Sequence[PreparedEmitter], centers: np.ndarray, extents: np.ndarray) -> np.ndarray:
+    """``surf_active`` for every emitter at once, uint8 [n_emit, n_surf] (reference main.py:167-204): the emitter's
+    own mesh is off; for a planar emitter every mesh whose bounding box lies wholly behind its plane is off."""
+    n = centers.shape[0]
+    active = np.ones((len(emitters), n), np.uint8)
+    for i, em in enumerate(emitters):
+        if i < n:
+            active[i, i] = 0
+        if not em.plane_is_planar:
+            continue
+        po, pn = em.plane_origin, em.plane_normal
+        an = np.abs(pn)
+        d = centers - po
+        signed = d[:, 0] * pn[0] + d[:, 1] * pn[1] + d[:, 2] * pn[2]
+        radius = an[0] * extents[:, 0] + an[1] * extents[:, 1] + an[2] * extents[:, 2]
+        behind = (signed + radius) <= float(em.plane_tol)
+        if i < n:
+            behind[i] = False
+        active[i, behind] = 0
+    return active
+
+
+def _rotation_table(seed: int, n_emit: int, max_iters: int) -> np.ndarray:
+    """Cranley-Patterson offsets.  The reference draws ``default_rng(seed + idx_emit + itr)`` per emitter and
+    iteration (main.py:1810-1812); only the sum matters, so one row per distinct sum: row s = rotation of
+    ``seed + s``; emitter i, iteration it uses row i + it."""
+    rows = max(0, n_emit + max(int(max_iters), 0))
+    table = np.empty((max(rows, 1), 7), np.float32)
+    for s in range(rows):
+        rng = np.random.default_rng(seed + s)
+        table[s, :2] = rng.random(2, dtype=np.float32)
+        table[s, 2:] = rng.random(5, dtype=np.float32)
+    return table
+
+
+def _shard(indices: List[int], weights: Sequence[float], rank: int, world: int) -> List[int]:
+    """Longest-processing-time-first assignment of emitters to ranks; returns this rank's emitters (sorted)."""
+    if world <= 1:
+        return list(indices)
+    order = sorted(indices, key=lambda i: -weights[i])
+    loads = [0.0] * world
+    mine: List[int] = []
+    for i in order:
+        r = min(range(world), key=lambda q: (loads[q], q))
+        loads[r] += weights[i]
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)
+
+
+def _run_solve(solve: _native.Solve, min_iters: int, max_iters: int) -> None:
+    """Drive a device solve to completion: first the iterations no stopping rule can interrupt, then small
+    batches (the device skips converged emitters on its own, so over-enqueueing is harmless)."""
+    if max_iters <= 0 or solve.n_local == 0:
+        return
+    first = max(1, min(int(max_iters), max(int(min_iters), 1)))
+    active = solve.step(first)
+    done = first
+    while active > 0 and done < max_iters:
+        chunk = min(4, max_iters - done)
+        active = solve.step(chunk)
+        done += chunk
+
+
+def _dist_env() -> Tuple[int, int]:
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Optional[PreparedSolver] = None):
+    """View factors between all meshes (reference main.py:1689-1945).
+
+    Returns ``{emitter: {"<receiver>_front" | "<receiver>_back": F}}`` with only positive entries; with
+    ``reciprocity=True`` receivers ``j > i`` are traced and ``F_ji = F_ij * A_i / A_j`` is filled in for front hits.
+    Inside an initialised ``torch.distributed`` group the emitters are sharded over the ranks and the integer
+    tallies all-reduced, every rank returns the full result."""
+    if not isinstance(params, MatrixParams):
+        raise TypeError("params must be a MatrixParams instance")
+    p = params.as_dict()
+    samples, rays, seed = p["samples"], p["rays"], p["seed"]
+    max_iters, tol, tol_mode, min_iters = p["max_iters"], p["tol"], p["tol_mode"], p["min_iters"]
+    interval = max(1, int(p["convergence_interval"]))
+    reciprocity, flip_faces = p["reciprocity"], p["flip_faces"]
+
+    schedule = _resolve_device(p["device"])
+    solver = _ensure_prepared(meshes, prepared)
+    use_bvh = _select_bvh(p["bvh"], solver.total_faces)
+    if tol_mode not in ("stderr", "delta"):
+        raise ValueError(f"Unknown tol_mode: {tol_mode}")
+    n_surf = len(meshes)
+    result: Dict[str, Dict[str, float]] = {name: {} for name, _, _ in meshes}
+    emitters = solver.get_emitters(samples=samples, rays=rays, flip_faces=flip_faces)
+    areas = [em.total_area for em in emitters] if reciprocity else None
+    centers, extents = solver.get_mesh_bounds()
+    ctx = _native.Context.for_device()
+    d_scene = solver.get_device_scene(use_bvh=use_bvh, ctx=ctx)
+    d_em = solver.get_device_emitters(samples=samples, rays=rays, flip_faces=flip_faces, ctx=ctx)
+
+    t0 = time.time()
+    active = _surface_masks(emitters, centers, extents)
+    # receivers of emitter i (main.py:161-164, 207-214): active meshes j > i (reciprocity) or j != i
+    emit_sid = np.arange(n_surf, dtype=np.int32)
+    min_sid = (emit_sid + 1) if reciprocity else np.zeros(n_surf, np.int32)
+    recv_mask = active.astype(bool)
+    col = np.arange(n_surf)[None, :]
+    recv_mask &= (col >= min_sid[:, None]) & (col != emit_sid[:, None])
+    has_recv = recv_mask.any(axis=1)
+    todo = [i for i in range(n_surf) if has_recv[i]]
+
+    rank, world = _dist_env()
+    weights = [float(em.n_cells * rays) for em in emitters]
+    mine = _shard(todo, weights, rank, world)
+    table = _rotation_table(seed, n_surf, max_iters)
+    ids = np.asarray(mine, np.int32)
+    solve = _native.Solve(ctx, d_scene.native, d_em.native, ids, active[ids] if len(mine) else np.zeros((0, n_surf), np.uint8),
+                          table, ids.copy(), max_iters=max_iters, min_iters=min_iters,
+                          interval=interval if schedule == "gpu" else 1, tol_mode=tol_mode, tol=tol,
+                          emit_sid=emit_sid[ids], min_sid=min_sid[ids])
+    try:
+        _run_solve(solve, min_iters, max_iters)
+        hf_loc, hb_loc, it_loc, tot_loc, _, _ = solve.read_matrix()
+    finally:
+        solve.close()
+
+    hits_f = np.zeros((n_surf, n_surf), np.int64)
+    hits_b = np.zeros((n_surf, n_surf), np.int64)
+    iters = np.zeros(n_surf, np.int64)
+    totals = np.zeros(n_surf, np.int64)
+    if len(mine):
+        hits_f[ids] = hf_loc
+        hits_b[ids] = hb_loc
+        iters[ids] = it_loc
+        totals[ids] = tot_loc
+    if world > 1:
+        from .dist import allreduce_sum_
+        allreduce_sum_([hits_f, hits_b, iters, totals], device=ctx.device)
+    elapsed = time.time() - t0
+
+    label = "builtin" if use_bvh else "off"
+    for i, (name_e, _, _) in enumerate(meshes):
+        if not has_recv[i]:
+            _log(f"({i+1}/{n_surf}) [{name_e}] 0 iter, 0 rays -> 0.000s  (BVH={label}, device=gpu)")
+            continue
+        total = float(totals[i])
+        row: Dict[str, float] = {}
+        with np.errstate(divide="ignore", invalid="ignore"):
+            f_row = hits_f[i] / total                                                  # main.py:1922-1923
+            b_row = hits_b[i] / total
+        for j in np.nonzero(recv_mask[i] & ((f_row > 0.0) | (b_row > 0.0)))[0]:
+            name_r = meshes[j][0]
+            f, b = f_row[j], b_row[j]
+            if f > 0.0:
+                row[f"{name_r}_front"] = f
+                if reciprocity and areas is not None and areas[j] > 0.0:
+                    result[name_r][f"{name_e}_front"] = f * (areas[i] / areas[j])      # main.py:1926-1927
+            if b > 0.0:
+                row[f"{name_r}_back"] = b
+        result[name_e].update(row)
+        share = elapsed * (weights[i] * max(int(iters[i]), 1)) / max(1.0, float(np.dot(weights, np.maximum(iters, 1))))
+        _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {share:0.3f}s  "
+             f"(BVH={label}, device=gpu)")
+
+    if p["enforce_reciprocity_rowsum"]:
+        from .reciprocity import enforce_reciprocity_and_rowsum
+        enforce_reciprocity_and_rowsum(result, meshes, areas, ctx=ctx)
+    return result
+
+
+def view_factor(sender, receiver, params: MatrixParams, *, prepared: Optional[PreparedSolver] = None):
+    """Rows of the sender meshes only (reference main.py:1948-1954)."""
+    senders = [sender] if isinstance(sender, tuple) else list(sender)
+    receivers = [receiver] if isinstance(receiver, tuple) else list(receiver)
+    vf_all = view_factor_matrix(senders + receivers, params=params, prepared=prepared)
+    return {s[0]: vf_all.get(s[0], {}) for s in senders}
+
+
+def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepared: Optional[PreparedSolver] = None):
+    """Sky view factors per mesh (reference main.py:1957-2185): rays that hit no other active mesh and point
+    upward are binned into the 145 Tregenza patches (``discrete=True``) or counted as one "Sky" entry."""
+    if not isinstance(params, SkyParams):
+        raise TypeError("params must be a SkyParams instance")
+    if len(meshes) == 0:
+        raise ValueError("meshes must not be empty")
+    p = params.as_dict()
+    samples, rays, seed = p["samples"], p["rays"], p["seed"]
+    max_iters, tol, tol_mode, min_iters = p["max_iters"], p["tol"], p["tol_mode"], p["min_iters"]
+    interval = max(1, int(p["convergence_interval"]))
+    discrete = bool(p["discrete"])
+
+    schedule = _resolve_device(p["device"])
+    solver = _ensure_prepared(meshes, prepared)
+    use_bvh = _select_bvh(p["bvh"], solver.total_faces)
+    if tol_mode not in ("stderr", "delta"):
+        raise ValueError(f"Unknown tol_mode: {tol_mode}")
+    emitters = solver.get_emitters(samples=samples, rays=rays, flip_faces=False)       # main.py:1985
+    centers, extents = solver.get_mesh_bounds()
+    keys = [f"Sky_Patch_{i}" for i in range(1, 146)] if discrete else ["Sky"]
+    result: Dict[str, Dict[str, float]] = {name: {k: 0.0 for k in keys} for name, _, _ in meshes}
+    n_surf = len(meshes)
+    if n_surf <= 1:                                                                    # main.py:1998-1999
+        return result
+
+    ctx = _native.Context.for_device()
+    d_scene = solver.get_device_scene(use_bvh=use_bvh, ctx=ctx)
+    d_em = solver.get_device_emitters(samples=samples, rays=rays, flip_faces=False, ctx=ctx)
+    t0 = time.time()
+    active = _surface_masks(emitters, centers, extents)
+    rank, world = _dist_env()
+    weights = [float(em.n_cells * rays) for em in emitters]
+    mine = _shard(list(range(n_surf)), weights, rank, world)
+    ids = np.asarray(mine, np.int32)
+    table = _rotation_table(seed, n_surf, max_iters)
+    solve = _native.Solve(ctx, d_scene.native, d_em.native, ids, active[ids] if len(mine) else np.zeros((0, n_surf), np.uint8),
+                          table, ids.copy(), max_iters=max_iters, min_iters=min_iters,
+                          interval=interval if schedule == "gpu" else 1, tol_mode=tol_mode, tol=tol,
+                          sky=True, discrete=discrete)
+    try:
+        _run_solve(solve, min_iters, max_iters)
+        c_loc, it_loc, tot_loc = solve.read_sky()
+    finally:
+        solve.close()
+    nb = 145 if discrete else 1
+    counts = np.zeros((n_surf, nb), np.int64)
+    iters = np.zeros(n_surf, np.int64)
+    totals = np.zeros(n_surf, np.int64)
+    if len(mine):
+        counts[ids] = c_loc
+        iters[ids] = it_loc
+        totals[ids] = tot_loc
+    if world > 1:
+        from .dist import allreduce_sum_
+        allreduce_sum_([counts, iters, totals], device=ctx.device)
+    elapsed = time.time() - t0
+
+    label = "builtin" if use_bvh else "off"
+    for i, (name_e, _, _) in enumerate(meshes):
+        denom = float(max(1, int(totals[i])))
+        if discrete:
+            frac = counts[i].astype(np.float64) / denom
+            result[name_e].update({f"Sky_Patch_{k+1}": float(frac[k]) for k in range(145)})
+        else:
+            result[name_e]["Sky"] = float(int(counts[i, 0]) / denom)
+        share = elapsed * (weights[i] * max(int(iters[i]), 1)) / max(1.0, float(np.dot(weights, np.maximum(iters, 1))))
+        _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {share:0.3f}s  "
+             f"(BVH={label}, device=gpu)")
+    return result
+
+
+__all__ = ["view_factor_matrix", "view_factor", "view_factor_to_tregenza_sky"]
