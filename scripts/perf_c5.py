@@ -1,0 +1,53 @@
+"""Quick throughput probe on the synthetic urban scene (not the bench contract; see bench.py)."""
+import argparse
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from raystrack_b200 import _native, synthetic                      # noqa: E402
+from raystrack_b200.main import _rotation_table, _surface_masks    # noqa: E402
+from raystrack_b200.prepared import PreparedSolver                 # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--side", type=int, default=20)
+ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--samples", type=int, default=4)
+ap.add_argument("--rays", type=int, default=64)
+ap.add_argument("--sky", action="store_true")
+args = ap.parse_args()
+
+t = time.time()
+meshes = synthetic.urban_block(args.side)
+ps = PreparedSolver(meshes)
+print(f"meshes {len(meshes)} tris {ps.total_faces} gen {time.time()-t:.2f}s", flush=True)
+t = time.time()
+ems = ps.get_emitters(samples=args.samples, rays=args.rays, flip_faces=False)
+hs = ps.get_scene(use_bvh=True)
+print(f"host prep {time.time()-t:.2f}s", flush=True)
+ctx = _native.Context.for_device(0)
+t = time.time()
+sc = ps.get_device_scene(use_bvh=True, ctx=ctx).native
+print(f"scene upload+BVH {time.time()-t:.2f}s info {sc.info()}", flush=True)
+t = time.time()
+em = ps.get_device_emitters(samples=args.samples, rays=args.rays, flip_faces=False, ctx=ctx).native
+print(f"emitters+tables {time.time()-t:.2f}s", flush=True)
+n = len(meshes)
+centers, extents = ps.get_mesh_bounds()
+active = _surface_masks(ems, centers, extents)
+ids = np.arange(n, dtype=np.int32)
+table = _rotation_table(1, n, args.iters + 2)
+solve = _native.Solve(ctx, sc, em, ids, active, table, ids.copy(), max_iters=args.iters + 2, min_iters=args.iters + 2, interval=1,
+                      tol_mode="stderr", tol=0.0, emit_sid=ids, min_sid=np.zeros(n, np.int32), sky=args.sky, discrete=True)
+solve.step(1)
+r0 = solve.rays_traced()
+ctx.timer_start()
+solve.step(args.iters)
+ms = ctx.timer_stop()
+rays = solve.rays_traced() - r0
+print(f"{rays} rays in {ms:.1f} ms -> {rays/ms/1e6:.4f} Grays/s", flush=True)
+if not args.sky:
+    hf, hb, it, tot, _, _ = solve.read_matrix()
+    print("hit fraction", (hf.sum() + hb.sum()) / tot.sum(), "iters", it[:3], "launches", ctx.launch_count())
