@@ -116,6 +116,8 @@ int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int32_t emi
  *   emit_ids[n_local]             emitters handled by this solve (this GPU's shard)
  *   surf_active[n_local][n_surf]  main.py:167-204 mask per emitter; emit_sid/min_sid[n_local]: main.py:1181-1182
  *   cp_table[n_rot][7]            rotations; iteration `it` of local emitter k uses row rot_base[k] + it
+ *   ray_range[n_local][2]         NULL, or per job the slice [begin,end) of the emitter's rays traced by THIS
+ *                                 context (multi-GPU ray-range sharding of very large emitters; see below)
  *   tol_mode: 0 = "stderr", 1 = "delta";  interval: convergence_interval (1 = the reference's CPU behaviour)
  *
  * rsk_matrix_step enqueues `n_iters` further iterations for every unconverged emitter: one fused
@@ -133,7 +135,7 @@ typedef struct rsk_solve_params {
 int rsk_matrix_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em,
                      const int32_t *emit_ids, int32_t n_local,
                      const uint8_t *surf_active, const int32_t *emit_sid, const int32_t *min_sid,
-                     const float *cp_table, int32_t n_rot, const int32_t *rot_base,
+                     const float *cp_table, int32_t n_rot, const int32_t *rot_base, const int64_t *ray_range,
                      const rsk_solve_params *params, rsk_solve **out);
 int rsk_matrix_step(rsk_solve *solve, int32_t n_iters, int32_t *n_active);
 /* hits_front/hits_back: int64[n_local][n_surf]; iters: int32[n_local]; total_rays: int64[n_local];
@@ -150,11 +152,22 @@ int rsk_matrix_device_tallies(rsk_solve *solve, void **device_ptr, int64_t *n_el
  * patches (utils/cpu_trace.py:735-798) when discrete != 0, else counted. */
 int rsk_sky_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em,
                   const int32_t *emit_ids, int32_t n_local, const uint8_t *surf_active,
-                  const float *cp_table, int32_t n_rot, const int32_t *rot_base,
+                  const float *cp_table, int32_t n_rot, const int32_t *rot_base, const int64_t *ray_range,
                   const rsk_solve_params *params, int32_t discrete, rsk_solve **out);
 int rsk_sky_step(rsk_solve *solve, int32_t n_iters, int32_t *n_active);
 /* counts: int64[n_local][145] (discrete) or int64[n_local][1]. */
 int rsk_sky_read(rsk_solve *solve, int64_t *counts, int32_t *iters, int64_t *total_rays);
+
+/* Split-phase stepping for multi-GPU solves in which an emitter's rays are divided over several GPUs: every
+ * participating context enqueues the trace of its slice, the caller all-reduces (SUM) the per-iteration tally
+ * block of the shared jobs on the context's stream (device pointer from rsk_solve_device_iter_tallies:
+ * uint64[n_local][n_per_job], jobs in emit_ids order), then every context enqueues the fold, so all of them
+ * take identical convergence decisions.  rsk_solve_poll synchronises and returns the number of running jobs.
+ * rsk_matrix_step / rsk_sky_step are exactly n_iters x (enqueue_trace, enqueue_fold) followed by a poll. */
+int rsk_solve_enqueue_trace(rsk_solve *solve);
+int rsk_solve_enqueue_fold(rsk_solve *solve);
+int rsk_solve_poll(rsk_solve *solve, int32_t *n_active);
+int rsk_solve_device_iter_tallies(rsk_solve *solve, void **device_ptr, int64_t *n_per_job);
 
 int rsk_solve_destroy(rsk_solve *solve);
 /* Rays traced so far by this solve (all emitters, all iterations). */

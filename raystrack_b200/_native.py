@@ -29,6 +29,7 @@ EXPORTS = (
     "rsk_trace_rays",
     "rsk_matrix_begin", "rsk_matrix_step", "rsk_matrix_read", "rsk_matrix_device_tallies",
     "rsk_sky_begin", "rsk_sky_step", "rsk_sky_read",
+    "rsk_solve_enqueue_trace", "rsk_solve_enqueue_fold", "rsk_solve_poll", "rsk_solve_device_iter_tallies",
     "rsk_solve_destroy", "rsk_solve_rays_traced", "rsk_reciprocity_rowsum",
 )
 
@@ -82,16 +83,18 @@ class Context:
         self.device = device
 
     @classmethod
-    def for_device(cls, device: Optional[int] = None) -> "Context":
+    def for_device(cls, device: Optional[int] = None, stream: int = 0) -> "Context":
+        """Cached context per (device, stream).  Default device: RSK_DEVICE or LOCAL_RANK (torchrun), else 0."""
         if device is None:
             device = int(os.environ.get("RSK_DEVICE", os.environ.get("LOCAL_RANK", "0")))
             n = device_count()
             if n > 0:
                 device %= n
-        ctx = cls._by_device.get(device)
+        key = (device, int(stream or 0))
+        ctx = cls._by_device.get(key)
         if ctx is None:
-            ctx = cls(device)
-            cls._by_device[device] = ctx
+            ctx = cls(device, stream)
+            cls._by_device[key] = ctx
         return ctx
 
     def synchronize(self) -> None:
@@ -223,7 +226,7 @@ class Solve:
 
     def __init__(self, ctx: Context, scene: DeviceScene, em: DeviceEmitters, emit_ids, surf_active, cp_table, rot_base,
                  *, max_iters: int, min_iters: int, interval: int, tol_mode: str, tol: float,
-                 emit_sid=None, min_sid=None, sky: bool = False, discrete: bool = False):
+                 emit_sid=None, min_sid=None, sky: bool = False, discrete: bool = False, ray_range=None):
         if tol_mode not in ("stderr", "delta"):
             raise ValueError(f"Unknown tol_mode: {tol_mode}")
         self.ctx, self.scene, self.em = ctx, scene, em
@@ -234,16 +237,17 @@ class Solve:
         act = np.ascontiguousarray(surf_active, np.uint8).reshape(self.n_local, scene.n_surf)
         cpt = np.ascontiguousarray(cp_table, np.float32).reshape(-1, 7)
         rb = np.ascontiguousarray(rot_base, np.int32)
+        rr = None if ray_range is None else np.ascontiguousarray(ray_range, np.int64).reshape(self.n_local, 2)
         p = SolveParams(int(max_iters), int(min_iters), int(interval), 0 if tol_mode == "stderr" else 1, float(tol))
         if sky:
             check(ctx.lib.rsk_sky_begin(ctx.handle, scene.handle, em.handle, ptr(self.emit_ids), C.c_int32(self.n_local),
-                                        ptr(act), ptr(cpt), C.c_int32(cpt.shape[0]), ptr(rb), C.byref(p),
+                                        ptr(act), ptr(cpt), C.c_int32(cpt.shape[0]), ptr(rb), ptr(rr), C.byref(p),
                                         C.c_int32(1 if discrete else 0), C.byref(self.handle)), "rsk_sky_begin")
         else:
             es = np.ascontiguousarray(emit_sid, np.int32)
             ms = np.ascontiguousarray(min_sid, np.int32)
             check(ctx.lib.rsk_matrix_begin(ctx.handle, scene.handle, em.handle, ptr(self.emit_ids), C.c_int32(self.n_local),
-                                           ptr(act), ptr(es), ptr(ms), ptr(cpt), C.c_int32(cpt.shape[0]), ptr(rb),
+                                           ptr(act), ptr(es), ptr(ms), ptr(cpt), C.c_int32(cpt.shape[0]), ptr(rb), ptr(rr),
                                            C.byref(p), C.byref(self.handle)), "rsk_matrix_begin")
 
     def step(self, n_iters: int) -> int:
@@ -251,6 +255,24 @@ class Solve:
         fn = self.ctx.lib.rsk_sky_step if self.sky else self.ctx.lib.rsk_matrix_step
         check(fn(self.handle, C.c_int32(n_iters), C.byref(n_active)), "solve step")
         return int(n_active.value)
+
+    def enqueue_trace(self) -> None:
+        check(self.ctx.lib.rsk_solve_enqueue_trace(self.handle), "rsk_solve_enqueue_trace")
+
+    def enqueue_fold(self) -> None:
+        check(self.ctx.lib.rsk_solve_enqueue_fold(self.handle), "rsk_solve_enqueue_fold")
+
+    def poll(self) -> int:
+        n_active = C.c_int32(0)
+        check(self.ctx.lib.rsk_solve_poll(self.handle, C.byref(n_active)), "rsk_solve_poll")
+        return int(n_active.value)
+
+    def device_iter_tallies(self):
+        """(device pointer, elements per job) of the uint64 per-iteration tally block."""
+        p = C.c_void_p()
+        n = C.c_int64(0)
+        check(self.ctx.lib.rsk_solve_device_iter_tallies(self.handle, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
 
     def read_matrix(self, want_stderr: bool = False):
         ns = self.scene.n_surf

@@ -319,10 +319,11 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
     const int64_t n_tiles = (n_rays + RSK_TILE_RAYS - 1) / RSK_TILE_RAYS;
     const int64_t tiles[2] = {0, n_tiles};
     const int32_t zero = 0;
+    const int64_t range[2] = {first_ray, first_ray + n_rays};
 
-    uint32_t *d_mask = nullptr; float *d_cp = nullptr; int32_t *d_ids = nullptr, *d_zero = nullptr; int64_t *d_tiles = nullptr;
+    uint32_t *d_mask = nullptr; float *d_cp = nullptr; int32_t *d_ids = nullptr, *d_zero = nullptr; int64_t *d_tiles = nullptr, *d_range = nullptr;
     float *d_orig = nullptr, *d_dirs = nullptr; int32_t *d_hit = nullptr; uint8_t *d_front = nullptr;
-    auto cleanup = [&]() { cudaFree(d_mask); cudaFree(d_cp); cudaFree(d_ids); cudaFree(d_zero); cudaFree(d_tiles);
+    auto cleanup = [&]() { cudaFree(d_mask); cudaFree(d_cp); cudaFree(d_ids); cudaFree(d_zero); cudaFree(d_tiles); cudaFree(d_range);
                            cudaFree(d_orig); cudaFree(d_dirs); cudaFree(d_hit); cudaFree(d_front); };
     int rc = RSK_OK;
 #define T_TRY(expr) do { rc = (expr); if (rc != RSK_OK) { cleanup(); return rc; } } while (0)
@@ -332,6 +333,7 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
     T_TRY(rsk_upload(ctx, &d_ids, &emitter, 1));
     T_TRY(rsk_upload(ctx, &d_zero, &zero, 1));
     T_TRY(rsk_upload(ctx, &d_tiles, tiles, 2));
+    T_TRY(rsk_upload(ctx, &d_range, range, 2));
     if (orig) T_TRY(rsk_dev_alloc(&d_orig, (size_t)n_rays * 3));
     if (dirs) T_TRY(rsk_dev_alloc(&d_dirs, (size_t)n_rays * 3));
     if (hit_sid) T_TRY(rsk_dev_alloc(&d_hit, (size_t)n_rays));
@@ -344,7 +346,7 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
     a.emit_ids = d_ids; a.tile_start = d_tiles; a.n_local = 1; a.surf_mask = d_mask;
     a.cp_table = d_cp; a.rot_base = d_zero; a.iters_done = d_zero; a.done = nullptr; a.tally = nullptr;
     a.n_hist = mode == MODE_MATRIX ? 2 * scene->n_surf : RSK_TREGENZA_BINS;
-    a.ray_first = first_ray; a.ray_count = n_rays;
+    a.ray_begin = d_range; a.ray_end = d_range + 1; a.dbg_base = first_ray;
     a.dbg_orig = d_orig; a.dbg_dirs = d_dirs; a.dbg_hit = d_hit; a.dbg_front = d_front;
     T_TRY(rsk_launch_trace(ctx, a, mode, n_tiles));
     if (orig) T_CUDA(cudaMemcpyAsync(orig, d_orig, (size_t)n_rays * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -371,7 +373,7 @@ struct rsk_solve {
     int64_t n_tiles = 0;
     // device state
     int32_t *emit_ids = nullptr, *rot_base = nullptr, *iters_done = nullptr, *done = nullptr, *not_conv = nullptr, *have_prev = nullptr;
-    int64_t *tile_start = nullptr, *n_rays_once = nullptr, *total_rays = nullptr;
+    int64_t *tile_start = nullptr, *n_rays_once = nullptr, *total_rays = nullptr, *ray_begin = nullptr, *ray_end = nullptr;
     uint32_t *mask = nullptr;
     float *cp_table = nullptr;
     unsigned long long *iter_tally = nullptr, *rays_traced = nullptr;
@@ -380,12 +382,13 @@ struct rsk_solve {
     int32_t *n_active = nullptr;
     int32_t *h_pinned = nullptr;     // [0] n_active
     int32_t last_active = 0;
+    bool stepped = false;
 };
 
 static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int mode, int discrete,
                            const int32_t *emit_ids, int32_t n_local, const uint8_t *surf_active,
                            const int32_t *emit_sid, const int32_t *min_sid,
-                           const float *cp_table, int32_t n_rot, const int32_t *rot_base,
+                           const float *cp_table, int32_t n_rot, const int32_t *rot_base, const int64_t *ray_range,
                            const rsk_solve_params *params, rsk_solve **out) {
     RSK_REQUIRE(ctx && scene && em && params && out, "solve begin: null argument");
     RSK_REQUIRE(n_local >= 0 && n_rot >= 0, "solve begin: negative sizes");
@@ -399,7 +402,7 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
     s->n_hist = mode == MODE_MATRIX ? 2 * scene->n_surf : (discrete ? RSK_TREGENZA_BINS : 1);
     const int nw = std::max((scene->n_surf + 31) / 32, 1);
     std::vector<uint32_t> mask((size_t)n_local * nw);
-    std::vector<int64_t> tiles(n_local + 1, 0), once(n_local);
+    std::vector<int64_t> tiles(n_local + 1, 0), once(n_local), rbeg(n_local), rend(n_local);
     int rc = RSK_OK;
     for (int k = 0; k < n_local; ++k) {
         if (emit_ids[k] < 0 || emit_ids[k] >= em->n_emit) { rsk_set_error("solve begin: emitter id out of range"); rc = RSK_ERR_INVALID; break; }
@@ -407,7 +410,10 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
         const int es = emit_sid ? emit_sid[k] : emit_ids[k], ms = min_sid ? min_sid[k] : 0;
         rsk_pack_mask(surf_active + (size_t)k * scene->n_surf, scene->n_surf, es, ms, mask.data() + (size_t)k * nw);
         once[k] = em->h_desc[emit_ids[k]].n_rays_once;
-        tiles[k + 1] = tiles[k] + (once[k] + RSK_TILE_RAYS - 1) / RSK_TILE_RAYS;
+        rbeg[k] = ray_range ? ray_range[2 * k] : 0;
+        rend[k] = ray_range ? ray_range[2 * k + 1] : once[k];
+        if (rbeg[k] < 0 || rend[k] < rbeg[k] || rend[k] > once[k]) { rsk_set_error("solve begin: ray range out of bounds"); rc = RSK_ERR_INVALID; break; }
+        tiles[k + 1] = tiles[k] + (rend[k] - rbeg[k] + RSK_TILE_RAYS - 1) / RSK_TILE_RAYS;
     }
     s->n_tiles = tiles[n_local];
     const size_t nh = (size_t)n_local * s->n_hist;
@@ -419,6 +425,8 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
     S_TRY(rsk_upload(ctx, &s->rot_base, rot_base, n_local));
     S_TRY(rsk_upload(ctx, &s->tile_start, tiles.data(), tiles.size()));
     S_TRY(rsk_upload(ctx, &s->n_rays_once, once.data(), once.size()));
+    S_TRY(rsk_upload(ctx, &s->ray_begin, rbeg.data(), rbeg.size()));
+    S_TRY(rsk_upload(ctx, &s->ray_end, rend.data(), rend.size()));
     S_TRY(rsk_upload(ctx, &s->mask, mask.data(), mask.size()));
     S_TRY(rsk_upload(ctx, &s->cp_table, cp_table, (size_t)n_rot * 7));
     S_TRY(rsk_dev_alloc(&s->iters_done, n_local)); S_TRY(rsk_dev_alloc(&s->done, n_local));
@@ -451,22 +459,25 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
     return RSK_OK;
 }
 
-static int rsk_solve_step(rsk_solve *s, int32_t n_iters, int32_t *n_active) {
-    RSK_REQUIRE(s && n_iters >= 0, "solve step: bad arguments");
+// One iteration = phase A (fused raygen+trace+tally of every unconverged job) + phase B (fold the iteration
+// tallies into totals / Welford statistics, decide convergence per job).  The phases are separate entry points
+// so that a multi-GPU caller can all-reduce the iteration tallies of ray-split emitters in between.
+static int rsk_solve_enqueue_trace_impl(rsk_solve *s) {
     rsk_ctx *ctx = s->ctx;
-    RSK_CUDA(cudaSetDevice(ctx->device));
-    if (s->n_local == 0 || s->p.max_iters <= 0 || s->last_active == 0 || n_iters == 0) {
-        if (n_active) *n_active = s->last_active;
-        return RSK_OK;
-    }
+    if (s->n_local == 0 || s->p.max_iters <= 0) return RSK_OK;
     TraceArgs a;
     memset(&a, 0, sizeof(a));
     a.sc = s->scene->view();
     a.ev = s->em->view();
     a.emit_ids = s->emit_ids; a.tile_start = s->tile_start; a.n_local = s->n_local; a.surf_mask = s->mask;
     a.cp_table = s->cp_table; a.rot_base = s->rot_base; a.iters_done = s->iters_done; a.done = s->done;
-    a.tally = s->iter_tally; a.n_hist = s->n_hist; a.ray_first = 0; a.ray_count = -1;
+    a.tally = s->iter_tally; a.n_hist = s->n_hist; a.ray_begin = s->ray_begin; a.ray_end = s->ray_end;
+    return rsk_launch_trace(ctx, a, s->mode, s->n_tiles);
+}
 
+static int rsk_solve_enqueue_fold_impl(rsk_solve *s) {
+    rsk_ctx *ctx = s->ctx;
+    if (s->n_local == 0 || s->p.max_iters <= 0) return RSK_OK;
     FoldArgs f;
     memset(&f, 0, sizeof(f));
     f.iter_tally = s->iter_tally; f.total = s->total; f.mean = s->mean; f.m2 = s->m2; f.prev = s->prev;
@@ -477,19 +488,24 @@ static int rsk_solve_step(rsk_solve *s, int32_t n_iters, int32_t *n_active) {
     f.max_iters = s->p.max_iters; f.min_iters = s->p.min_iters; f.interval = s->p.interval; f.tol_mode = s->p.tol_mode;
     f.scalar_sky = (s->mode == MODE_SKY && !s->discrete) ? 1 : 0;
     f.tol = s->p.tol;
-
     DecideArgs d;
     memset(&d, 0, sizeof(d));
     d.iters_done = s->iters_done; d.total_rays = s->total_rays; d.done = s->done; d.not_converged = s->not_conv;
     d.have_prev = s->have_prev; d.n_rays_once = s->n_rays_once; d.n_active = s->n_active; d.rays_traced = s->rays_traced;
+    d.ray_begin = s->ray_begin; d.ray_end = s->ray_end;
     d.n_local = s->n_local; d.max_iters = s->p.max_iters; d.min_iters = s->p.min_iters; d.interval = s->p.interval;
     d.tol_mode = s->p.tol_mode;
+    RSK_TRY(rsk_launch_fold(ctx, f));
+    RSK_CUDA(cudaMemsetAsync(s->n_active, 0, sizeof(int32_t), ctx->stream));
+    RSK_TRY(rsk_launch_decide(ctx, d));
+    return RSK_OK;
+}
 
-    for (int it = 0; it < n_iters; ++it) {
-        RSK_TRY(rsk_launch_trace(ctx, a, s->mode, s->n_tiles));
-        RSK_TRY(rsk_launch_fold(ctx, f));
-        RSK_CUDA(cudaMemsetAsync(s->n_active, 0, sizeof(int32_t), ctx->stream));
-        RSK_TRY(rsk_launch_decide(ctx, d));
+static int rsk_solve_poll_impl(rsk_solve *s, int32_t *n_active) {
+    rsk_ctx *ctx = s->ctx;
+    if (s->n_local == 0 || s->p.max_iters <= 0 || !s->stepped) {
+        if (n_active) *n_active = s->last_active;
+        return RSK_OK;
     }
     RSK_CUDA(cudaMemcpyAsync(s->h_pinned, s->n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     RSK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -499,12 +515,51 @@ static int rsk_solve_step(rsk_solve *s, int32_t n_iters, int32_t *n_active) {
     return RSK_OK;
 }
 
+static int rsk_solve_step(rsk_solve *s, int32_t n_iters, int32_t *n_active) {
+    RSK_REQUIRE(s && n_iters >= 0, "solve step: bad arguments");
+    RSK_CUDA(cudaSetDevice(s->ctx->device));
+    if (s->last_active > 0) {
+        for (int it = 0; it < n_iters; ++it) {
+            RSK_TRY(rsk_solve_enqueue_trace_impl(s));
+            RSK_TRY(rsk_solve_enqueue_fold_impl(s));
+            s->stepped = true;
+        }
+    }
+    return rsk_solve_poll_impl(s, n_active);
+}
+
+extern "C" int rsk_solve_enqueue_trace(rsk_solve *s) {
+    RSK_REQUIRE(s, "null solve");
+    RSK_CUDA(cudaSetDevice(s->ctx->device));
+    return rsk_solve_enqueue_trace_impl(s);
+}
+
+extern "C" int rsk_solve_enqueue_fold(rsk_solve *s) {
+    RSK_REQUIRE(s, "null solve");
+    RSK_CUDA(cudaSetDevice(s->ctx->device));
+    s->stepped = true;
+    return rsk_solve_enqueue_fold_impl(s);
+}
+
+extern "C" int rsk_solve_poll(rsk_solve *s, int32_t *n_active) {
+    RSK_REQUIRE(s, "null solve");
+    RSK_CUDA(cudaSetDevice(s->ctx->device));
+    return rsk_solve_poll_impl(s, n_active);
+}
+
+extern "C" int rsk_solve_device_iter_tallies(rsk_solve *s, void **device_ptr, int64_t *n_per_job) {
+    RSK_REQUIRE(s && device_ptr && n_per_job, "rsk_solve_device_iter_tallies: bad arguments");
+    *device_ptr = s->iter_tally;
+    *n_per_job = s->n_hist;
+    return RSK_OK;
+}
+
 extern "C" int rsk_matrix_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, const int32_t *emit_ids, int32_t n_local,
                                 const uint8_t *surf_active, const int32_t *emit_sid, const int32_t *min_sid,
-                                const float *cp_table, int32_t n_rot, const int32_t *rot_base,
+                                const float *cp_table, int32_t n_rot, const int32_t *rot_base, const int64_t *ray_range,
                                 const rsk_solve_params *params, rsk_solve **out) {
     RSK_REQUIRE(n_local == 0 || (emit_sid && min_sid), "rsk_matrix_begin: null emit_sid/min_sid");
-    return rsk_solve_begin(ctx, scene, em, MODE_MATRIX, 0, emit_ids, n_local, surf_active, emit_sid, min_sid, cp_table, n_rot, rot_base, params, out);
+    return rsk_solve_begin(ctx, scene, em, MODE_MATRIX, 0, emit_ids, n_local, surf_active, emit_sid, min_sid, cp_table, n_rot, rot_base, ray_range, params, out);
 }
 
 extern "C" int rsk_matrix_step(rsk_solve *s, int32_t n_iters, int32_t *n_active) {
@@ -562,9 +617,9 @@ extern "C" int rsk_matrix_device_tallies(rsk_solve *s, void **device_ptr, int64_
 
 extern "C" int rsk_sky_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, const int32_t *emit_ids, int32_t n_local,
                              const uint8_t *surf_active, const float *cp_table, int32_t n_rot, const int32_t *rot_base,
-                             const rsk_solve_params *params, int32_t discrete, rsk_solve **out) {
+                             const int64_t *ray_range, const rsk_solve_params *params, int32_t discrete, rsk_solve **out) {
     // main.py:2112: emit_sid = emitter index, min_sid = 0
-    return rsk_solve_begin(ctx, scene, em, MODE_SKY, discrete ? 1 : 0, emit_ids, n_local, surf_active, nullptr, nullptr, cp_table, n_rot, rot_base, params, out);
+    return rsk_solve_begin(ctx, scene, em, MODE_SKY, discrete ? 1 : 0, emit_ids, n_local, surf_active, nullptr, nullptr, cp_table, n_rot, rot_base, ray_range, params, out);
 }
 
 extern "C" int rsk_sky_step(rsk_solve *s, int32_t n_iters, int32_t *n_active) {
@@ -597,7 +652,7 @@ extern "C" int rsk_solve_destroy(rsk_solve *s) {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     cudaFree(s->emit_ids); cudaFree(s->rot_base); cudaFree(s->iters_done); cudaFree(s->done); cudaFree(s->not_conv);
-    cudaFree(s->have_prev); cudaFree(s->tile_start); cudaFree(s->n_rays_once); cudaFree(s->total_rays); cudaFree(s->mask);
+    cudaFree(s->have_prev); cudaFree(s->tile_start); cudaFree(s->n_rays_once); cudaFree(s->total_rays); cudaFree(s->ray_begin); cudaFree(s->ray_end); cudaFree(s->mask);
     cudaFree(s->cp_table); cudaFree(s->iter_tally); cudaFree(s->rays_traced); cudaFree(s->total); cudaFree(s->mean);
     cudaFree(s->m2); cudaFree(s->prev); cudaFree(s->n_active);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);

@@ -167,7 +167,9 @@ struct TraceArgs {
     unsigned long long *tally;      // [n_local][n_hist]
     int32_t n_hist;                 // matrix: 2*n_surf; sky: 145 or 1
     int32_t hist_in_smem;
-    int64_t ray_first, ray_count;   // sub-range of each job's rays (ray_count < 0: all)
+    const int64_t *ray_begin;       // [n_local] first ray of each job's slice (null: 0)
+    const int64_t *ray_end;         // [n_local] one past the last ray of each job's slice (null: n_rays_once)
+    int64_t dbg_base;               // ray index stored at element 0 of the per-ray outputs
     float *dbg_orig, *dbg_dirs;     // optional per-ray outputs (test hook)
     int32_t *dbg_hit;
     uint8_t *dbg_front;

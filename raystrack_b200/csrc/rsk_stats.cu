@@ -71,7 +71,7 @@ __global__ void rsk_decide_kernel(const DecideArgs a) {
     const int n = a.iters_done[k] + 1;
     a.iters_done[k] = n;
     a.total_rays[k] += a.n_rays_once[k];
-    atomicAdd(a.rays_traced, (unsigned long long)a.n_rays_once[k]);
+    atomicAdd(a.rays_traced, (unsigned long long)(a.ray_end[k] - a.ray_begin[k]));
     const bool check = rsk_checkpoint(n, a.min_iters, a.interval, a.max_iters, a.tol_mode == 0);
     bool converged = false;
     if (check) {

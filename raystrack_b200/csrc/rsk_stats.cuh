@@ -26,6 +26,7 @@ struct DecideArgs {
     int32_t *not_converged;
     int32_t *have_prev;              // delta mode: a previous checkpoint exists
     const int64_t *n_rays_once;
+    const int64_t *ray_begin, *ray_end;   // this rank's slice of each job (for the rays-traced counter)
     int32_t *n_active;               // scalar counter, zeroed by the launcher
     unsigned long long *rays_traced; // scalar
     int32_t n_local;

@@ -31,7 +31,7 @@ __device__ __forceinline__ int rsk_result_key(const TraceArgs &a, const Walk &w,
 
 template <int MODE>
 __device__ __forceinline__ void rsk_debug_store(const TraceArgs &a, int64_t k, const Walk &w, int key, bool any_hit) {
-    const int64_t i = k - a.ray_first;
+    const int64_t i = k - a.dbg_base;
     if (a.dbg_orig) { a.dbg_orig[3 * i] = w.ox; a.dbg_orig[3 * i + 1] = w.oy; a.dbg_orig[3 * i + 2] = w.oz; }
     if (a.dbg_dirs) { a.dbg_dirs[3 * i] = w.dx; a.dbg_dirs[3 * i + 1] = w.dy; a.dbg_dirs[3 * i + 2] = w.dz; }
     if (MODE == MODE_MATRIX) {
@@ -64,8 +64,9 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS) rsk_trace_kernel(const Trace
 
     const EmitterDesc e = a.ev.desc[a.emit_ids[job]];
     const int64_t tile = (int64_t)blockIdx.x - a.tile_start[job];
-    const int64_t range_end = a.ray_count < 0 ? e.n_rays_once : a.ray_first + a.ray_count;
-    const int64_t begin = a.ray_first + tile * RSK_TILE_RAYS;
+    const int64_t range_begin = a.ray_begin ? a.ray_begin[job] : 0;
+    const int64_t range_end = a.ray_end ? a.ray_end[job] : e.n_rays_once;
+    const int64_t begin = range_begin + tile * RSK_TILE_RAYS;
     const int64_t end = min(begin + (int64_t)RSK_TILE_RAYS, range_end);
 
     float cp[7];

@@ -63,3 +63,28 @@ def max_over_ranks(value: float, device: int = 0) -> float:
         t = t.cuda(device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class _DeviceBuffer:
+    """Zero-copy view of library-owned device memory for torch (CUDA array interface, int64 elements)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False), "version": 3}
+
+
+def device_int64_view(ptr: int, n_per_job: int, n_jobs: int, device: int = 0):
+    """torch tensor aliasing the first ``n_jobs`` rows of a solve's per-iteration tally block (uint64 counters
+    viewed as int64), or None when there is nothing to reduce."""
+    import torch
+    n = int(n_per_job) * int(n_jobs)
+    if n <= 0 or not ptr:
+        return None
+    return torch.as_tensor(_DeviceBuffer(ptr, n), device=f"cuda:{device}")
+
+
+def all_reduce_device_(tensor, device: int = 0) -> None:
+    """SUM all-reduce of a device tensor on torch's current stream (NCCL over NVLink)."""
+    import torch.distributed as dist
+    if tensor is None:
+        return
+    dist.all_reduce(tensor, op=dist.ReduceOp.SUM)

@@ -97,19 +97,42 @@ def _rotation_table(seed: int, n_emit: int, max_iters: int) -> np.ndarray:
     return table
 
 
-def _shard(indices: List[int], weights: Sequence[float], rank: int, world: int) -> List[int]:
-    """Longest-processing-time-first assignment of emitters to ranks; returns this rank's emitters (sorted)."""
-    if world <= 1:
-        return list(indices)
-    order = sorted(indices, key=lambda i: -weights[i])
+TILE_RAYS = 4096               # rays per CTA tile (csrc/rsk_common.cuh RSK_TILE_RAYS): slices are cut on tile boundaries
+
+
+def plan_shards(todo: Sequence[int], n_rays_once: Sequence[int], world: int) -> List[List[Tuple[int, int, int, bool]]]:
+    """Partition the (emitter, ray range) work of one iteration over ``world`` GPUs.
+
+    Returns, per rank, a list of jobs ``(emitter, ray_begin, ray_end, shared)``.  Emitters are independent units
+    (reference main.py:1758-1939) and are assigned whole, longest first, to the least loaded rank; an emitter that
+    alone exceeds an eighth of a rank's fair share is cut into ``world`` tile-aligned ray slices instead (``shared``):
+    its per-iteration tallies are summed across ranks before the statistics update, so every rank takes the same
+    convergence decision for it.  Shared jobs come first in every rank's list, in the same order."""
+    world = max(1, int(world))
+    plans: List[List[Tuple[int, int, int, bool]]] = [[] for _ in range(world)]
+    if world == 1:
+        plans[0] = [(int(i), 0, int(n_rays_once[i]), False) for i in todo]
+        return plans
+    total = float(sum(int(n_rays_once[i]) for i in todo))
+    limit = total / (8.0 * world)
+    shared = [int(i) for i in todo if n_rays_once[i] > limit and n_rays_once[i] >= 2 * world * TILE_RAYS]
+    whole = [int(i) for i in todo if int(i) not in set(shared)]
     loads = [0.0] * world
-    mine: List[int] = []
-    for i in order:
+    for i in shared:
+        n = int(n_rays_once[i])
+        tiles = (n + TILE_RAYS - 1) // TILE_RAYS
+        cuts = [min(n, (tiles * r // world) * TILE_RAYS) for r in range(world)] + [n]
+        for r in range(world):
+            plans[r].append((i, cuts[r], cuts[r + 1], True))
+            loads[r] += cuts[r + 1] - cuts[r]
+    per_rank: List[List[int]] = [[] for _ in range(world)]
+    for i in sorted(whole, key=lambda k: (-int(n_rays_once[k]), k)):
         r = min(range(world), key=lambda q: (loads[q], q))
-        loads[r] += weights[i]
-        if r == rank:
-            mine.append(i)
-    return sorted(mine)
+        loads[r] += int(n_rays_once[i])
+        per_rank[r].append(i)
+    for r in range(world):
+        plans[r].extend((i, 0, int(n_rays_once[i]), False) for i in sorted(per_rank[r]))
+    return plans
 
 
 def _run_solve(solve: _native.Solve, min_iters: int, max_iters: int) -> None:
@@ -126,6 +149,28 @@ def _run_solve(solve: _native.Solve, min_iters: int, max_iters: int) -> None:
         done += chunk
 
 
+def _run_solve_shared(solve: _native.Solve, n_shared: int, min_iters: int, max_iters: int, device: int) -> None:
+    """Multi-GPU variant when some emitters are ray-split over the ranks: per iteration trace -> all-reduce of the
+    shared jobs' iteration tallies (NCCL, on the solve's stream) -> statistics.  Every rank issues the same
+    sequence of collectives; the loop ends when no rank has a running job."""
+    from . import dist as D
+    if max_iters <= 0:
+        return
+    tally = D.device_int64_view(*solve.device_iter_tallies(), n_jobs=n_shared, device=device) if solve.n_local else None
+    done = 0
+    chunk = max(1, min(int(max_iters), max(int(min_iters), 1)))
+    while done < max_iters:
+        for _ in range(chunk):
+            solve.enqueue_trace()
+            D.all_reduce_device_(tally, device)
+            solve.enqueue_fold()
+        done += chunk
+        active = solve.poll() if solve.n_local else 0
+        if D.max_over_ranks(float(active), device) <= 0:
+            break
+        chunk = min(4, max_iters - done)
+
+
 def _dist_env() -> Tuple[int, int]:
     try:
         import torch.distributed as dist
@@ -134,6 +179,66 @@ def _dist_env() -> Tuple[int, int]:
     except Exception:
         pass
     return 0, 1
+
+
+def _context() -> _native.Context:
+    """The CUDA context of this process.  Under torch.distributed/NCCL the library shares torch's current stream
+    so that collectives and kernels are ordered without host synchronisation."""
+    rank, world = _dist_env()
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        if dist.get_backend() == "nccl":
+            dev = torch.cuda.current_device()
+            return _native.Context.for_device(dev, torch.cuda.current_stream(dev).cuda_stream)
+    return _native.Context.for_device()
+
+
+def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_iters, min_iters, interval, tol_mode, tol,
+                   emit_sid=None, min_sid=None, sky=False, discrete=False):
+    """Run the jobs of ``todo`` (emitter indices) on this rank's shard and return full-size, rank-summed integer
+    results: (tallies int64 [n_emit, n_hist], iterations int64 [n_emit], total rays int64 [n_emit])."""
+    n_emit = active.shape[0]
+    n_surf = active.shape[1]
+    rank, world = _dist_env()
+    plan = plan_shards(todo, n_rays_once, world)[rank]
+    ids = np.asarray([j[0] for j in plan], np.int32)
+    ranges = np.asarray([[j[1], j[2]] for j in plan], np.int64).reshape(-1, 2)
+    n_shared = sum(1 for j in plan if j[3])
+    any_shared = world > 1 and any(j[3] for shard in plan_shards(todo, n_rays_once, world) for j in shard)
+    kw = {}
+    if not sky:
+        kw = dict(emit_sid=np.asarray(emit_sid)[ids], min_sid=np.asarray(min_sid)[ids])
+    solve = _native.Solve(ctx, d_scene.native, d_em.native, ids,
+                          active[ids] if len(plan) else np.zeros((0, n_surf), np.uint8),
+                          table, ids.copy(), max_iters=max_iters, min_iters=min_iters, interval=interval,
+                          tol_mode=tol_mode, tol=tol, sky=sky, discrete=discrete, ray_range=ranges, **kw)
+    try:
+        if any_shared:
+            _run_solve_shared(solve, n_shared, min_iters, max_iters, ctx.device)
+        else:
+            _run_solve(solve, min_iters, max_iters)
+        if sky:
+            loc, it_loc, tot_loc = solve.read_sky()
+        else:
+            hf, hb, it_loc, tot_loc, _, _ = solve.read_matrix()
+            loc = np.concatenate([hf, hb], axis=1)
+    finally:
+        solve.close()
+    n_hist = (145 if discrete else 1) if sky else 2 * n_surf
+    tallies = np.zeros((n_emit, n_hist), np.int64)
+    iters = np.zeros(n_emit, np.int64)
+    totals = np.zeros(n_emit, np.int64)
+    for k, (e, _, _, shared) in enumerate(plan):
+        if shared and rank != 0:
+            continue                      # replicated state: counted once
+        tallies[e] = loc[k]
+        iters[e] = it_loc[k]
+        totals[e] = tot_loc[k]
+    if world > 1:
+        from .dist import allreduce_sum_
+        allreduce_sum_([tallies, iters, totals], device=ctx.device)
+    return tallies, iters, totals
 
 
 def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Optional[PreparedSolver] = None):
@@ -161,7 +266,7 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
     emitters = solver.get_emitters(samples=samples, rays=rays, flip_faces=flip_faces)
     areas = [em.total_area for em in emitters] if reciprocity else None
     centers, extents = solver.get_mesh_bounds()
-    ctx = _native.Context.for_device()
+    ctx = _context()
     d_scene = solver.get_device_scene(use_bvh=use_bvh, ctx=ctx)
     d_em = solver.get_device_emitters(samples=samples, rays=rays, flip_faces=flip_faces, ctx=ctx)
 
@@ -176,33 +281,13 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
     has_recv = recv_mask.any(axis=1)
     todo = [i for i in range(n_surf) if has_recv[i]]
 
-    rank, world = _dist_env()
     weights = [float(em.n_cells * rays) for em in emitters]
-    mine = _shard(todo, weights, rank, world)
+    n_once = [int(em.n_cells * rays) for em in emitters]
     table = _rotation_table(seed, n_surf, max_iters)
-    ids = np.asarray(mine, np.int32)
-    solve = _native.Solve(ctx, d_scene.native, d_em.native, ids, active[ids] if len(mine) else np.zeros((0, n_surf), np.uint8),
-                          table, ids.copy(), max_iters=max_iters, min_iters=min_iters,
-                          interval=interval if schedule == "gpu" else 1, tol_mode=tol_mode, tol=tol,
-                          emit_sid=emit_sid[ids], min_sid=min_sid[ids])
-    try:
-        _run_solve(solve, min_iters, max_iters)
-        hf_loc, hb_loc, it_loc, tot_loc, _, _ = solve.read_matrix()
-    finally:
-        solve.close()
-
-    hits_f = np.zeros((n_surf, n_surf), np.int64)
-    hits_b = np.zeros((n_surf, n_surf), np.int64)
-    iters = np.zeros(n_surf, np.int64)
-    totals = np.zeros(n_surf, np.int64)
-    if len(mine):
-        hits_f[ids] = hf_loc
-        hits_b[ids] = hb_loc
-        iters[ids] = it_loc
-        totals[ids] = tot_loc
-    if world > 1:
-        from .dist import allreduce_sum_
-        allreduce_sum_([hits_f, hits_b, iters, totals], device=ctx.device)
+    tallies, iters, totals = _solve_sharded(ctx, d_scene, d_em, todo, n_once, active, table, max_iters=max_iters,
+                                            min_iters=min_iters, interval=interval if schedule == "gpu" else 1,
+                                            tol_mode=tol_mode, tol=tol, emit_sid=emit_sid, min_sid=min_sid)
+    hits_f, hits_b = tallies[:, :n_surf], tallies[:, n_surf:]
     elapsed = time.time() - t0
 
     label = "builtin" if use_bvh else "off"
@@ -269,36 +354,17 @@ def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepar
     if n_surf <= 1:                                                                    # main.py:1998-1999
         return result
 
-    ctx = _native.Context.for_device()
+    ctx = _context()
     d_scene = solver.get_device_scene(use_bvh=use_bvh, ctx=ctx)
     d_em = solver.get_device_emitters(samples=samples, rays=rays, flip_faces=False, ctx=ctx)
     t0 = time.time()
     active = _surface_masks(emitters, centers, extents)
-    rank, world = _dist_env()
     weights = [float(em.n_cells * rays) for em in emitters]
-    mine = _shard(list(range(n_surf)), weights, rank, world)
-    ids = np.asarray(mine, np.int32)
+    n_once = [int(em.n_cells * rays) for em in emitters]
     table = _rotation_table(seed, n_surf, max_iters)
-    solve = _native.Solve(ctx, d_scene.native, d_em.native, ids, active[ids] if len(mine) else np.zeros((0, n_surf), np.uint8),
-                          table, ids.copy(), max_iters=max_iters, min_iters=min_iters,
-                          interval=interval if schedule == "gpu" else 1, tol_mode=tol_mode, tol=tol,
-                          sky=True, discrete=discrete)
-    try:
-        _run_solve(solve, min_iters, max_iters)
-        c_loc, it_loc, tot_loc = solve.read_sky()
-    finally:
-        solve.close()
-    nb = 145 if discrete else 1
-    counts = np.zeros((n_surf, nb), np.int64)
-    iters = np.zeros(n_surf, np.int64)
-    totals = np.zeros(n_surf, np.int64)
-    if len(mine):
-        counts[ids] = c_loc
-        iters[ids] = it_loc
-        totals[ids] = tot_loc
-    if world > 1:
-        from .dist import allreduce_sum_
-        allreduce_sum_([counts, iters, totals], device=ctx.device)
+    counts, iters, totals = _solve_sharded(ctx, d_scene, d_em, list(range(n_surf)), n_once, active, table, max_iters=max_iters,
+                                           min_iters=min_iters, interval=interval if schedule == "gpu" else 1,
+                                           tol_mode=tol_mode, tol=tol, sky=True, discrete=discrete)
     elapsed = time.time() - t0
 
     label = "builtin" if use_bvh else "off"

@@ -1,0 +1,148 @@
+"""Host-side logic of the product (no GPU): preparation, masks, rotations, shard planning, JSON I/O, params --
+each against the oracle / the reference-generated golden vectors."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from raystrack_b200 import MatrixParams, SkyParams, synthetic
+from raystrack_b200 import io as rio
+from raystrack_b200 import main as M
+from raystrack_b200 import prepared as P
+
+
+@pytest.mark.parametrize("tag,flip", [("tilted", False), ("tiltedflip", True), ("canyon", False)])
+def test_emitter_preparation_matches_reference(stage, tag, flip):
+    meshes = synthetic.street_canyon() if tag == "canyon" else synthetic.tilted_pair()
+    for i, em in enumerate(P.prepare_emitters(meshes, samples=16, rays=8, flip_faces=flip)):
+        for f in ("tri_a", "tri_e1", "tri_e2", "tri_u", "tri_v", "tri_n", "tri_origin_eps", "cdf", "plane_origin", "plane_normal"):
+            assert np.array_equal(getattr(em, f), stage[f"em_{tag}_{i}_{f}"]), (tag, i, f)
+        sc = stage[f"em_{tag}_{i}_scalars"]
+        assert (sc[0], sc[1], bool(sc[2]), int(sc[3])) == (em.total_area, em.plane_tol, em.plane_is_planar, em.g)
+
+
+def test_vectorised_frames_equal_per_triangle_frames():
+    rng = np.random.default_rng(3)
+    n = rng.normal(size=(5000, 3)).astype(np.float32)
+    n = (n / np.linalg.norm(n, axis=1, keepdims=True)).astype(np.float32)
+    n[:5] = [[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, 0, 0], [0, 0, 0]]
+    u, v = P._triangle_frames(n)
+    ou, ov = O.triangle_frames(n)
+    assert np.array_equal(u, ou) and np.array_equal(v, ov)
+
+
+def test_scene_matches_oracle_in_mesh_order():
+    meshes = synthetic.urban_block(3, 4, 8, 0)
+    mine = P.prepare_scene(meshes, use_bvh=True)
+    ref = O.prepare_scene(meshes, use_bvh=False)
+    for f in ("v0", "e1", "e2", "normals", "sid"):
+        assert np.array_equal(getattr(mine, f), getattr(ref, f))
+    assert mine.use_bvh and mine.bb_min is None
+
+
+def test_host_halton_properties_match_reference(stage):
+    em = P.prepare_emitters(synthetic.street_canyon(), samples=16, rays=8, flip_faces=False)[0]
+    assert em.g == 26
+    assert np.array_equal(em.u_grid, stage["grid_u_26"]) and np.array_equal(em.v_grid, stage["grid_v_26"])
+    n = em.n_cells * 8
+    for r, name in enumerate(("halton_tri", "halton_u", "halton_v", "halton_r1", "halton_r2")):
+        assert np.array_equal(getattr(em, name)[:4096], stage["halton_dims_head"][r][:min(n, 4096)])
+
+
+def test_surface_masks_and_receivers_match_oracle():
+    for meshes in (synthetic.urban_block(3, 4, 8, 0), synthetic.street_canyon(), synthetic.tilted_pair()):
+        ps = P.PreparedSolver(meshes)
+        ems = ps.get_emitters(samples=4, rays=8, flip_faces=False)
+        c, e = ps.get_mesh_bounds()
+        oc, oe = O.mesh_bounds(meshes)
+        assert np.array_equal(c, oc) and np.array_equal(e, oe)
+        masks = M._surface_masks(ems, c, e)
+        oems = O.prepare_emitters(meshes, 4, 8, False)
+        for i in range(len(meshes)):
+            assert np.array_equal(masks[i], O.surface_mask(i, oems[i], oc, oe))
+
+
+def test_rotation_table_matches_reference_rng():
+    table = M._rotation_table(7, 5, 9)
+    assert table.shape == (14, 7)
+    for i in range(5):
+        for it in range(9):
+            cpg, cpd = O.rotation(7, i, it)
+            assert np.array_equal(table[i + it, :2], cpg) and np.array_equal(table[i + it, 2:], cpd)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_plan_shards_covers_every_ray_once(world):
+    rng = np.random.default_rng(world)
+    n_once = [int(x) for x in rng.integers(2048, 200000, 60)] + [45158400, 9000000]
+    todo = [i for i in range(len(n_once)) if i % 7 != 3]
+    plans = M.plan_shards(todo, n_once, world)
+    assert len(plans) == world
+    cover = {}
+    for r, plan in enumerate(plans):
+        shared_part = [j for j in plan if j[3]]
+        assert plan[: len(shared_part)] == shared_part            # shared jobs first ...
+        assert [j[0] for j in shared_part] == [j[0] for j in plans[0] if j[3]]   # ... same order on every rank
+        assert len({j[0] for j in plan}) == len(plan)              # an emitter appears once per rank
+        for i, b, e, shared in plan:
+            assert 0 <= b <= e <= n_once[i]
+            assert b % M.TILE_RAYS == 0
+            cover.setdefault(i, []).append((b, e))
+    assert sorted(cover) == sorted(todo)
+    for i, parts in cover.items():
+        parts.sort()
+        assert parts[0][0] == 0 and parts[-1][1] == n_once[i]
+        assert all(parts[k][1] == parts[k + 1][0] for k in range(len(parts) - 1))
+    loads = [sum(e - b for _, b, e, _ in plan) for plan in plans]
+    assert max(loads) <= 1.05 * (sum(loads) / world) + 250000
+
+
+def test_select_bvh_and_errors():
+    assert M._select_bvh("auto", 511) is False and M._select_bvh("auto", 512) is True
+    assert M._select_bvh("builtin", 1) is True and M._select_bvh("off", 10 ** 6) is False and M._select_bvh(None, 600) is True
+    with pytest.raises(ValueError):
+        M._select_bvh("fast", 10)
+    with pytest.raises(TypeError):
+        M._ensure_prepared([], object())
+
+
+def test_params_roundtrip_and_defaults():
+    p = MatrixParams()
+    assert (p.samples, p.rays, p.seed, p.bvh, p.device, p.max_iters, p.tol, p.tol_mode, p.min_iters, p.convergence_interval,
+            p.reciprocity, p.enforce_reciprocity_rowsum, p.flip_faces) == (16, 128, 1, "auto", "auto", 100, 1e-4, "stderr", 5, 1, True, False, False)
+    assert MatrixParams.from_dict(p.as_dict()) == p
+    s = SkyParams(discrete=True)
+    assert SkyParams.from_dict(s.as_dict()) == s and "reciprocity" not in s.as_dict()
+
+
+def test_save_vf_matrix_json(tmp_path):
+    vf = {"b": {"a_front": 0.25, "a_back": 0.5, "c_front": 0.0}, "a": {"b_front": np.float64(0.125)}}
+    path = rio.save_vf_matrix_json(vf, str(tmp_path / "sub" / "out"))
+    assert path.endswith("out.json")
+    text = open(path).read()
+    assert text == json.dumps({"a": {"b_front": 0.125}, "b": {"a_back": 0.5, "a_front": 0.25}}, indent=2, sort_keys=True)
+    assert rio.load_vf_matrix_json(path) == {"a": {"b_front": 0.125}, "b": {"a_back": 0.5, "a_front": 0.25}}
+    path2 = rio.save_vf_matrix_json([vf, {"b": {"d_back": 1.0}}], str(tmp_path / "m.json"), strip_dir=True)
+    assert json.load(open(path2)) == {"a": {"b": 0.125}, "b": {"a": 0.75, "d": 1.0}}
+    with pytest.raises(TypeError):
+        rio.save_vf_matrix_json({"a": {"b": "x"}}, str(tmp_path / "bad.json"))
+    with pytest.raises(TypeError):
+        rio.save_vf_matrix_json(3, str(tmp_path / "bad.json"))
+
+
+def test_meshes_json_roundtrip(tmp_path):
+    meshes = synthetic.street_canyon()
+    path = rio.save_meshes_json(meshes, str(tmp_path / "geo"))
+    back = rio.load_meshes_json(path)
+    assert [m[0] for m in back] == [m[0] for m in meshes]
+    assert all(np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) for a, b in zip(meshes, back))
+
+
+def test_reciprocity_write_back_split():
+    from raystrack_b200 import reciprocity as R
+    res = {"a": {"b_front": 0.2, "b_back": 0.2}, "b": {"a_back": 0.1}}
+    Fp = np.array([[0.0, 0.8], [0.3, 0.0]])
+    R._write_back(res, ["a", "b"], Fp)
+    assert res["a"] == {"b_front": 0.4, "b_back": 0.4} and res["b"] == {"a_back": pytest.approx(0.3)}
+    assert np.array_equal(R._totals_matrix(res, ["a", "b"]), np.array([[0.0, 0.8], [0.3, 0.0]]))
