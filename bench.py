@@ -1,0 +1,372 @@
+#!/usr/bin/env python3
+"""Benchmark of the Monte-Carlo view-factor hot path on the synthetic 1M-triangle urban scene (BASELINE.json
+config #5, SURVEY.md 8d "C5").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One *step* = one Monte-Carlo iteration of every emitter of the scene: 2001 emitters, 239 026 176 rays, each ray
+generated (QMC sampler), traced to its closest hit through the wide BVH and tallied per receiver x {front, back},
+followed by the on-device statistics/convergence pass.  Prints ONE JSON line (rank 0).
+
+  value     closest-hit Grays/s of the whole job, inputs resident in HBM, timed with CUDA events on the launching
+            stream, max over ranks; L2 is flushed between timed steps
+  e2e       the same metric through the public API ``view_factor_matrix`` (C ABI underneath) with HOST buffers:
+            scene + emitter upload, GPU BVH build, one iteration, tally download and result assembly per step
+  roofline  memory roofline of the dominant kernel (rsk_trace_kernel<matrix,bvh>): algorithmic bytes per ray
+            (reference data layout, counted by the oracle's instrumented replay) x rays / kernel time
+  cpu_baseline / --impl reference: the CPU oracle port of the reference's Numba kernels (oracle/), all host threads,
+            on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "closest-hit Grays/s (1M-triangle urban scene)"
+UNIT = "Grays/s"
+WORKLOAD = "C5 synthetic urban block: 2001 meshes, 1,026,048 triangles, samples=4 rays=64 (239,026,176 rays/iteration)"
+SAMPLE_STRIDE = 16          # CPU sample: every 16th emitter (126 emitters incl. the ground) ...
+SAMPLE_RAYS = 16384         # ... first 16384 rays of each  (= 2,064,384 rays per CPU step)
+FALLBACK_BYTES_PER_RAY = 5400.0   # SURVEY.md 8d, used only if the live replay is not run (N>1) and no file exists
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, device: int):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(int(r[0]))
+                mx = max(mx, int(r[1]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 2), ("hw_thermal_slowdown", 3), ("sw_thermal_slowdown", 4), ("sw_power_cap", 5)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene(side: int):
+    from raystrack_b200 import synthetic
+    return synthetic.urban_block(side)
+
+
+# --------------------------------------------------------------------------------------------- CPU (oracle) legs
+
+class CpuSample:
+    """Bounded sample of the workload for the CPU oracle: SAMPLE_RAYS first rays of every SAMPLE_STRIDE-th emitter."""
+
+    def __init__(self, meshes, samples, rays, seed):
+        from oracle import oracle as O
+        self.O = O
+        t = time.time()
+        self.solver = O.OracleSolver(meshes)
+        self.scene = self.solver.scene(True)                       # reference BVH (utils/bvh.py), built in Python
+        self.ems = self.solver.emitters(samples, rays, False)
+        self.centers, self.extents = self.solver.bounds()
+        self.emit = list(range(0, len(meshes), SAMPLE_STRIDE))
+        self.counts = [min(SAMPLE_RAYS, self.ems[i].n_rays_once) for i in self.emit]
+        O.halton_dims(max(self.counts))
+        self.masks = [O.surface_mask(i, self.ems[i], self.centers, self.extents) for i in self.emit]
+        self.seed = seed
+        self.prep_s = time.time() - t
+        self.rays_per_step = int(sum(self.counts))
+
+    def step(self, itr: int, stats=None, keep=None):
+        O = self.O
+        for i, n, act in zip(self.emit, self.counts, self.masks):
+            cpg, cpd = O.rotation(self.seed, i, itr)
+            o, d = O.build_rays(self.ems[i], cpg, cpd, count=n)
+            hs, fr = O.trace_firsthit(self.scene, o, d, act, i, 0, stats=stats)
+            if keep is not None:
+                keep[i] = (hs, fr)
+
+    def describe(self):
+        return (f"every {SAMPLE_STRIDE}th emitter ({len(self.emit)} incl. ground), first {SAMPLE_RAYS} rays of each = "
+                f"{self.rays_per_step} rays/step, reference BVH (median split, leaf 8), closest hit")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    meshes = build_scene(args.side)
+    cpu = CpuSample(meshes, args.samples, args.rays, args.seed)
+    cores = O.num_threads()
+    log(f"[reference] oracle prep {cpu.prep_s:.1f}s, {cores} threads, {cpu.rays_per_step} rays/step")
+    for w in range(args.warmup):
+        cpu.step(w)
+    t = time.perf_counter()
+    for k in range(args.steps):
+        cpu.step(args.warmup + k)
+    dt = time.perf_counter() - t
+    v = cpu.rays_per_step * args.steps / dt / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 (f64 ray generation)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": cpu.describe()},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu.describe()},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+
+def run_ours(args):
+    import torch
+    from raystrack_b200 import MatrixParams, _native, dist as D, main as M, view_factor_matrix
+    from raystrack_b200.prepared import PreparedSolver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, world = D.init_from_env("nccl") if world > 1 else (0, 1)
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if _native.device_count() <= 0:
+        raise RuntimeError("bench.py needs a B200: no CUDA device visible")
+    ctx = M._context() if world > 1 else _native.Context.for_device(local, torch.cuda.current_stream(local).cuda_stream)
+
+    meshes = build_scene(args.side)
+    ps = PreparedSolver(meshes)
+    t = time.time()
+    ems = ps.get_emitters(samples=args.samples, rays=args.rays, flip_faces=False)
+    ps.get_scene(use_bvh=True)
+    prep_s = time.time() - t
+    t = time.time()
+    sc = ps.get_device_scene(use_bvh=True, ctx=ctx)
+    em = ps.get_device_emitters(samples=args.samples, rays=args.rays, flip_faces=False, ctx=ctx)
+    upload_s = time.time() - t
+    info = sc.info()
+    n = len(meshes)
+    centers, extents = ps.get_mesh_bounds()
+    active = M._surface_masks(ems, centers, extents)
+    n_once = [int(e.n_cells * args.rays) for e in ems]
+    rays_per_step = int(sum(n_once))
+    total_iters = args.warmup + 2 * args.steps + 2
+    table = M._rotation_table(args.seed, n, total_iters)
+    plans = M.plan_shards(list(range(n)), n_once, world)
+    plan = plans[rank]
+    ids = np.asarray([j[0] for j in plan], np.int32)
+    ranges = np.asarray([[j[1], j[2]] for j in plan], np.int64).reshape(-1, 2)
+    n_shared = sum(1 for j in plan if j[3])
+    solve = _native.Solve(ctx, sc.native, em.native, ids, active[ids], table, ids.copy(), max_iters=total_iters,
+                          min_iters=total_iters, interval=1, tol_mode="stderr", tol=0.0,
+                          emit_sid=ids, min_sid=np.zeros(len(ids), np.int32), ray_range=ranges)
+    tally = D.device_int64_view(*solve.device_iter_tallies(), n_jobs=n_shared, device=local) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local}")     # > 126 MB L2
+
+    def one_step(trace_only_timer=None):
+        if trace_only_timer is not None:
+            ctx.timer_start()
+        solve.enqueue_trace()
+        if trace_only_timer is not None:
+            trace_only_timer.append(ctx.timer_stop())
+        if tally is not None:
+            D.all_reduce_device_(tally, local)
+        solve.enqueue_fold()
+
+    for _ in range(max(args.warmup, 3) if args.warmup else 0):
+        one_step()
+    ctx.synchronize()
+    if world > 1:
+        D.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    step_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)                      # L2 flush between timed iterations (not timed)
+        torch.cuda.synchronize()
+        ctx.timer_start()
+        one_step()
+        step_ms.append(ctx.timer_stop())
+    launches = ctx.launch_count() - launches0
+    torch.cuda.synchronize()
+    if world > 1:
+        D.barrier()
+    total_ms = D.max_over_ranks(float(sum(step_ms)), local)
+    value = rays_per_step * args.steps / (total_ms * 1e-3) / 1e9
+
+    # dominant kernel alone (same stream, CUDA events around the trace launch only)
+    trace_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        one_step(trace_ms)
+    ctx.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    my_rays = int(sum(j[2] - j[1] for j in plan))
+    trace_avg_ms = float(np.mean(trace_ms))
+    solve.close()
+
+    # ---- e2e through the public API with host buffers: the BASELINE config-#5 call (fixed iteration count so every
+    # implementation traces identical rays), device copies rebuilt from the host arrays inside every timed call
+    ps2 = PreparedSolver(meshes)          # shares nothing on the device with `ps`; host preparation is cached
+    ps2._scene_cache, ps2._emitter_cache, ps2._mesh_bounds_cache, ps2._emitter_pack_cache = \
+        ps._scene_cache, ps._emitter_cache, ps._mesh_bounds_cache, ps._emitter_pack_cache
+    old_log = M._log
+    M._log = lambda msg: None
+
+    def timed_call(iters):
+        prm = MatrixParams(samples=args.samples, rays=args.rays, seed=args.seed, bvh="builtin", reciprocity=False,
+                           max_iters=iters, min_iters=iters, tol=0.0)
+        ps2.clear_device_cache()
+        torch.cuda.synchronize()
+        if world > 1:
+            D.barrier()
+        t0 = time.perf_counter()
+        view_factor_matrix(meshes, prm, prepared=ps2)
+        torch.cuda.synchronize()
+        return D.max_over_ranks(time.perf_counter() - t0, local)
+
+    e2e_times, e2e_single = [], []
+    try:
+        if args.e2e_steps > 0:
+            timed_call(1)                                       # warm-up of the public path
+            e2e_times = [timed_call(args.e2e_iters) for _ in range(args.e2e_steps)]
+            e2e_single = [timed_call(1) for _ in range(3)]
+    finally:
+        M._log = old_log
+        ps2.clear_device_cache()
+    e2e_value = rays_per_step * args.e2e_iters / float(np.mean(e2e_times)) / 1e9 if e2e_times else None
+    e2e_single_value = rays_per_step / float(np.mean(e2e_single)) / 1e9 if e2e_single else None
+    n_tri = ps.total_faces
+    h2d = n_tri * 52 + n_tri * 80 + n * n + table.nbytes       # scene arrays + emitter arrays + surf_active + rotations
+    d2h = len(ids) * 2 * n * 8 + len(ids) * 12                 # int64 tally block + iteration/ray counters
+
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (f64 ray generation)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "step": "one Monte-Carlo iteration of all 2001 emitters", "rays_per_step": rays_per_step,
+                       "bvh": f"GPU LBVH -> 8-wide quantised, {info['n_nodes']} nodes, depth {info['depth']}, built in {info['build_us']/1e3:.1f} ms",
+                       "l2": "flushed between timed steps (256 MB write)", "sharding": f"emitters over {world} GPU(s), {n_shared} ray-split",
+                       "host_prep_s": round(prep_s, 3), "upload_build_s": round(upload_s, 3)},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "call": f"view_factor_matrix(meshes, MatrixParams(samples=4, rays=64, bvh='builtin', reciprocity=False, "
+                            f"min_iters=max_iters={args.e2e_iters}, tol=0)): upload of scene+emitters, GPU BVH build, "
+                            f"{args.e2e_iters} iterations, tally download, result dict",
+                    "ms_per_step": 1e3 * float(np.mean(e2e_times)) if e2e_times else None,
+                    "single_iteration_call": {"value": e2e_single_value, "unit": UNIT,
+                                              "ms": 1e3 * float(np.mean(e2e_single)) if e2e_single else None}}}
+
+    # ---- CPU oracle: baseline + algorithmic bytes per ray + per-ray parity on the sample (N=1 only)
+    bpr_file = ROOT / "profiles" / "c5_bytes_per_ray.json"
+    bytes_per_ray, bpr_src = FALLBACK_BYTES_PER_RAY, "SURVEY.md 8d"
+    if bpr_file.exists():
+        bytes_per_ray = float(json.loads(bpr_file.read_text())["bytes_per_ray"])
+        bpr_src = "profiles/c5_bytes_per_ray.json"
+    if world == 1 and not args.no_cpu:
+        from oracle import oracle as O
+        cpu = CpuSample(meshes, args.samples, args.rays, args.seed)
+        cpu.step(0)                                              # warm-up
+        stats = np.zeros(4, np.int64)
+        keep = {}
+        t = time.perf_counter()
+        reps = 0
+        while reps < 3 or (time.perf_counter() - t < 10.0 and reps < 12):
+            cpu.step(1 + reps, stats=stats if reps == 0 else None, keep=keep if reps == 0 else None)
+            reps += 1
+        dt = time.perf_counter() - t
+        cpu_v = cpu.rays_per_step * reps / dt / 1e9
+        n_in, n_leaf, n_tri_t, n_skip = (stats / cpu.rays_per_step).tolist()
+        bytes_per_ray = 60 * n_in + 8 * n_leaf + 53 * n_tri_t + 5 * n_skip
+        bpr_src = "oracle replay on the CPU sample (this run)"
+        line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "sample": cpu.describe(),
+                                "visits_per_ray": {"inner": n_in, "leaf": n_leaf, "tri": n_tri_t, "skipped": n_skip}}
+        # per-ray parity of the GPU path on the same sample (iteration 1), through the C-ABI per-ray hook
+        agree = tot = 0
+        for i, cnt in zip(cpu.emit, cpu.counts):
+            cpg, cpd = O.rotation(args.seed, i, 1)
+            _, _, hit, front = _native.trace_rays(ctx, sc.native, em.native, i, active[i], i, 0, np.concatenate([cpg, cpd]),
+                                                  mode=0, n_rays=cnt, want_rays=False)
+            hs, fr = keep[i]
+            agree += int(np.sum((hit == hs) & (front == fr)))
+            tot += cnt
+        line["parity"] = {"per_ray_agreement": agree / tot, "rays_compared": tot}
+    peak, peak_src = measured_peaks()
+    achieved = my_rays * bytes_per_ray / (trace_avg_ms * 1e-3) / 1e9
+    line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "kernel": "rsk_trace_kernel<matrix,bvh>", "kernel_ms": trace_avg_ms, "bytes_per_ray": bytes_per_ray,
+                        "bytes_per_ray_source": bpr_src, "peak_source": peak_src,
+                        "note": "algorithmic bytes of the reference layout; the 80 MB scene is L2-resident, so frac > 1 of HBM is expected"}
+    traffic_file = ROOT / "profiles" / "c5_trace_dram_bytes.json"
+    if traffic_file.exists():
+        line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch")
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--side", type=int, default=20, help="buildings per side (20 = the 1M-triangle C5 scene)")
+    ap.add_argument("--samples", type=int, default=4)
+    ap.add_argument("--rays", type=int, default=64)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=2, help="timed public-API calls (0 = skip the e2e leg)")
+    ap.add_argument("--e2e-iters", type=int, default=40, help="iterations per public-API call (C5: min_iters=max_iters=40)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle legs (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

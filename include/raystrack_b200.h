@@ -142,8 +142,10 @@ int rsk_matrix_step(rsk_solve *solve, int32_t n_iters, int32_t *n_active);
  * stderr_front/back: float64[n_local][n_surf] replicate standard errors (may be NULL). */
 int rsk_matrix_read(rsk_solve *solve, int64_t *hits_front, int64_t *hits_back, int32_t *iters,
                     int64_t *total_rays, double *stderr_front, double *stderr_back);
-/* Device pointer + element count of the int64 tally block [n_local][2][n_surf] (front rows then back rows per
- * emitter) for collectives issued by the caller (torch.distributed / NCCL). */
+/* The whole tally block in one contiguous copy: matrix solves int64[n_local][n_surf][2] ((front, back) pair per
+ * receiver), sky solves int64[n_local][145 or 1]; what the host driver uses. */
+int rsk_solve_read_block(rsk_solve *solve, int64_t *tallies, int32_t *iters, int64_t *total_rays);
+/* Device pointer + element count of the int64 tally block [n_local][n_surf][2] ((front, back) per receiver) for collectives issued by the caller (torch.distributed / NCCL). */
 int rsk_matrix_device_tallies(rsk_solve *solve, void **device_ptr, int64_t *n_elements);
 
 /* ------------------------------------------------------------------------------------------- sky solve

@@ -27,7 +27,7 @@ EXPORTS = (
     "rsk_scene_create", "rsk_scene_destroy", "rsk_scene_info", "rsk_scene_download_bvh",
     "rsk_emitters_create", "rsk_emitters_destroy", "rsk_emitters_download_tables",
     "rsk_trace_rays",
-    "rsk_matrix_begin", "rsk_matrix_step", "rsk_matrix_read", "rsk_matrix_device_tallies",
+    "rsk_matrix_begin", "rsk_matrix_step", "rsk_matrix_read", "rsk_solve_read_block", "rsk_matrix_device_tallies",
     "rsk_sky_begin", "rsk_sky_step", "rsk_sky_read",
     "rsk_solve_enqueue_trace", "rsk_solve_enqueue_fold", "rsk_solve_poll", "rsk_solve_device_iter_tallies",
     "rsk_solve_destroy", "rsk_solve_rays_traced", "rsk_reciprocity_rowsum",
@@ -284,6 +284,15 @@ class Solve:
         sb = np.zeros((self.n_local, ns), np.float64) if want_stderr else None
         check(self.ctx.lib.rsk_matrix_read(self.handle, ptr(hf), ptr(hb), ptr(iters), ptr(total), ptr(sf), ptr(sb)), "rsk_matrix_read")
         return hf, hb, iters, total, sf, sb
+
+    def read_block(self):
+        """(tallies int64 [n_local, n_hist], iterations, total rays) in one contiguous device-to-host copy."""
+        nh = (145 if self.discrete else 1) if self.sky else 2 * self.scene.n_surf
+        tallies = np.empty((self.n_local, nh), np.int64)
+        iters = np.zeros(self.n_local, np.int32)
+        total = np.zeros(self.n_local, np.int64)
+        check(self.ctx.lib.rsk_solve_read_block(self.handle, ptr(tallies), ptr(iters), ptr(total)), "rsk_solve_read_block")
+        return tallies, iters, total
 
     def read_sky(self):
         nb = 145 if self.discrete else 1

@@ -4,6 +4,7 @@
 #include "rsk_stats.cuh"
 
 static thread_local char g_error[1024] = "";
+thread_local cudaStream_t rsk_tl_stream = nullptr;
 
 void rsk_set_error(const char *fmt, ...) {
     va_list ap;
@@ -54,16 +55,24 @@ extern "C" int rsk_ctx_create(int device, void *stream, rsk_ctx **out) {
     }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = ctx;
     return RSK_OK;
 }
 
 extern "C" int rsk_ctx_destroy(rsk_ctx *ctx) {
     if (!ctx) return RSK_OK;
-    cudaSetDevice(ctx->device);
+    RskScope scope(ctx);
+    rsk_dev_free(ctx->halton);
+    rsk_dev_free(ctx->grid);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->halton);
-    cudaFree(ctx->grid);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -108,6 +117,18 @@ extern "C" int rsk_ctx_device_info(rsk_ctx *ctx, char *name, int64_t *info) {
 
 // ----------------------------------------------------------------------------- scene
 
+// pack the reference's SoA scene arrays into traversal records on the device
+__global__ void rsk_pack_scene_kernel(const float *v0, const float *e1, const float *e2, const float *nrm, const int32_t *sid,
+                                      int64_t n, float4 *tri, float4 *nrm4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float sbits = __int_as_float(sid[i]);
+    tri[3 * i] = make_float4(v0[3 * i], v0[3 * i + 1], v0[3 * i + 2], sbits);
+    tri[3 * i + 1] = make_float4(e1[3 * i], e1[3 * i + 1], e1[3 * i + 2], 0.f);
+    tri[3 * i + 2] = make_float4(e2[3 * i], e2[3 * i + 1], e2[3 * i + 2], 0.f);
+    nrm4[i] = make_float4(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2], sbits);
+}
+
 extern "C" int rsk_scene_create(rsk_ctx *ctx, const float *v0, const float *e1, const float *e2, const float *normals,
                                 const int32_t *sid, int64_t n_tri, int32_t n_surf, int32_t use_bvh, rsk_scene **out) {
     RSK_REQUIRE(ctx && out, "rsk_scene_create: null context/output");
@@ -115,46 +136,45 @@ extern "C" int rsk_scene_create(rsk_ctx *ctx, const float *v0, const float *e1, 
     RSK_REQUIRE(n_tri == 0 || (v0 && e1 && e2 && normals && sid), "rsk_scene_create: null arrays");
     RSK_REQUIRE(n_tri < (1ll << 30), "rsk_scene_create: too many triangles");
     *out = nullptr;
-    RSK_CUDA(cudaSetDevice(ctx->device));
-    // pack (v0,sid) (e1,0) (e2,0) and (normal,sid) records in input order
-    std::vector<float4> tri((size_t)n_tri * 3), nrm((size_t)n_tri);
-    for (int64_t i = 0; i < n_tri; ++i) {
-        RSK_REQUIRE(sid[i] >= 0 && sid[i] < n_surf, "rsk_scene_create: sid out of range");
-        float sbits;
-        memcpy(&sbits, &sid[i], 4);
-        tri[3 * i] = make_float4(v0[3 * i], v0[3 * i + 1], v0[3 * i + 2], sbits);
-        tri[3 * i + 1] = make_float4(e1[3 * i], e1[3 * i + 1], e1[3 * i + 2], 0.f);
-        tri[3 * i + 2] = make_float4(e2[3 * i], e2[3 * i + 1], e2[3 * i + 2], 0.f);
-        nrm[i] = make_float4(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2], sbits);
-    }
+    RskScope scope(ctx);
+    for (int64_t i = 0; i < n_tri; ++i) RSK_REQUIRE(sid[i] >= 0 && sid[i] < n_surf, "rsk_scene_create: sid out of range");
     rsk_scene *sc = new rsk_scene();
     sc->ctx = ctx;
     sc->n_tri = n_tri;
     sc->n_surf = n_surf;
     sc->use_bvh = (use_bvh && n_tri > 0) ? 1 : 0;
-    float4 *d_tri = nullptr, *d_nrm = nullptr;
-    int rc = rsk_dev_alloc(&d_tri, (size_t)n_tri * 3);
+    // the caller's five arrays go to the device as they are; records are packed there
+    float *raw = nullptr; int32_t *d_sid = nullptr; float4 *d_tri = nullptr, *d_nrm = nullptr;
+    auto fail = [&](int code) { rsk_dev_free(raw); rsk_dev_free(d_sid); rsk_dev_free(d_tri); rsk_dev_free(d_nrm); delete sc; return code; };
+    int rc = rsk_dev_alloc(&raw, (size_t)n_tri * 12);
+    if (rc == RSK_OK) rc = rsk_dev_alloc(&d_sid, (size_t)n_tri);
+    if (rc == RSK_OK) rc = rsk_dev_alloc(&d_tri, (size_t)n_tri * 3);
     if (rc == RSK_OK) rc = rsk_dev_alloc(&d_nrm, (size_t)n_tri);
-    if (rc != RSK_OK) { cudaFree(d_tri); cudaFree(d_nrm); delete sc; return rc; }
-    cudaError_t e = cudaSuccess;
+    if (rc != RSK_OK) return fail(rc);
     if (n_tri > 0) {
-        e = cudaMemcpyAsync(d_tri, tri.data(), tri.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_nrm, nrm.data(), nrm.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        const size_t b3 = (size_t)n_tri * 3 * sizeof(float);
+        const float *src[4] = {v0, e1, e2, normals};
+        cudaError_t e = cudaSuccess;
+        for (int k = 0; k < 4 && e == cudaSuccess; ++k)
+            e = cudaMemcpyAsync(raw + (size_t)k * n_tri * 3, src[k], b3, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_sid, sid, (size_t)n_tri * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { rsk_set_error("scene upload failed: %s", cudaGetErrorString(e)); return fail(RSK_ERR_CUDA); }
+        rsk_pack_scene_kernel<<<rsk_blocks(n_tri, 256), 256, 0, ctx->stream>>>(raw, raw + (size_t)n_tri * 3, raw + (size_t)n_tri * 6,
+                                                                             raw + (size_t)n_tri * 9, d_sid, n_tri, d_tri, d_nrm);
+        ctx->launches++;
     }
-    if (e != cudaSuccess) {
-        rsk_set_error("scene upload failed: %s", cudaGetErrorString(e));
-        cudaFree(d_tri); cudaFree(d_nrm); delete sc;
-        return RSK_ERR_CUDA;
-    }
+    rsk_dev_free(raw); raw = nullptr;
+    rsk_dev_free(d_sid); d_sid = nullptr;
     if (sc->use_bvh) {
         rc = rsk_bvh_build(sc, d_tri, d_nrm);
-        cudaFree(d_tri);
-        cudaFree(d_nrm);
+        rsk_dev_free(d_tri);
+        rsk_dev_free(d_nrm);
         if (rc != RSK_OK) { rsk_scene_destroy(sc); return rc; }
     } else {
         sc->tri = d_tri;
         sc->nrm = d_nrm;
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { rsk_set_error("scene upload failed: %s", cudaGetErrorString(e)); rsk_scene_destroy(sc); return RSK_ERR_CUDA; }
     }
     *out = sc;
     return RSK_OK;
@@ -162,12 +182,11 @@ extern "C" int rsk_scene_create(rsk_ctx *ctx, const float *v0, const float *e1, 
 
 extern "C" int rsk_scene_destroy(rsk_scene *sc) {
     if (!sc) return RSK_OK;
-    cudaSetDevice(sc->ctx->device);
-    cudaStreamSynchronize(sc->ctx->stream);
-    cudaFree(sc->tri);
-    cudaFree(sc->nrm);
-    cudaFree(sc->nodes);
-    cudaFree(sc->tri_index);
+    RskScope scope(sc->ctx);
+    rsk_dev_free(sc->tri);
+    rsk_dev_free(sc->nrm);
+    rsk_dev_free(sc->nodes);
+    rsk_dev_free(sc->tri_index);
     delete sc;
     return RSK_OK;
 }
@@ -181,7 +200,7 @@ extern "C" int rsk_scene_info(rsk_scene *sc, int64_t *info) {
 
 extern "C" int rsk_scene_download_bvh(rsk_scene *sc, void *nodes, int32_t *tri_index) {
     RSK_REQUIRE(sc && sc->use_bvh, "rsk_scene_download_bvh: scene has no BVH");
-    RSK_CUDA(cudaSetDevice(sc->ctx->device));
+    RskScope scope(sc->ctx);
     RSK_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     if (nodes) RSK_CUDA(cudaMemcpy(nodes, sc->nodes, sc->n_nodes * sizeof(WideNode), cudaMemcpyDeviceToHost));
     if (tri_index) RSK_CUDA(cudaMemcpy(tri_index, sc->tri_index, sc->n_tri * sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -189,6 +208,17 @@ extern "C" int rsk_scene_download_bvh(rsk_scene *sc, void *nodes, int32_t *tri_i
 }
 
 // ----------------------------------------------------------------------------- emitters
+
+__global__ void rsk_pack_emitters_kernel(const float *a, const float *e1, const float *e2, const float *u, const float *v,
+                                         const float *n, const float *eps, int64_t total, float4 *rec) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    rec[5 * t + 0] = make_float4(a[3 * t], a[3 * t + 1], a[3 * t + 2], eps[t]);
+    rec[5 * t + 1] = make_float4(e1[3 * t], e1[3 * t + 1], e1[3 * t + 2], n[3 * t]);
+    rec[5 * t + 2] = make_float4(e2[3 * t], e2[3 * t + 1], e2[3 * t + 2], n[3 * t + 1]);
+    rec[5 * t + 3] = make_float4(u[3 * t], u[3 * t + 1], u[3 * t + 2], n[3 * t + 2]);
+    rec[5 * t + 4] = make_float4(v[3 * t], v[3 * t + 1], v[3 * t + 2], 0.f);
+}
 
 extern "C" int rsk_emitters_create(rsk_ctx *ctx, int32_t n_emit, const int64_t *tri_offset,
                                    const float *tri_a, const float *tri_e1, const float *tri_e2,
@@ -198,7 +228,7 @@ extern "C" int rsk_emitters_create(rsk_ctx *ctx, int32_t n_emit, const int64_t *
     RSK_REQUIRE(ctx && out && n_emit >= 0 && rays_per_cell > 0, "rsk_emitters_create: bad arguments");
     RSK_REQUIRE(n_emit == 0 || (tri_offset && g), "rsk_emitters_create: null tables");
     *out = nullptr;
-    RSK_CUDA(cudaSetDevice(ctx->device));
+    RskScope scope(ctx);
     const int64_t total = n_emit ? tri_offset[n_emit] : 0;
     RSK_REQUIRE(total < (1ll << 31), "rsk_emitters_create: too many emitter triangles");
     RSK_REQUIRE(total == 0 || (tri_a && tri_e1 && tri_e2 && tri_u && tri_v && tri_n && tri_eps && cdf), "rsk_emitters_create: null arrays");
@@ -222,28 +252,32 @@ extern "C" int rsk_emitters_create(rsk_ctx *ctx, int32_t n_emit, const int64_t *
         d.grid_off = (int32_t)off;
     }
     if (rc == RSK_OK) rc = rsk_qmc_ensure_halton(ctx, em->max_rays_once);
-    std::vector<float4> rec((size_t)total * 5);
-    for (int64_t t = 0; t < total; ++t) {
-        rec[5 * t + 0] = make_float4(tri_a[3 * t], tri_a[3 * t + 1], tri_a[3 * t + 2], tri_eps[t]);
-        rec[5 * t + 1] = make_float4(tri_e1[3 * t], tri_e1[3 * t + 1], tri_e1[3 * t + 2], tri_n[3 * t]);
-        rec[5 * t + 2] = make_float4(tri_e2[3 * t], tri_e2[3 * t + 1], tri_e2[3 * t + 2], tri_n[3 * t + 1]);
-        rec[5 * t + 3] = make_float4(tri_u[3 * t], tri_u[3 * t + 1], tri_u[3 * t + 2], tri_n[3 * t + 2]);
-        rec[5 * t + 4] = make_float4(tri_v[3 * t], tri_v[3 * t + 1], tri_v[3 * t + 2], 0.f);
-    }
-    if (rc == RSK_OK) rc = rsk_dev_alloc(&em->tri, rec.size());
+    float *raw = nullptr;
+    if (rc == RSK_OK) rc = rsk_dev_alloc(&raw, (size_t)total * 19);
+    if (rc == RSK_OK) rc = rsk_dev_alloc(&em->tri, (size_t)total * 5);
     if (rc == RSK_OK) rc = rsk_dev_alloc(&em->cdf, (size_t)total);
     if (rc == RSK_OK) rc = rsk_dev_alloc(&em->desc, (size_t)n_emit);
     if (rc == RSK_OK) {
         cudaError_t e = cudaSuccess;
         if (total > 0) {
-            e = cudaMemcpyAsync(em->tri, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
+            const float *src[6] = {tri_a, tri_e1, tri_e2, tri_u, tri_v, tri_n};
+            for (int k = 0; k < 6 && e == cudaSuccess; ++k)
+                e = cudaMemcpyAsync(raw + (size_t)k * total * 3, src[k], (size_t)total * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(raw + (size_t)total * 18, tri_eps, total * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
             if (e == cudaSuccess) e = cudaMemcpyAsync(em->cdf, cdf, total * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) {
+                rsk_pack_emitters_kernel<<<rsk_blocks(total, 256), 256, 0, ctx->stream>>>(
+                    raw, raw + (size_t)total * 3, raw + (size_t)total * 6, raw + (size_t)total * 9, raw + (size_t)total * 12,
+                    raw + (size_t)total * 15, raw + (size_t)total * 18, total, em->tri);
+                ctx->launches++;
+            }
         }
         if (e == cudaSuccess && n_emit > 0)
             e = cudaMemcpyAsync(em->desc, em->h_desc.data(), n_emit * sizeof(EmitterDesc), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { rsk_set_error("emitter upload failed: %s", cudaGetErrorString(e)); rc = RSK_ERR_CUDA; }
     }
+    rsk_dev_free(raw);
     if (rc != RSK_OK) { rsk_emitters_destroy(em); return rc; }
     *out = em;
     return RSK_OK;
@@ -251,11 +285,10 @@ extern "C" int rsk_emitters_create(rsk_ctx *ctx, int32_t n_emit, const int64_t *
 
 extern "C" int rsk_emitters_destroy(rsk_emitters *em) {
     if (!em) return RSK_OK;
-    cudaSetDevice(em->ctx->device);
-    cudaStreamSynchronize(em->ctx->stream);
-    cudaFree(em->tri);
-    cudaFree(em->cdf);
-    cudaFree(em->desc);
+    RskScope scope(em->ctx);
+    rsk_dev_free(em->tri);
+    rsk_dev_free(em->cdf);
+    rsk_dev_free(em->desc);
     delete em;
     return RSK_OK;
 }
@@ -263,7 +296,7 @@ extern "C" int rsk_emitters_destroy(rsk_emitters *em) {
 extern "C" int rsk_emitters_download_tables(rsk_emitters *em, int64_t n, float *dims, int32_t g, float *grid_u, float *grid_v) {
     RSK_REQUIRE(em, "null emitters");
     rsk_ctx *ctx = em->ctx;
-    RSK_CUDA(cudaSetDevice(ctx->device));
+    RskScope scope(ctx);
     RSK_CUDA(cudaStreamSynchronize(ctx->stream));
     if (dims) {
         RSK_REQUIRE(n <= ctx->halton_cap, "rsk_emitters_download_tables: n exceeds the cached table");
@@ -312,7 +345,7 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
     const int64_t n_once = em->h_desc[emitter].n_rays_once;
     RSK_REQUIRE(first_ray >= 0 && n_rays >= 0 && first_ray + n_rays <= n_once, "rsk_trace_rays: ray range out of bounds");
     if (n_rays == 0) return RSK_OK;
-    RSK_CUDA(cudaSetDevice(ctx->device));
+    RskScope scope(ctx);
     const int nw = (scene->n_surf + 31) / 32;
     std::vector<uint32_t> mask(std::max(nw, 1));
     rsk_pack_mask(surf_active, scene->n_surf, emit_sid, min_sid, mask.data());
@@ -323,8 +356,8 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
 
     uint32_t *d_mask = nullptr; float *d_cp = nullptr; int32_t *d_ids = nullptr, *d_zero = nullptr; int64_t *d_tiles = nullptr, *d_range = nullptr;
     float *d_orig = nullptr, *d_dirs = nullptr; int32_t *d_hit = nullptr; uint8_t *d_front = nullptr;
-    auto cleanup = [&]() { cudaFree(d_mask); cudaFree(d_cp); cudaFree(d_ids); cudaFree(d_zero); cudaFree(d_tiles); cudaFree(d_range);
-                           cudaFree(d_orig); cudaFree(d_dirs); cudaFree(d_hit); cudaFree(d_front); };
+    auto cleanup = [&]() { rsk_dev_free(d_mask); rsk_dev_free(d_cp); rsk_dev_free(d_ids); rsk_dev_free(d_zero); rsk_dev_free(d_tiles); rsk_dev_free(d_range);
+                           rsk_dev_free(d_orig); rsk_dev_free(d_dirs); rsk_dev_free(d_hit); rsk_dev_free(d_front); };
     int rc = RSK_OK;
 #define T_TRY(expr) do { rc = (expr); if (rc != RSK_OK) { cleanup(); return rc; } } while (0)
 #define T_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rsk_set_error("%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); return RSK_ERR_CUDA; } } while (0)
@@ -395,7 +428,7 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
     RSK_REQUIRE(n_local == 0 || (emit_ids && surf_active && cp_table && rot_base), "solve begin: null arrays");
     RSK_REQUIRE(params->tol_mode == 0 || params->tol_mode == 1, "solve begin: tol_mode must be 0 (stderr) or 1 (delta)");
     *out = nullptr;
-    RSK_CUDA(cudaSetDevice(ctx->device));
+    RskScope scope(ctx);
     rsk_solve *s = new rsk_solve();
     s->ctx = ctx; s->scene = scene; s->em = em; s->mode = mode; s->n_local = n_local; s->discrete = discrete;
     s->p = *params;
@@ -517,7 +550,7 @@ static int rsk_solve_poll_impl(rsk_solve *s, int32_t *n_active) {
 
 static int rsk_solve_step(rsk_solve *s, int32_t n_iters, int32_t *n_active) {
     RSK_REQUIRE(s && n_iters >= 0, "solve step: bad arguments");
-    RSK_CUDA(cudaSetDevice(s->ctx->device));
+    RskScope scope(s->ctx);
     if (s->last_active > 0) {
         for (int it = 0; it < n_iters; ++it) {
             RSK_TRY(rsk_solve_enqueue_trace_impl(s));
@@ -530,20 +563,20 @@ static int rsk_solve_step(rsk_solve *s, int32_t n_iters, int32_t *n_active) {
 
 extern "C" int rsk_solve_enqueue_trace(rsk_solve *s) {
     RSK_REQUIRE(s, "null solve");
-    RSK_CUDA(cudaSetDevice(s->ctx->device));
+    RskScope scope(s->ctx);
     return rsk_solve_enqueue_trace_impl(s);
 }
 
 extern "C" int rsk_solve_enqueue_fold(rsk_solve *s) {
     RSK_REQUIRE(s, "null solve");
-    RSK_CUDA(cudaSetDevice(s->ctx->device));
+    RskScope scope(s->ctx);
     s->stepped = true;
     return rsk_solve_enqueue_fold_impl(s);
 }
 
 extern "C" int rsk_solve_poll(rsk_solve *s, int32_t *n_active) {
     RSK_REQUIRE(s, "null solve");
-    RSK_CUDA(cudaSetDevice(s->ctx->device));
+    RskScope scope(s->ctx);
     return rsk_solve_poll_impl(s, n_active);
 }
 
@@ -576,7 +609,7 @@ static int rsk_read_common(rsk_solve *s, int32_t *iters, int64_t *total_rays) {
 extern "C" int rsk_matrix_read(rsk_solve *s, int64_t *hits_front, int64_t *hits_back, int32_t *iters, int64_t *total_rays,
                                double *stderr_front, double *stderr_back) {
     RSK_REQUIRE(s && s->mode == MODE_MATRIX, "rsk_matrix_read: not a matrix solve");
-    RSK_CUDA(cudaSetDevice(s->ctx->device));
+    RskScope scope(s->ctx);
     const int ns = s->scene->n_surf;
     const size_t nh = (size_t)s->n_local * s->n_hist;
     std::vector<int32_t> h_iters(std::max(s->n_local, 1));
@@ -592,19 +625,29 @@ extern "C" int rsk_matrix_read(rsk_solve *s, int64_t *hits_front, int64_t *hits_
     for (int k = 0; k < s->n_local; ++k) {
         if (iters) iters[k] = h_iters[k];
         for (int j = 0; j < ns; ++j) {
-            if (hits_front) hits_front[(size_t)k * ns + j] = tot[(size_t)k * s->n_hist + j];
-            if (hits_back) hits_back[(size_t)k * ns + j] = tot[(size_t)k * s->n_hist + ns + j];
+            if (hits_front) hits_front[(size_t)k * ns + j] = tot[(size_t)k * s->n_hist + 2 * j];
+            if (hits_back) hits_back[(size_t)k * ns + j] = tot[(size_t)k * s->n_hist + 2 * j + 1];
             if (!m2.empty()) {
                 const int n = h_iters[k];
                 for (int side = 0; side < 2; ++side) {
                     double *dst = side ? stderr_back : stderr_front;
                     if (!dst) continue;
-                    const double v = m2[(size_t)k * s->n_hist + side * ns + j];
+                    const double v = m2[(size_t)k * s->n_hist + 2 * j + side];
                     dst[(size_t)k * ns + j] = n > 1 ? sqrt(std::max(v / (n - 1), 0.0) / n) : INFINITY;   // main.py:1911-1916
                 }
             }
         }
     }
+    return RSK_OK;
+}
+
+extern "C" int rsk_solve_read_block(rsk_solve *s, int64_t *tallies, int32_t *iters, int64_t *total_rays) {
+    RSK_REQUIRE(s, "rsk_solve_read_block: null solve");
+    RskScope scope(s->ctx);
+    RSK_TRY(rsk_read_common(s, iters, total_rays));
+    const size_t nh = (size_t)s->n_local * s->n_hist;
+    if (tallies && nh) RSK_CUDA(cudaMemcpyAsync(tallies, s->total, nh * 8, cudaMemcpyDeviceToHost, s->ctx->stream));
+    RSK_CUDA(cudaStreamSynchronize(s->ctx->stream));
     return RSK_OK;
 }
 
@@ -629,7 +672,7 @@ extern "C" int rsk_sky_step(rsk_solve *s, int32_t n_iters, int32_t *n_active) {
 
 extern "C" int rsk_sky_read(rsk_solve *s, int64_t *counts, int32_t *iters, int64_t *total_rays) {
     RSK_REQUIRE(s && s->mode == MODE_SKY, "rsk_sky_read: not a sky solve");
-    RSK_CUDA(cudaSetDevice(s->ctx->device));
+    RskScope scope(s->ctx);
     RSK_TRY(rsk_read_common(s, iters, total_rays));
     const size_t nh = (size_t)s->n_local * s->n_hist;
     if (counts && nh) RSK_CUDA(cudaMemcpyAsync(counts, s->total, nh * 8, cudaMemcpyDeviceToHost, s->ctx->stream));
@@ -639,7 +682,7 @@ extern "C" int rsk_sky_read(rsk_solve *s, int64_t *counts, int32_t *iters, int64
 
 extern "C" int rsk_solve_rays_traced(rsk_solve *s, int64_t *rays) {
     RSK_REQUIRE(s && rays, "rsk_solve_rays_traced: bad arguments");
-    RSK_CUDA(cudaSetDevice(s->ctx->device));
+    RskScope scope(s->ctx);
     unsigned long long v = 0;
     RSK_CUDA(cudaMemcpyAsync(&v, s->rays_traced, 8, cudaMemcpyDeviceToHost, s->ctx->stream));
     RSK_CUDA(cudaStreamSynchronize(s->ctx->stream));
@@ -649,12 +692,11 @@ extern "C" int rsk_solve_rays_traced(rsk_solve *s, int64_t *rays) {
 
 extern "C" int rsk_solve_destroy(rsk_solve *s) {
     if (!s) return RSK_OK;
-    cudaSetDevice(s->ctx->device);
-    cudaStreamSynchronize(s->ctx->stream);
-    cudaFree(s->emit_ids); cudaFree(s->rot_base); cudaFree(s->iters_done); cudaFree(s->done); cudaFree(s->not_conv);
-    cudaFree(s->have_prev); cudaFree(s->tile_start); cudaFree(s->n_rays_once); cudaFree(s->total_rays); cudaFree(s->ray_begin); cudaFree(s->ray_end); cudaFree(s->mask);
-    cudaFree(s->cp_table); cudaFree(s->iter_tally); cudaFree(s->rays_traced); cudaFree(s->total); cudaFree(s->mean);
-    cudaFree(s->m2); cudaFree(s->prev); cudaFree(s->n_active);
+    RskScope scope(s->ctx);
+    rsk_dev_free(s->emit_ids); rsk_dev_free(s->rot_base); rsk_dev_free(s->iters_done); rsk_dev_free(s->done); rsk_dev_free(s->not_conv);
+    rsk_dev_free(s->have_prev); rsk_dev_free(s->tile_start); rsk_dev_free(s->n_rays_once); rsk_dev_free(s->total_rays); rsk_dev_free(s->ray_begin); rsk_dev_free(s->ray_end); rsk_dev_free(s->mask);
+    rsk_dev_free(s->cp_table); rsk_dev_free(s->iter_tally); rsk_dev_free(s->rays_traced); rsk_dev_free(s->total); rsk_dev_free(s->mean);
+    rsk_dev_free(s->m2); rsk_dev_free(s->prev); rsk_dev_free(s->n_active);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     delete s;
     return RSK_OK;

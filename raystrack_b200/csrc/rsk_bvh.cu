@@ -344,13 +344,13 @@ int rsk_bvh_build(rsk_scene *sc, const float4 *tri_in, const float4 *nrm_in) {
     WideNode *nodes = nullptr;
     int rc = RSK_OK;
     auto cleanup = [&]() {
-        cudaFree(tlo); cudaFree(thi); cudaFree(nlo); cudaFree(nhi); cudaFree(bounds); cudaFree(ids); cudaFree(ids_sorted);
-        cudaFree(codes); cudaFree(codes_sorted); cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(first); cudaFree(last);
-        cudaFree(arrivals); cudaFree(queue[0]); cudaFree(queue[1]); cudaFree(counters); cudaFree(sort_tmp);
+        rsk_dev_free(tlo); rsk_dev_free(thi); rsk_dev_free(nlo); rsk_dev_free(nhi); rsk_dev_free(bounds); rsk_dev_free(ids); rsk_dev_free(ids_sorted);
+        rsk_dev_free(codes); rsk_dev_free(codes_sorted); rsk_dev_free(left); rsk_dev_free(right); rsk_dev_free(parent); rsk_dev_free(first); rsk_dev_free(last);
+        rsk_dev_free(arrivals); rsk_dev_free(queue[0]); rsk_dev_free(queue[1]); rsk_dev_free(counters); rsk_dev_free(sort_tmp);
         cudaEventDestroy(t0); cudaEventDestroy(t1);
     };
-#define B_TRY(expr) do { rc = (expr); if (rc != RSK_OK) { cleanup(); cudaFree(nodes); return rc; } } while (0)
-#define B_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rsk_set_error("%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); cudaFree(nodes); return RSK_ERR_CUDA; } } while (0)
+#define B_TRY(expr) do { rc = (expr); if (rc != RSK_OK) { cleanup(); rsk_dev_free(nodes); return rc; } } while (0)
+#define B_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rsk_set_error("%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); rsk_dev_free(nodes); return RSK_ERR_CUDA; } } while (0)
 
     B_TRY(rsk_dev_alloc(&tlo, n)); B_TRY(rsk_dev_alloc(&thi, n));
     B_TRY(rsk_dev_alloc(&bounds, 6));
@@ -393,7 +393,7 @@ int rsk_bvh_build(rsk_scene *sc, const float4 *tri_in, const float4 *nrm_in) {
         ctx->launches++;
         size_t tmp_bytes = 0;
         B_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, codes, codes_sorted, ids, ids_sorted, n, 0, 63, s));
-        B_CUDA(cudaMalloc(&sort_tmp, tmp_bytes));
+        { unsigned char *tmp = nullptr; B_TRY(rsk_dev_alloc(&tmp, tmp_bytes)); sort_tmp = tmp; }
         B_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, tmp_bytes, codes, codes_sorted, ids, ids_sorted, n, 0, 63, s));
         ctx->launches += 8;
 
@@ -434,7 +434,7 @@ int rsk_bvh_build(rsk_scene *sc, const float4 *tri_in, const float4 *nrm_in) {
         }
         if (depth > RSK_MAX_DEPTH_HOST) {
             rsk_set_error("rsk_bvh_build: wide tree depth %d exceeds the traversal stack (%d)", depth, RSK_MAX_DEPTH_HOST);
-            cleanup(); cudaFree(nodes);
+            cleanup(); rsk_dev_free(nodes);
             return RSK_ERR_INVALID;
         }
     }
@@ -456,7 +456,7 @@ int rsk_bvh_build(rsk_scene *sc, const float4 *tri_in, const float4 *nrm_in) {
     sc->n_nodes = n_nodes;
     sc->depth = depth;
     sc->build_us = (int64_t)(ms * 1000.f);
-    cudaFree(nodes);
+    rsk_dev_free(nodes);
     cleanup();
 #undef B_TRY
 #undef B_CUDA

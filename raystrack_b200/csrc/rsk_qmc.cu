@@ -47,7 +47,7 @@ int rsk_qmc_ensure_halton(rsk_ctx *ctx, int64_t n) {
     ctx->launches++;
     RSK_CUDA(cudaGetLastError());
     RSK_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->halton) cudaFree(ctx->halton);
+    if (ctx->halton) rsk_dev_free(ctx->halton);
     ctx->halton = fresh;
     ctx->halton_cap = cap;
     return RSK_OK;
@@ -68,7 +68,7 @@ int rsk_qmc_ensure_grid(rsk_ctx *ctx, int g, int64_t *offset) {
         if (ctx->grid_used > 0)
             RSK_CUDA(cudaMemcpyAsync(fresh, ctx->grid, ctx->grid_used * sizeof(float2), cudaMemcpyDeviceToDevice, ctx->stream));
         RSK_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->grid) cudaFree(ctx->grid);
+        if (ctx->grid) rsk_dev_free(ctx->grid);
         ctx->grid = fresh;
         ctx->grid_cap = cap;
     }

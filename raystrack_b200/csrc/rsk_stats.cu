@@ -46,7 +46,7 @@ __global__ void rsk_fold_kernel(const FoldArgs a) {
     if (a.tol_mode == 0) {
         // main.py:1904-1906: only active receivers are tested (front and back); sky: every bin
         if (a.surf_mask) {
-            const int s = j % a.n_surf;
+            const int s = j >> 1;                       // matrix bins are (receiver, side) pairs
             if (!((a.surf_mask[(int64_t)k * a.mask_words + (s >> 5)] >> (s & 31)) & 1u)) return;
         }
         double se;
@@ -147,11 +147,11 @@ extern "C" int rsk_reciprocity_rowsum(rsk_ctx *ctx, int32_t n, const double *are
     RSK_REQUIRE(ctx && area && F && n >= 0, "rsk_reciprocity_rowsum: bad arguments");
     if (sweeps) *sweeps = 0;
     if (n == 0) return RSK_OK;
-    RSK_CUDA(cudaSetDevice(ctx->device));
+    RskScope scope(ctx);
     const int64_t nn = (int64_t)n * n;
     double *dF = nullptr, *dG = nullptr, *dA = nullptr, *dT = nullptr, *dd = nullptr, *dd2 = nullptr, *dmax = nullptr;
     int rc = RSK_OK;
-    auto cleanup = [&]() { cudaFree(dF); cudaFree(dG); cudaFree(dA); cudaFree(dT); cudaFree(dd); cudaFree(dd2); cudaFree(dmax); };
+    auto cleanup = [&]() { rsk_dev_free(dF); rsk_dev_free(dG); rsk_dev_free(dA); rsk_dev_free(dT); rsk_dev_free(dd); rsk_dev_free(dd2); rsk_dev_free(dmax); };
 #define RSK_R(expr) do { rc = (expr); if (rc != RSK_OK) { cleanup(); return rc; } } while (0)
 #define RSK_RC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rsk_set_error("%s: %s", #call, cudaGetErrorString(e__)); cleanup(); return RSK_ERR_CUDA; } } while (0)
     RSK_R(rsk_dev_alloc(&dF, nn)); RSK_R(rsk_dev_alloc(&dG, nn)); RSK_R(rsk_dev_alloc(&dA, n)); RSK_R(rsk_dev_alloc(&dT, n));

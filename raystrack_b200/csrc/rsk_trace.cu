@@ -21,7 +21,7 @@ __device__ __forceinline__ int rsk_result_key(const TraceArgs &a, const Walk &w,
         const float4 n = __ldg(a.sc.nrm + w.best_tri);
         const int sid = __float_as_int(n.w);
         const bool front = -(w.dx * n.x + w.dy * n.y + w.dz * n.z) > 0.0f;     // cpu_trace.py:114
-        return front ? sid : a.sc.n_surf + sid;
+        return 2 * sid + (front ? 0 : 1);                                       // interleaved (front, back) per receiver
     } else {
         if (any_hit) return -1;
         if (a.n_hist == 1) return w.dz > 0.0f ? 0 : -1;                       // cpu_trace.py:796
@@ -35,8 +35,8 @@ __device__ __forceinline__ void rsk_debug_store(const TraceArgs &a, int64_t k, c
     if (a.dbg_orig) { a.dbg_orig[3 * i] = w.ox; a.dbg_orig[3 * i + 1] = w.oy; a.dbg_orig[3 * i + 2] = w.oz; }
     if (a.dbg_dirs) { a.dbg_dirs[3 * i] = w.dx; a.dbg_dirs[3 * i + 1] = w.dy; a.dbg_dirs[3 * i + 2] = w.dz; }
     if (MODE == MODE_MATRIX) {
-        if (a.dbg_hit) a.dbg_hit[i] = key < 0 ? -1 : (key >= a.sc.n_surf ? key - a.sc.n_surf : key);
-        if (a.dbg_front) a.dbg_front[i] = (key >= 0 && key < a.sc.n_surf) ? 1 : 0;
+        if (a.dbg_hit) a.dbg_hit[i] = key < 0 ? -1 : (key >> 1);
+        if (a.dbg_front) a.dbg_front[i] = (key >= 0 && !(key & 1)) ? 1 : 0;
     } else {
         if (a.dbg_hit) a.dbg_hit[i] = any_hit ? 1 : 0;
         if (a.dbg_front) a.dbg_front[i] = key < 0 ? 255 : (uint8_t)key;

@@ -9,6 +9,7 @@ reads "how many emitters are still running".
 """
 from __future__ import annotations
 
+import functools
 import time
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -64,23 +65,33 @@ def _ensure_prepared(meshes: List[Mesh], prepared: Optional[PreparedSolver]) -> 
 
 def _surface_masks(emitters: Sequence[PreparedEmitter], centers: np.ndarray, extents: np.ndarray) -> np.ndarray:
     """``surf_active`` for every emitter at once, uint8 [n_emit, n_surf] (reference main.py:167-204): the emitter's
-    own mesh is off; for a planar emitter every mesh whose bounding box lies wholly behind its plane is off."""
+    own mesh is off; for a planar emitter every mesh whose bounding box lies wholly behind its plane is off.
+    Same float32 operation order as the reference's scalar loop (dx*nx + dy*ny + dz*nz; |n|.extent)."""
     n = centers.shape[0]
-    active = np.ones((len(emitters), n), np.uint8)
-    for i, em in enumerate(emitters):
-        if i < n:
-            active[i, i] = 0
-        if not em.plane_is_planar:
-            continue
-        po, pn = em.plane_origin, em.plane_normal
-        an = np.abs(pn)
-        d = centers - po
-        signed = d[:, 0] * pn[0] + d[:, 1] * pn[1] + d[:, 2] * pn[2]
-        radius = an[0] * extents[:, 0] + an[1] * extents[:, 1] + an[2] * extents[:, 2]
-        behind = (signed + radius) <= float(em.plane_tol)
-        if i < n:
-            behind[i] = False
-        active[i, behind] = 0
+    ne = len(emitters)
+    active = np.ones((ne, n), np.uint8)
+    if ne == 0 or n == 0:
+        return active
+    planar = np.fromiter((em.plane_is_planar for em in emitters), bool, ne)
+    po = np.stack([em.plane_origin for em in emitters]).astype(np.float32, copy=False)
+    pn = np.stack([em.plane_normal for em in emitters]).astype(np.float32, copy=False)
+    tol = np.fromiter((em.plane_tol for em in emitters), np.float64, ne).astype(np.float32)
+    an = np.abs(pn)
+    c = [np.ascontiguousarray(centers[:, k]) for k in range(3)]
+    x = [np.ascontiguousarray(extents[:, k]) for k in range(3)]
+    rows = np.nonzero(planar)[0]
+    for lo in range(0, rows.size, 256):                    # row blocks keep the temporaries cache-sized
+        r = rows[lo:lo + 256]
+        signed = (c[0][None, :] - po[r, 0:1]) * pn[r, 0:1]
+        signed += (c[1][None, :] - po[r, 1:2]) * pn[r, 1:2]
+        signed += (c[2][None, :] - po[r, 2:3]) * pn[r, 2:3]
+        radius = an[r, 0:1] * x[0][None, :]
+        radius += an[r, 1:2] * x[1][None, :]
+        radius += an[r, 2:3] * x[2][None, :]
+        signed += radius
+        active[r] = ~(signed <= tol[r, None])
+    idx = np.arange(min(ne, n))
+    active[idx, idx] = 0
     return active
 
 
@@ -89,11 +100,17 @@ def _rotation_table(seed: int, n_emit: int, max_iters: int) -> np.ndarray:
     iteration (main.py:1810-1812); only the sum matters, so one row per distinct sum: row s = rotation of
     ``seed + s``; emitter i, iteration it uses row i + it."""
     rows = max(0, n_emit + max(int(max_iters), 0))
-    table = np.empty((max(rows, 1), 7), np.float32)
+    return _rotation_rows(int(seed), max(rows, 1))
+
+
+@functools.lru_cache(maxsize=8)
+def _rotation_rows(seed: int, rows: int) -> np.ndarray:
+    table = np.zeros((rows, 7), np.float32)
     for s in range(rows):
         rng = np.random.default_rng(seed + s)
         table[s, :2] = rng.random(2, dtype=np.float32)
         table[s, 2:] = rng.random(5, dtype=np.float32)
+    table.setflags(write=False)
     return table
 
 
@@ -218,23 +235,20 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
             _run_solve_shared(solve, n_shared, min_iters, max_iters, ctx.device)
         else:
             _run_solve(solve, min_iters, max_iters)
-        if sky:
-            loc, it_loc, tot_loc = solve.read_sky()
-        else:
-            hf, hb, it_loc, tot_loc, _, _ = solve.read_matrix()
-            loc = np.concatenate([hf, hb], axis=1)
+        loc, it_loc, tot_loc = solve.read_block()
     finally:
         solve.close()
     n_hist = (145 if discrete else 1) if sky else 2 * n_surf
+    if world == 1 and len(plan) == n_emit:
+        return loc, it_loc.astype(np.int64), tot_loc          # every emitter, in order: no scatter needed
     tallies = np.zeros((n_emit, n_hist), np.int64)
     iters = np.zeros(n_emit, np.int64)
     totals = np.zeros(n_emit, np.int64)
-    for k, (e, _, _, shared) in enumerate(plan):
-        if shared and rank != 0:
-            continue                      # replicated state: counted once
-        tallies[e] = loc[k]
-        iters[e] = it_loc[k]
-        totals[e] = tot_loc[k]
+    keep = np.asarray([not (j[3] and rank != 0) for j in plan], bool)      # replicated (ray-split) jobs count once
+    if keep.any():
+        tallies[ids[keep]] = loc[keep]
+        iters[ids[keep]] = it_loc[keep]
+        totals[ids[keep]] = tot_loc[keep]
     if world > 1:
         from .dist import allreduce_sum_
         allreduce_sum_([tallies, iters, totals], device=ctx.device)
@@ -275,10 +289,11 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
     # receivers of emitter i (main.py:161-164, 207-214): active meshes j > i (reciprocity) or j != i
     emit_sid = np.arange(n_surf, dtype=np.int32)
     min_sid = (emit_sid + 1) if reciprocity else np.zeros(n_surf, np.int32)
-    recv_mask = active.astype(bool)
-    col = np.arange(n_surf)[None, :]
-    recv_mask &= (col >= min_sid[:, None]) & (col != emit_sid[:, None])
-    has_recv = recv_mask.any(axis=1)
+    if reciprocity:
+        # suffix-any: emitter i has receivers iff some active mesh j > i exists (the diagonal is already off)
+        has_recv = np.asarray([bool(active[i, i + 1:].any()) for i in range(n_surf)], bool)
+    else:
+        has_recv = active.any(axis=1)
     todo = [i for i in range(n_surf) if has_recv[i]]
 
     weights = [float(em.n_cells * rays) for em in emitters]
@@ -287,31 +302,30 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
     tallies, iters, totals = _solve_sharded(ctx, d_scene, d_em, todo, n_once, active, table, max_iters=max_iters,
                                             min_iters=min_iters, interval=interval if schedule == "gpu" else 1,
                                             tol_mode=tol_mode, tol=tol, emit_sid=emit_sid, min_sid=min_sid)
-    hits_f, hits_b = tallies[:, :n_surf], tallies[:, n_surf:]
     elapsed = time.time() - t0
 
+    # result rows (main.py:1918-1934).  The tally block is [emitter][receiver][front, back], i.e. already in the
+    # reference's key order "<r0>_front, <r0>_back, <r1>_front, ..."; only non-zero bins become keys.
     label = "builtin" if use_bvh else "off"
+    keys = [f"{name}{suffix}" for name, _, _ in meshes for suffix in ("_front", "_back")]
+    work = np.asarray(weights) * np.maximum(iters, 1)
+    work_sum = max(1.0, float(work.sum()))
     for i, (name_e, _, _) in enumerate(meshes):
         if not has_recv[i]:
             _log(f"({i+1}/{n_surf}) [{name_e}] 0 iter, 0 rays -> 0.000s  (BVH={label}, device=gpu)")
             continue
-        total = float(totals[i])
-        row: Dict[str, float] = {}
+        cols = np.nonzero(tallies[i])[0]
         with np.errstate(divide="ignore", invalid="ignore"):
-            f_row = hits_f[i] / total                                                  # main.py:1922-1923
-            b_row = hits_b[i] / total
-        for j in np.nonzero(recv_mask[i] & ((f_row > 0.0) | (b_row > 0.0)))[0]:
-            name_r = meshes[j][0]
-            f, b = f_row[j], b_row[j]
-            if f > 0.0:
-                row[f"{name_r}_front"] = f
-                if reciprocity and areas is not None and areas[j] > 0.0:
-                    result[name_r][f"{name_e}_front"] = f * (areas[i] / areas[j])      # main.py:1926-1927
-            if b > 0.0:
-                row[f"{name_r}_back"] = b
+            vals = tallies[i, cols] / float(totals[i])                                  # main.py:1922-1923
+        cols_l = cols.tolist()
+        row = dict(zip([keys[c] for c in cols_l], vals))
+        if reciprocity and areas is not None:
+            for c, f in zip(cols_l, vals):
+                j = c >> 1
+                if not (c & 1) and areas[j] > 0.0:
+                    result[meshes[j][0]][f"{name_e}_front"] = f * (areas[i] / areas[j])     # main.py:1926-1927
         result[name_e].update(row)
-        share = elapsed * (weights[i] * max(int(iters[i]), 1)) / max(1.0, float(np.dot(weights, np.maximum(iters, 1))))
-        _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {share:0.3f}s  "
+        _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {elapsed * work[i] / work_sum:0.3f}s  "
              f"(BVH={label}, device=gpu)")
 
     if p["enforce_reciprocity_rowsum"]:
@@ -368,6 +382,8 @@ def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepar
     elapsed = time.time() - t0
 
     label = "builtin" if use_bvh else "off"
+    work = np.asarray(weights) * np.maximum(iters, 1)
+    work_sum = max(1.0, float(work.sum()))
     for i, (name_e, _, _) in enumerate(meshes):
         denom = float(max(1, int(totals[i])))
         if discrete:
@@ -375,8 +391,7 @@ def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepar
             result[name_e].update({f"Sky_Patch_{k+1}": float(frac[k]) for k in range(145)})
         else:
             result[name_e]["Sky"] = float(int(counts[i, 0]) / denom)
-        share = elapsed * (weights[i] * max(int(iters[i]), 1)) / max(1.0, float(np.dot(weights, np.maximum(iters, 1))))
-        _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {share:0.3f}s  "
+        _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {elapsed * work[i] / work_sum:0.3f}s  "
              f"(BVH={label}, device=gpu)")
     return result
 

@@ -257,6 +257,7 @@ class PreparedSolver:
         self._device_scene_cache: Dict[Tuple[int, bool], PreparedDeviceScene] = {}
         self._device_emitter_cache: Dict[Tuple[int, int, int, bool], PreparedDeviceEmitters] = {}
         self._mesh_bounds_cache: Optional[Tuple[np.ndarray, np.ndarray]] = None
+        self._emitter_pack_cache: Dict[Tuple[int, int, bool], tuple] = {}
 
     def get_scene(self, *, use_bvh: bool) -> PreparedScene:
         key = bool(use_bvh)
@@ -315,18 +316,22 @@ class PreparedSolver:
         got = self._device_emitter_cache.get(key)
         if got is None:
             ems = self.get_emitters(samples=samples, rays=rays, flip_faces=flip_faces)
-            counts = np.asarray([e.tri_a.shape[0] for e in ems], np.int64)
-            off = np.zeros(len(ems) + 1, np.int64)
-            np.cumsum(counts, out=off[1:])
+            hkey = (int(samples), int(rays), bool(flip_faces))
+            pack = self._emitter_pack_cache.get(hkey)
+            if pack is None:                      # concatenated host arrays: host preparation, kept across device resets
+                counts = np.asarray([e.tri_a.shape[0] for e in ems], np.int64)
+                off = np.zeros(len(ems) + 1, np.int64)
+                np.cumsum(counts, out=off[1:])
 
-            def cat(name, width):
-                if not ems:
-                    return np.empty((0, width) if width else (0,), np.float32)
-                return np.ascontiguousarray(np.concatenate([getattr(e, name) for e in ems], axis=0), np.float32)
+                def cat(name, width):
+                    if not ems:
+                        return np.empty((0, width) if width else (0,), np.float32)
+                    return np.ascontiguousarray(np.concatenate([getattr(e, name) for e in ems], axis=0), np.float32)
 
-            nat = _native.DeviceEmitters(ctx, off, cat("tri_a", 3), cat("tri_e1", 3), cat("tri_e2", 3), cat("tri_u", 3),
-                                         cat("tri_v", 3), cat("tri_n", 3), cat("tri_origin_eps", 0), cat("cdf", 0),
-                                         np.asarray([e.g for e in ems], np.int32), int(rays))
+                pack = (off, cat("tri_a", 3), cat("tri_e1", 3), cat("tri_e2", 3), cat("tri_u", 3), cat("tri_v", 3),
+                        cat("tri_n", 3), cat("tri_origin_eps", 0), cat("cdf", 0), np.asarray([e.g for e in ems], np.int32))
+                self._emitter_pack_cache[hkey] = pack
+            nat = _native.DeviceEmitters(ctx, *pack, int(rays))
             got = PreparedDeviceEmitters(nat, np.asarray([e.n_cells * int(rays) for e in ems], np.int64))
             self._device_emitter_cache[key] = got
         return got

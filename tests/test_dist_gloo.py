@@ -60,9 +60,8 @@ class FakeSolve:
     def device_iter_tallies(self):
         return self.iter_t, self.n_hist
 
-    def read_matrix(self, want_stderr=False):
-        ns = self.n_hist // 2
-        return self.total[:, :ns], self.total[:, ns:], self.it.astype(np.int32), self.it * self.n_once[self.ids], None, None
+    def read_block(self):
+        return self.total.copy(), self.it.astype(np.int32), self.it * self.n_once[self.ids]
 
     def close(self):
         pass
