@@ -264,9 +264,11 @@ def run_ours(args):
         t0 = time.perf_counter()
         view_factor_matrix(meshes, prm, prepared=ps2)
         torch.cuda.synchronize()
-        return D.max_over_ranks(time.perf_counter() - t0, local)
+        dt = time.perf_counter() - t0
+        phases.append({k: round(1e3 * v, 1) for k, v in M.LAST_TIMING.items()})
+        return D.max_over_ranks(dt, local)
 
-    e2e_times, e2e_single = [], []
+    e2e_times, e2e_single, phases = [], [], []
     try:
         if args.e2e_steps > 0:
             timed_call(1)                                       # warm-up of the public path
@@ -296,6 +298,7 @@ def run_ours(args):
                             f"min_iters=max_iters={args.e2e_iters}, tol=0)): upload of scene+emitters, GPU BVH build, "
                             f"{args.e2e_iters} iterations, tally download, result dict",
                     "ms_per_step": 1e3 * float(np.mean(e2e_times)) if e2e_times else None,
+                    "phases_ms_last_call": phases[args.e2e_steps] if len(phases) > args.e2e_steps else None,
                     "single_iteration_call": {"value": e2e_single_value, "unit": UNIT,
                                               "ms": 1e3 * float(np.mean(e2e_single)) if e2e_single else None}}}
 

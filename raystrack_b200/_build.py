@@ -34,11 +34,14 @@ def _stale() -> bool:
     return any(p.stat().st_mtime > t for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: Path | None = None) -> Path:
+    """Compile and link.  ``defines`` (e.g. ("RSK_PRMT=0",)) + ``out`` build an experimental variant next to the
+    product library (scripts/kernel_variants.py); the product itself is always built without defines."""
+    target = Path(out) if out else LIB
+    if not force and not defines and not _stale():
         return LIB
     OUT_DIR.mkdir(exist_ok=True)
-    obj_dir = OUT_DIR / "obj"
+    obj_dir = OUT_DIR / ("obj" if not defines else "obj_" + "_".join(d.replace("=", "") for d in defines))
     obj_dir.mkdir(exist_ok=True)
     nvcc = _nvcc()
     env = dict(os.environ)
@@ -46,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(src: str) -> Path:
         obj = obj_dir / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", str(CSRC / src), "-o", str(obj)]
         if host_cxx:
             cmd[1:1] = ["-ccbin", host_cxx]
         if verbose:
@@ -61,13 +64,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
     link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-            "-o", str(LIB), *map(str, objs)]
+            "-o", str(target), *map(str, objs)]
     if host_cxx:
         link[1:1] = ["-ccbin", host_cxx]
     r = subprocess.run(link, capture_output=True, text=True, env=env)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

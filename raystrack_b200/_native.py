@@ -46,7 +46,8 @@ def load() -> C.CDLL:
     if not LIB_PATH.exists() or os.environ.get("RSK_REBUILD"):
         from . import _build
         _build.build(force=bool(os.environ.get("RSK_REBUILD")))
-    lib = C.CDLL(str(LIB_PATH))
+    # RSK_LIB: load an experimental build of the same library (kernel tuning, scripts/kernel_variants.py)
+    lib = C.CDLL(os.environ.get("RSK_LIB") or str(LIB_PATH))
     lib.rsk_last_error.restype = C.c_char_p
     for name in EXPORTS:
         if name != "rsk_last_error":

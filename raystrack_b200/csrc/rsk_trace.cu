@@ -11,7 +11,14 @@
 
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int REFILL_BELOW = 20;     // leave the traversal loop to fetch new rays when fewer lanes are busy
+#ifndef RSK_MIN_CTAS_PER_SM
+#define RSK_MIN_CTAS_PER_SM 4
+#endif
+#ifndef RSK_REFILL_BELOW
+#define RSK_REFILL_BELOW 20
+#endif
+constexpr int RSK_MIN_CTAS = RSK_MIN_CTAS_PER_SM;   // 4 CTAs x 256 threads per SM -> at most 64 registers per thread
+constexpr int REFILL_BELOW = RSK_REFILL_BELOW;     // leave the traversal loop to fetch new rays when fewer lanes are busy
 
 
 template <int MODE>
@@ -44,7 +51,7 @@ __device__ __forceinline__ void rsk_debug_store(const TraceArgs &a, int64_t k, c
 }
 
 template <int MODE, bool BVH>
-__global__ void __launch_bounds__(RSK_TILE_THREADS) rsk_trace_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kernel(const TraceArgs a) {
     extern __shared__ uint32_t smem[];
     __shared__ int s_job;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -123,7 +130,9 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS) rsk_trace_kernel(const Trace
         const bool rays_left = next < wend;
 
         if (BVH) {
-            // ---- 8-wide BVH walk
+            // ---- 8-wide BVH walk, one node step per loop trip; the triangles a step uncovers are tested at once.
+            // (A "while-while" form that postpones triangles until the warp reconverges measured 30 % slower on
+            // B200 -- profiles/kernel_variants_r1.md -- because lanes idle through other lanes' node steps.)
             while (active) {
                 bool finished = false, any_hit = false;
                 if (w.ng.y <= 0x00ffffffu) {

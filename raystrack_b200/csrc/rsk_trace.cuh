@@ -60,6 +60,11 @@ __device__ __forceinline__ void rsk_walk_begin(Walk &w, const Ray &r) {
     w.sp = 0;
 }
 
+// Byte j of `word` as a float without the (slow) integer->float conversion pipe: PRMT builds the bit pattern of
+// 2^23 + byte, one full-rate FADD removes the bias (exact).
+// Byte j of `word` as a float (shift + mask + I2F).  PRMT-based extraction and the 2^23-bias trick were measured
+// 5-7 % slower on B200 (profiles/kernel_variants_r1.md): the conversion pipe is otherwise idle, the ALU/FMA pipes
+// are the busy ones.
 __device__ __forceinline__ float rsk_byte(uint32_t word, int j) { return (float)((word >> (8 * j)) & 0xffu); }
 
 // Slab test of the 8 quantised child boxes of node `idx` against the ray over [0, tmax].

@@ -23,6 +23,21 @@ Mesh = Tuple[str, np.ndarray, np.ndarray]
 _BVH_AUTO_THRESHOLD = 512      # reference main.py:48
 
 
+LAST_TIMING: Dict[str, float] = {}     # wall-clock seconds per phase of the most recent solve (diagnostics / bench.py)
+
+
+class _Phase:
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        self.t = time.perf_counter()
+
+    def __exit__(self, *exc):
+        LAST_TIMING[self.name] = LAST_TIMING.get(self.name, 0.0) + time.perf_counter() - self.t
+        return False
+
+
 def _log(msg: str) -> None:
     """Progress line sink.  A module attribute on purpose: the reference's validation harness and examples
     replace ``raystrack.main._log`` to capture iteration counts (validation/common_validation.py:139-141)."""
@@ -226,18 +241,22 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
     kw = {}
     if not sky:
         kw = dict(emit_sid=np.asarray(emit_sid)[ids], min_sid=np.asarray(min_sid)[ids])
-    solve = _native.Solve(ctx, d_scene.native, d_em.native, ids,
-                          active[ids] if len(plan) else np.zeros((0, n_surf), np.uint8),
-                          table, ids.copy(), max_iters=max_iters, min_iters=min_iters, interval=interval,
-                          tol_mode=tol_mode, tol=tol, sky=sky, discrete=discrete, ray_range=ranges, **kw)
+    with _Phase("solve_begin"):
+        solve = _native.Solve(ctx, d_scene.native, d_em.native, ids,
+                              active[ids] if len(plan) else np.zeros((0, n_surf), np.uint8),
+                              table, ids.copy(), max_iters=max_iters, min_iters=min_iters, interval=interval,
+                              tol_mode=tol_mode, tol=tol, sky=sky, discrete=discrete, ray_range=ranges, **kw)
     try:
-        if any_shared:
-            _run_solve_shared(solve, n_shared, min_iters, max_iters, ctx.device)
-        else:
-            _run_solve(solve, min_iters, max_iters)
-        loc, it_loc, tot_loc = solve.read_block()
+        with _Phase("iterate"):
+            if any_shared:
+                _run_solve_shared(solve, n_shared, min_iters, max_iters, ctx.device)
+            else:
+                _run_solve(solve, min_iters, max_iters)
+        with _Phase("download"):
+            loc, it_loc, tot_loc = solve.read_block()
     finally:
-        solve.close()
+        with _Phase("solve_end"):
+            solve.close()
     n_hist = (145 if discrete else 1) if sky else 2 * n_surf
     if world == 1 and len(plan) == n_emit:
         return loc, it_loc.astype(np.int64), tot_loc          # every emitter, in order: no scatter needed
@@ -277,15 +296,20 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
         raise ValueError(f"Unknown tol_mode: {tol_mode}")
     n_surf = len(meshes)
     result: Dict[str, Dict[str, float]] = {name: {} for name, _, _ in meshes}
-    emitters = solver.get_emitters(samples=samples, rays=rays, flip_faces=flip_faces)
-    areas = [em.total_area for em in emitters] if reciprocity else None
-    centers, extents = solver.get_mesh_bounds()
-    ctx = _context()
-    d_scene = solver.get_device_scene(use_bvh=use_bvh, ctx=ctx)
-    d_em = solver.get_device_emitters(samples=samples, rays=rays, flip_faces=flip_faces, ctx=ctx)
+    LAST_TIMING.clear()
+    with _Phase("host_prepare"):
+        emitters = solver.get_emitters(samples=samples, rays=rays, flip_faces=flip_faces)
+        areas = [em.total_area for em in emitters] if reciprocity else None
+        centers, extents = solver.get_mesh_bounds()
+        ctx = _context()
+    with _Phase("scene_upload_bvh"):
+        d_scene = solver.get_device_scene(use_bvh=use_bvh, ctx=ctx)
+    with _Phase("emitter_upload"):
+        d_em = solver.get_device_emitters(samples=samples, rays=rays, flip_faces=flip_faces, ctx=ctx)
 
     t0 = time.time()
-    active = _surface_masks(emitters, centers, extents)
+    with _Phase("masks"):
+        active = _surface_masks(emitters, centers, extents)
     # receivers of emitter i (main.py:161-164, 207-214): active meshes j > i (reciprocity) or j != i
     emit_sid = np.arange(n_surf, dtype=np.int32)
     min_sid = (emit_sid + 1) if reciprocity else np.zeros(n_surf, np.int32)
@@ -298,11 +322,13 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
 
     weights = [float(em.n_cells * rays) for em in emitters]
     n_once = [int(em.n_cells * rays) for em in emitters]
-    table = _rotation_table(seed, n_surf, max_iters)
+    with _Phase("rotations"):
+        table = _rotation_table(seed, n_surf, max_iters)
     tallies, iters, totals = _solve_sharded(ctx, d_scene, d_em, todo, n_once, active, table, max_iters=max_iters,
                                             min_iters=min_iters, interval=interval if schedule == "gpu" else 1,
                                             tol_mode=tol_mode, tol=tol, emit_sid=emit_sid, min_sid=min_sid)
     elapsed = time.time() - t0
+    t_asm = time.perf_counter()
 
     # result rows (main.py:1918-1934).  The tally block is [emitter][receiver][front, back], i.e. already in the
     # reference's key order "<r0>_front, <r0>_back, <r1>_front, ..."; only non-zero bins become keys.
@@ -328,9 +354,11 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
         _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {elapsed * work[i] / work_sum:0.3f}s  "
              f"(BVH={label}, device=gpu)")
 
+    LAST_TIMING["assemble"] = time.perf_counter() - t_asm
     if p["enforce_reciprocity_rowsum"]:
         from .reciprocity import enforce_reciprocity_and_rowsum
-        enforce_reciprocity_and_rowsum(result, meshes, areas, ctx=ctx)
+        with _Phase("reciprocity_rowsum"):
+            enforce_reciprocity_and_rowsum(result, meshes, areas, ctx=ctx)
     return result
 
 

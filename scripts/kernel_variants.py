@@ -1,0 +1,40 @@
+"""Build experimental variants of librsk_b200 (compile-time knobs of the trace kernel) for A/B runs on the GPU:
+
+    python scripts/kernel_variants.py build            # here (no GPU needed)
+    python scripts/kernel_variants.py run [--iters 3]   # on the GPU box: perf_c5.py once per variant
+"""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+VARIANTS = {
+    "regs64_refill20": ("RSK_MIN_CTAS_PER_SM=4", "RSK_REFILL_BELOW=20"),      # the shipped configuration
+    "regs80_refill20": ("RSK_MIN_CTAS_PER_SM=3", "RSK_REFILL_BELOW=20"),
+    "regs51_refill20": ("RSK_MIN_CTAS_PER_SM=5", "RSK_REFILL_BELOW=20"),
+    "regs64_refill24": ("RSK_MIN_CTAS_PER_SM=4", "RSK_REFILL_BELOW=24"),
+}
+OUT = ROOT / "raystrack_b200" / "_lib" / "variants"
+
+if __name__ == "__main__":
+    cmd = sys.argv[1] if len(sys.argv) > 1 else "build"
+    only = [a for a in sys.argv[2:] if not a.startswith("--")] if cmd == "build" else []
+    if cmd == "build":
+        from raystrack_b200 import _build
+        OUT.mkdir(parents=True, exist_ok=True)
+        for name, defs in VARIANTS.items():
+            if only and name not in only:
+                continue
+            print(name, _build.build(force=True, defines=defs, out=OUT / f"librsk_{name}.so"), flush=True)
+    else:
+        extra = sys.argv[2:] or ["--iters", "3"]
+        for name in VARIANTS:
+            lib = OUT / f"librsk_{name}.so"
+            if not lib.exists():
+                continue
+            env = dict(os.environ, RSK_LIB=str(lib))
+            r = subprocess.run([sys.executable, str(ROOT / "scripts" / "perf_c5.py"), *extra], env=env, capture_output=True, text=True)
+            line = [l for l in r.stdout.splitlines() if "Grays" in l]
+            print(f"{name:28s} {line[-1] if line else r.stderr[-300:]}", flush=True)
