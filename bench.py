@@ -169,7 +169,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if _native.device_count() <= 0:
         raise RuntimeError("bench.py needs a B200: no CUDA device visible")
-    ctx = M._context() if world > 1 else _native.Context.for_device(local, torch.cuda.current_stream(local).cuda_stream)
+    ctx = M._context() if world > 1 else _native.Context.for_device(local, _native.torch_stream_handle(local))
 
     meshes = build_scene(args.side)
     ps = PreparedSolver(meshes)
@@ -197,7 +197,7 @@ def run_ours(args):
     solve = _native.Solve(ctx, sc.native, em.native, ids, active[ids], table, ids.copy(), max_iters=total_iters,
                           min_iters=total_iters, interval=1, tol_mode="stderr", tol=0.0,
                           emit_sid=ids, min_sid=np.zeros(len(ids), np.int32), ray_range=ranges)
-    tally = D.device_int64_view(*solve.device_iter_tallies(), n_jobs=n_shared, device=local) if world > 1 else None
+    tally = D.attach_tally_tensor(solve, n_shared, local) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local}")     # > 126 MB L2
 
     def one_step(trace_only_timer=None):
@@ -283,6 +283,10 @@ def run_ours(args):
     h2d = n_tri * 52 + n_tri * 80 + n * n + table.nbytes       # scene arrays + emitter arrays + surf_active + rotations
     d2h = len(ids) * 2 * n * 8 + len(ids) * 12                 # int64 tally block + iteration/ray counters
 
+    if world > 1:
+        D.barrier()
+        import torch.distributed as dist
+        dist.destroy_process_group()
     if rank != 0:
         return
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -346,9 +350,6 @@ def run_ours(args):
     if traffic_file.exists():
         line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch")
     print(json.dumps(line), flush=True)
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
 
 
 def main():

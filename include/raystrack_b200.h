@@ -50,8 +50,8 @@ int rsk_device_count(int *count);
 
 /* ------------------------------------------------------------------------------------------- context */
 
-/* One context per (process, GPU).  `stream` is a cudaStream_t to order all work on, or NULL for a private
- * non-blocking stream.  Replaces cuda.get_current_device()/cuda.stream() (main.py:109, 419-495). */
+/* One context per (process, GPU).  `stream` is a cudaStream_t to order all work on (pass cudaStreamLegacy, i.e.
+ * (void*)1, to name the legacy default stream), or NULL for a private non-blocking stream.  Replaces cuda.get_current_device()/cuda.stream() (main.py:109, 419-495). */
 int rsk_ctx_create(int device_ordinal, void *stream, rsk_ctx **out);
 int rsk_ctx_destroy(rsk_ctx *ctx);
 int rsk_ctx_synchronize(rsk_ctx *ctx);
@@ -170,6 +170,10 @@ int rsk_solve_enqueue_trace(rsk_solve *solve);
 int rsk_solve_enqueue_fold(rsk_solve *solve);
 int rsk_solve_poll(rsk_solve *solve, int32_t *n_active);
 int rsk_solve_device_iter_tallies(rsk_solve *solve, void **device_ptr, int64_t *n_per_job);
+/* Make the solve accumulate its per-iteration tallies in a caller-owned device buffer (uint64[n_local][n_per_job],
+ * e.g. a torch tensor that NCCL can all-reduce in place).  Call before the first iteration; the caller keeps the
+ * buffer alive until rsk_solve_destroy. */
+int rsk_solve_set_iter_tally_buffer(rsk_solve *solve, void *device_ptr, int64_t n_elements);
 
 int rsk_solve_destroy(rsk_solve *solve);
 /* Rays traced so far by this solve (all emitters, all iterations). */

@@ -29,7 +29,7 @@ EXPORTS = (
     "rsk_trace_rays",
     "rsk_matrix_begin", "rsk_matrix_step", "rsk_matrix_read", "rsk_solve_read_block", "rsk_matrix_device_tallies",
     "rsk_sky_begin", "rsk_sky_step", "rsk_sky_read",
-    "rsk_solve_enqueue_trace", "rsk_solve_enqueue_fold", "rsk_solve_poll", "rsk_solve_device_iter_tallies",
+    "rsk_solve_enqueue_trace", "rsk_solve_enqueue_fold", "rsk_solve_poll", "rsk_solve_device_iter_tallies", "rsk_solve_set_iter_tally_buffer",
     "rsk_solve_destroy", "rsk_solve_rays_traced", "rsk_reciprocity_rowsum",
 )
 
@@ -70,6 +70,17 @@ def device_count() -> int:
     n = C.c_int(0)
     check(load().rsk_device_count(C.byref(n)), "rsk_device_count")
     return int(n.value)
+
+
+CUDA_STREAM_LEGACY = 1      # cudaStreamLegacy: the handle that names the legacy default stream explicitly
+
+
+def torch_stream_handle(device: int) -> int:
+    """cudaStream_t of torch's current stream on ``device`` in a form rsk_ctx_create accepts: torch reports the
+    default stream as 0, which the C ABI reads as "create a private stream", so it is passed as cudaStreamLegacy."""
+    import torch
+    handle = int(torch.cuda.current_stream(device).cuda_stream)
+    return handle if handle != 0 else CUDA_STREAM_LEGACY
 
 
 class Context:
@@ -274,6 +285,10 @@ class Solve:
         n = C.c_int64(0)
         check(self.ctx.lib.rsk_solve_device_iter_tallies(self.handle, C.byref(p), C.byref(n)))
         return int(p.value or 0), int(n.value)
+
+    def set_iter_tally_buffer(self, device_ptr: int, n_elements: int) -> None:
+        check(self.ctx.lib.rsk_solve_set_iter_tally_buffer(self.handle, C.c_void_p(device_ptr), C.c_int64(n_elements)),
+              "rsk_solve_set_iter_tally_buffer")
 
     def read_matrix(self, want_stderr: bool = False):
         ns = self.scene.n_surf

@@ -416,6 +416,7 @@ struct rsk_solve {
     int32_t *h_pinned = nullptr;     // [0] n_active
     int32_t last_active = 0;
     bool stepped = false;
+    bool external_tally = false;     // iter_tally belongs to the caller (rsk_solve_set_iter_tally_buffer)
 };
 
 static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int mode, int discrete,
@@ -580,6 +581,18 @@ extern "C" int rsk_solve_poll(rsk_solve *s, int32_t *n_active) {
     return rsk_solve_poll_impl(s, n_active);
 }
 
+extern "C" int rsk_solve_set_iter_tally_buffer(rsk_solve *s, void *device_ptr, int64_t n_elements) {
+    RSK_REQUIRE(s && device_ptr, "rsk_solve_set_iter_tally_buffer: null argument");
+    RSK_REQUIRE(n_elements >= (int64_t)s->n_local * s->n_hist, "rsk_solve_set_iter_tally_buffer: buffer too small");
+    RSK_REQUIRE(!s->stepped, "rsk_solve_set_iter_tally_buffer: must be called before the first iteration");
+    RskScope scope(s->ctx);
+    if (!s->external_tally) rsk_dev_free(s->iter_tally);
+    s->iter_tally = (unsigned long long *)device_ptr;
+    s->external_tally = true;
+    RSK_CUDA(cudaMemsetAsync(s->iter_tally, 0, (size_t)s->n_local * s->n_hist * 8, s->ctx->stream));
+    return RSK_OK;
+}
+
 extern "C" int rsk_solve_device_iter_tallies(rsk_solve *s, void **device_ptr, int64_t *n_per_job) {
     RSK_REQUIRE(s && device_ptr && n_per_job, "rsk_solve_device_iter_tallies: bad arguments");
     *device_ptr = s->iter_tally;
@@ -695,7 +708,7 @@ extern "C" int rsk_solve_destroy(rsk_solve *s) {
     RskScope scope(s->ctx);
     rsk_dev_free(s->emit_ids); rsk_dev_free(s->rot_base); rsk_dev_free(s->iters_done); rsk_dev_free(s->done); rsk_dev_free(s->not_conv);
     rsk_dev_free(s->have_prev); rsk_dev_free(s->tile_start); rsk_dev_free(s->n_rays_once); rsk_dev_free(s->total_rays); rsk_dev_free(s->ray_begin); rsk_dev_free(s->ray_end); rsk_dev_free(s->mask);
-    rsk_dev_free(s->cp_table); rsk_dev_free(s->iter_tally); rsk_dev_free(s->rays_traced); rsk_dev_free(s->total); rsk_dev_free(s->mean);
+    rsk_dev_free(s->cp_table); if (!s->external_tally) rsk_dev_free(s->iter_tally); rsk_dev_free(s->rays_traced); rsk_dev_free(s->total); rsk_dev_free(s->mean);
     rsk_dev_free(s->m2); rsk_dev_free(s->prev); rsk_dev_free(s->n_active);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     delete s;

@@ -16,7 +16,7 @@ def init_from_env(backend: str | None = None) -> tuple[int, int]:
     import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world <= 1:
+    if world <= 1 and "RANK" not in os.environ:
         return 0, 1
     if not dist.is_initialized():
         if backend is None:
@@ -65,21 +65,18 @@ def max_over_ranks(value: float, device: int = 0) -> float:
     return float(t.item())
 
 
-class _DeviceBuffer:
-    """Zero-copy view of library-owned device memory for torch (CUDA array interface, int64 elements)."""
-
-    def __init__(self, ptr: int, n: int):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False), "version": 3}
-
-
-def device_int64_view(ptr: int, n_per_job: int, n_jobs: int, device: int = 0):
-    """torch tensor aliasing the first ``n_jobs`` rows of a solve's per-iteration tally block (uint64 counters
-    viewed as int64), or None when there is nothing to reduce."""
+def attach_tally_tensor(solve, n_jobs: int, device: int = 0):
+    """Give ``solve`` a torch-owned per-iteration tally buffer and return the tensor view of its first ``n_jobs``
+    rows (the ray-split jobs, which come first) for in-place NCCL all-reduces; None when there is nothing to reduce.
+    The returned object keeps the whole buffer alive."""
     import torch
-    n = int(n_per_job) * int(n_jobs)
-    if n <= 0 or not ptr:
+    _, n_per_job = solve.device_iter_tallies()
+    if solve.n_local == 0 or n_jobs <= 0:
         return None
-    return torch.as_tensor(_DeviceBuffer(ptr, n), device=f"cuda:{device}")
+    full = torch.zeros(solve.n_local * n_per_job, dtype=torch.int64, device=f"cuda:{device}")
+    solve.set_iter_tally_buffer(full.data_ptr(), full.numel())
+    solve._tally_tensor = full
+    return full[: n_jobs * n_per_job]
 
 
 def all_reduce_device_(tensor, device: int = 0) -> None:

@@ -188,7 +188,7 @@ def _run_solve_shared(solve: _native.Solve, n_shared: int, min_iters: int, max_i
     from . import dist as D
     if max_iters <= 0:
         return
-    tally = D.device_int64_view(*solve.device_iter_tallies(), n_jobs=n_shared, device=device) if solve.n_local else None
+    tally = D.attach_tally_tensor(solve, n_shared, device)
     done = 0
     chunk = max(1, min(int(max_iters), max(int(min_iters), 1)))
     while done < max_iters:
@@ -222,7 +222,7 @@ def _context() -> _native.Context:
         import torch.distributed as dist
         if dist.get_backend() == "nccl":
             dev = torch.cuda.current_device()
-            return _native.Context.for_device(dev, torch.cuda.current_stream(dev).cuda_stream)
+            return _native.Context.for_device(dev, _native.torch_stream_handle(dev))
     return _native.Context.for_device()
 
 

@@ -75,7 +75,7 @@ def _worker(rank, world, port, out_dir):
     if world > 1:
         dist.init_process_group("gloo", rank=rank, world_size=world)
     _native.Solve = FakeSolve
-    D.device_int64_view = lambda buf, n_per_job, n_jobs, device=0: (buf[: n_per_job * n_jobs] if n_jobs else None)
+    D.attach_tally_tensor = lambda solve, n_jobs, device=0: (solve.iter_t[: solve.n_hist * n_jobs] if n_jobs and solve.n_local else None)
 
     class Obj:
         pass
