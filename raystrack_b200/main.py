@@ -274,7 +274,8 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
     return tallies, iters, totals
 
 
-def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Optional[PreparedSolver] = None):
+def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Optional[PreparedSolver] = None,
+                       _hook: Optional[dict] = None):
     """View factors between all meshes (reference main.py:1689-1945).
 
     Returns ``{emitter: {"<receiver>_front" | "<receiver>_back": F}}`` with only positive entries; with
@@ -338,7 +339,8 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
     work_sum = max(1.0, float(work.sum()))
     for i, (name_e, _, _) in enumerate(meshes):
         if not has_recv[i]:
-            _log(f"({i+1}/{n_surf}) [{name_e}] 0 iter, 0 rays -> 0.000s  (BVH={label}, device=gpu)")
+            if _hook is None:
+                _log(f"({i+1}/{n_surf}) [{name_e}] 0 iter, 0 rays -> 0.000s  (BVH={label}, device=gpu)")
             continue
         cols = np.nonzero(tallies[i])[0]
         with np.errstate(divide="ignore", invalid="ignore"):
@@ -351,10 +353,14 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
                 if not (c & 1) and areas[j] > 0.0:
                     result[meshes[j][0]][f"{name_e}_front"] = f * (areas[i] / areas[j])     # main.py:1926-1927
         result[name_e].update(row)
-        _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {elapsed * work[i] / work_sum:0.3f}s  "
-             f"(BVH={label}, device=gpu)")
+        if _hook is None:
+            _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {elapsed * work[i] / work_sum:0.3f}s  "
+                 f"(BVH={label}, device=gpu)")
 
     LAST_TIMING["assemble"] = time.perf_counter() - t_asm
+    if _hook is not None:
+        _hook.update(iters=iters, totals=totals, n_once=n_once, label=label, elapsed=elapsed)
+        return result
     if p["enforce_reciprocity_rowsum"]:
         from .reciprocity import enforce_reciprocity_and_rowsum
         with _Phase("reciprocity_rowsum"):
@@ -370,7 +376,8 @@ def view_factor(sender, receiver, params: MatrixParams, *, prepared: Optional[Pr
     return {s[0]: vf_all.get(s[0], {}) for s in senders}
 
 
-def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepared: Optional[PreparedSolver] = None):
+def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepared: Optional[PreparedSolver] = None,
+                                _hook: Optional[dict] = None):
     """Sky view factors per mesh (reference main.py:1957-2185): rays that hit no other active mesh and point
     upward are binned into the 145 Tregenza patches (``discrete=True``) or counted as one "Sky" entry."""
     if not isinstance(params, SkyParams):
@@ -393,7 +400,7 @@ def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepar
     keys = [f"Sky_Patch_{i}" for i in range(1, 146)] if discrete else ["Sky"]
     result: Dict[str, Dict[str, float]] = {name: {k: 0.0 for k in keys} for name, _, _ in meshes}
     n_surf = len(meshes)
-    if n_surf <= 1:                                                                    # main.py:1998-1999
+    if n_surf <= 1 and _hook is None:                                                  # main.py:1998-1999
         return result
 
     ctx = _context()
@@ -419,9 +426,51 @@ def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepar
             result[name_e].update({f"Sky_Patch_{k+1}": float(frac[k]) for k in range(145)})
         else:
             result[name_e]["Sky"] = float(int(counts[i, 0]) / denom)
-        _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {elapsed * work[i] / work_sum:0.3f}s  "
-             f"(BVH={label}, device=gpu)")
+        if _hook is None:
+            _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {elapsed * work[i] / work_sum:0.3f}s  "
+                 f"(BVH={label}, device=gpu)")
+    if _hook is not None:
+        _hook.update(iters=iters, totals=totals, n_once=n_once, label=label, elapsed=elapsed)
     return result
 
 
-__all__ = ["view_factor_matrix", "view_factor", "view_factor_to_tregenza_sky"]
+def outside_workflow_shareable(matrix_params: MatrixParams, sky_params: SkyParams) -> bool:
+    """True when the matrix and the sky solve may share one ray set (reference main.py:1185-1206): identical
+    ``samples, rays, seed, bvh, device, cuda_async, gpu_raygen`` and ``flip_faces=False`` on the matrix side."""
+    if bool(matrix_params.flip_faces):
+        return False
+    fields = ("samples", "rays", "seed", "bvh", "device", "cuda_async", "gpu_raygen")
+    return all(getattr(matrix_params, k) == getattr(sky_params, k) for k in fields)
+
+
+def view_factor_matrix_and_sky(meshes: List[Mesh], *, matrix_params: MatrixParams, sky_params: SkyParams,
+                               prepared: Optional[PreparedSolver] = None):
+    """Scene view factors and sky view factors from the same per-iteration ray samples (reference
+    main.py:1209-1686).  Both sides converge independently and use, per emitter and iteration, exactly the rays the
+    separate solves would use, so the results equal ``view_factor_matrix`` + ``view_factor_to_tregenza_sky``
+    (the reference documents the same equivalence, main.py:1231-1234); the device runs the closest-hit and the
+    any-hit kernel of an iteration back to back on one stream, sharing scene, BVH, emitter tables and uploads.
+    ``enforce_reciprocity_rowsum`` is not applied here (main.py never does in this function)."""
+    if not isinstance(matrix_params, MatrixParams):
+        raise TypeError("matrix_params must be a MatrixParams instance")
+    if not isinstance(sky_params, SkyParams):
+        raise TypeError("sky_params must be a SkyParams instance")
+    if not outside_workflow_shareable(matrix_params, sky_params):
+        raise ValueError("matrix_params and sky_params are not compatible for shared tracing")
+    solver = _ensure_prepared(meshes, prepared)
+    mh: dict = {}
+    sh: dict = {}
+    vf_scene = view_factor_matrix(meshes, matrix_params, prepared=solver, _hook=mh)
+    sky_vf = view_factor_to_tregenza_sky(meshes, sky_params, prepared=solver, _hook=sh)
+    n = len(meshes)
+    for i, (name_e, _, _) in enumerate(meshes):
+        m_it, s_it = int(mh["iters"][i]), int(sh["iters"][i])
+        traced = max(m_it, s_it)
+        _log(f"({i+1}/{n}) [{name_e}] traced {traced} iter, {traced * int(mh['n_once'][i]):,} rays -> "
+             f"{(mh['elapsed'] + sh['elapsed']) / max(1, n):0.3f}s  (scene={m_it} iter, sky={s_it} iter, "
+             f"BVH={mh['label']}, device=gpu)")
+    return vf_scene, sky_vf
+
+
+__all__ = ["view_factor_matrix", "view_factor", "view_factor_to_tregenza_sky", "view_factor_matrix_and_sky",
+           "outside_workflow_shareable"]

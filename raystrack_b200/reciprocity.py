@@ -93,4 +93,52 @@ def enforce_reciprocity_and_rowsum(result: Dict[str, Dict[str, float]], meshes: 
     _write_back(result, names, F)
 
 
-__all__ = ["enforce_reciprocity_and_rowsum"]
+def enforce_reciprocity_only(result: Dict[str, Dict[str, float]], meshes: List[Mesh], tol: float = 1e-12) -> None:
+    """In place: A_i F_ij = A_j F_ji without touching the row sums (reference helpers.py:143-257):
+    ``g = (A_i F_ij + A_j F_ji) / 2``, ``F'_ij = g / A_i``, ``F'_ji = g / A_j``; pairs with both entries <= tol are
+    cleared; front/back keep their old proportions; entries <= tol are removed."""
+    if tol <= 0.0:
+        tol = 1e-12
+    names = [m[0] for m in meshes]
+    n = len(names)
+    A = _mesh_areas(meshes)
+    F = _totals_matrix(result, names)
+    G = 0.5 * (A[:, None] * F + (A[:, None] * F).T)               # symmetric by construction (same summation order)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        Fn = np.where(A[:, None] > 0.0, np.maximum(G / A[:, None], 0.0), 0.0)
+    dead = (F <= tol) & (F.T <= tol)
+    Fn[dead] = 0.0
+    for i, sname in enumerate(names):
+        row = result.get(sname, {})
+        if not isinstance(row, dict):
+            row = {}
+        fb: Dict[str, Tuple[float, float]] = {}
+        for k, v in row.items():
+            f, b = fb.get(_base(k), (0.0, 0.0))
+            if k.endswith("_front"):
+                fb[_base(k)] = (f + float(v), b)
+            else:
+                fb[_base(k)] = (f, b + float(v))
+        touched = set(np.nonzero(Fn[i])[0].tolist())
+        index = {nm: j for j, nm in enumerate(names)}
+        touched.update(index[b] for b in fb if b in index)
+        touched.discard(i)
+        for j in sorted(touched):
+            rname = names[j]
+            t_new = float(max(Fn[i, j], 0.0))
+            f, b = fb.get(rname, (0.0, 0.0))
+            t_old = f + b
+            if t_old > 0.0:
+                s_ = t_new / t_old
+                nf, nb = f * s_, b * s_
+            else:
+                nf, nb = 0.0, t_new
+            for key, val in ((f"{rname}_front", nf), (f"{rname}_back", nb)):
+                if val > tol:
+                    row[key] = val
+                elif key in row:
+                    del row[key]
+        result[sname] = row
+
+
+__all__ = ["enforce_reciprocity_and_rowsum", "enforce_reciprocity_only"]

@@ -30,3 +30,8 @@ def solves():
 @pytest.fixture(scope="session")
 def shipped():
     return json.loads((GOLDEN / "shipped.json").read_text())
+
+
+@pytest.fixture(scope="session")
+def workflow_golden():
+    return json.loads((GOLDEN / "workflow.json").read_text())

@@ -10,6 +10,7 @@ Outputs (committed):
                       hit masks, Tregenza patch ids  (reference functions called directly)
   solves.json         whole-solve results + per-emitter iteration counts for the BASELINE configs C1-C4,
                       two validation cases and the sky variants (reference public API, device="cpu")
+  workflow.json       view_factor_outside_workflow / view_factor_matrix_and_sky results (reference api.py, main.py:1209)
   shipped.json        the result files the reference ships (examples/*.json, validation/results/*), verbatim data
 """
 from __future__ import annotations
@@ -241,6 +242,42 @@ def solves():
     (HERE / "solves.json").write_text(json.dumps(out, indent=1, sort_keys=True))
 
 
+def workflow():
+    """view_factor_outside_workflow (api.py) and view_factor_matrix_and_sky (main.py:1209) on the canyon."""
+    from raystrack import view_factor_outside_workflow
+    from raystrack.main import view_factor_matrix_and_sky
+    canyon = load_meshes_json(str(REF / "examples" / "street_canyon.json"))
+    out = {}
+
+    def clean(d):
+        return {k: {kk: float(vv) for kk, vv in row.items()} for k, row in d.items()}
+
+    cases = {
+        "W1_shared_recip_merged": (dict(samples=8, rays=64, seed=4, bvh="off", device="cpu", max_iters=40, min_iters=6, tol=5e-4, reciprocity=True),
+                                   dict(samples=8, rays=64, seed=4, bvh="off", device="cpu", max_iters=30, min_iters=5, tol=5e-4, discrete=False)),
+        "W2_shared_discrete_rowsum": (dict(samples=8, rays=64, seed=4, bvh="builtin", device="cpu", max_iters=25, min_iters=6, tol=1e-3,
+                                           reciprocity=True, enforce_reciprocity_rowsum=True),
+                                      dict(samples=8, rays=64, seed=4, bvh="builtin", device="cpu", max_iters=12, min_iters=12, tol=0.0, discrete=True)),
+        "W3_separate_norecip": (dict(samples=8, rays=64, seed=4, bvh="off", device="cpu", max_iters=20, min_iters=6, tol=1e-3, reciprocity=False),
+                                dict(samples=6, rays=32, seed=9, bvh="off", device="cpu", max_iters=15, min_iters=5, tol=1e-3, discrete=False)),
+    }
+    old = ref_main._log
+    ref_main._log = lambda m: None
+    try:
+        for name, (mp, sp) in cases.items():
+            vf, sky, rest = view_factor_outside_workflow(canyon, matrix_params=MatrixParams(**mp), sky_params=SkyParams(**sp))
+            out[name] = {"matrix_params": MatrixParams(**mp).as_dict(), "sky_params": SkyParams(**sp).as_dict(),
+                         "vf_scene": clean(vf), "sky_vf": clean(sky), "rest_vf": clean(rest)}
+            print(name, "done")
+        mp, sp = cases["W1_shared_recip_merged"]
+        vf, sky = view_factor_matrix_and_sky(canyon[:1], matrix_params=MatrixParams(**mp), sky_params=SkyParams(**sp))
+        out["W4_single_mesh_shared"] = {"matrix_params": MatrixParams(**mp).as_dict(), "sky_params": SkyParams(**sp).as_dict(),
+                                        "vf_scene": clean(vf), "sky_vf": clean(sky)}
+    finally:
+        ref_main._log = old
+    (HERE / "workflow.json").write_text(json.dumps(out, indent=1, sort_keys=True))
+
+
 def shipped():
     out = {}
     for rel in ("examples/vf_matrix.json", "examples/inside_vf_matrix.json",
@@ -259,10 +296,12 @@ def shipped():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["stage", "solves", "shipped"]
+    what = sys.argv[1:] or ["stage", "solves", "shipped", "workflow"]
     if "stage" in what:
         stage_vectors()
     if "solves" in what:
         solves()
     if "shipped" in what:
         shipped()
+    if "workflow" in what:
+        workflow()

@@ -298,3 +298,41 @@ def test_reciprocity_rowsum_kernel(rb, ctx):
     assert np.allclose(got, want, rtol=0, atol=1e-11)
     assert np.allclose(got.sum(1), 1.0, atol=1e-8)
     assert np.allclose(A[:, None] * got, (A[:, None] * got).T, atol=1e-12)
+
+
+@pytest.mark.parametrize("case", ["W1_shared_recip_merged", "W2_shared_discrete_rowsum", "W3_separate_norecip"])
+def test_outside_workflow_matches_reference(rb, workflow_golden, case):
+    """view_factor_outside_workflow (reference api.py:24-194) incl. shared-ray solve, reciprocity-only and
+    row-sum enforcement, against the reference's own output on the canyon."""
+    import raystrack_b200.main as M
+    from raystrack_b200 import synthetic
+    g = workflow_golden[case]
+    old = M._log
+    M._log = lambda m: None
+    try:
+        vf, sky, rest = rb.view_factor_outside_workflow(synthetic.street_canyon(), matrix_params=rb.MatrixParams(**g["matrix_params"]),
+                                                        sky_params=rb.SkyParams(**g["sky_params"]))
+    finally:
+        M._log = old
+    for got, want, tol in ((vf, g["vf_scene"], 2e-5), (sky, g["sky_vf"], 2e-5), (rest, g["rest_vf"], 5e-5)):
+        for name in want:
+            for key in set(want[name]) | set(got[name]):
+                assert abs(got[name].get(key, 0.0) - want[name].get(key, 0.0)) <= tol, (name, key)
+
+
+def test_matrix_and_sky_single_mesh(rb, workflow_golden):
+    """The shared-ray entry point computes the sky of a lone mesh (main.py:1277-1286), unlike the plain sky solve."""
+    import raystrack_b200.main as M
+    from raystrack_b200 import synthetic
+    g = workflow_golden["W4_single_mesh_shared"]
+    logs = []
+    old = M._log
+    M._log = logs.append
+    try:
+        vf, sky = M.view_factor_matrix_and_sky(synthetic.street_canyon()[:1], matrix_params=rb.MatrixParams(**g["matrix_params"]),
+                                               sky_params=rb.SkyParams(**g["sky_params"]))
+    finally:
+        M._log = old
+    assert vf == {"east_side_0": {}}
+    assert abs(sky["east_side_0"]["Sky"] - g["sky_vf"]["east_side_0"]["Sky"]) <= 2e-5
+    assert "traced" in logs[0] and "scene=0 iter" in logs[0]
