@@ -68,7 +68,7 @@ int rsk_ctx_device_info(rsk_ctx *ctx, char *name, int64_t *info);
  * (utils/prepared.py:170-243, 381-403; utils/bvh.py:14-72).
  * Input is the reference's flattened scene in mesh order: v0,e1,e2,normals float32[n_tri,3], sid int32[n_tri]
  * (mesh index of each triangle, 0 <= sid < n_surf).  With use_bvh != 0 the library builds, on the GPU, a
- * Morton-code LBVH and collapses it into 80-byte 8-wide quantised nodes; otherwise rays test every triangle
+ * Morton-code LBVH and collapses it into 96-byte 8-wide quantised nodes; otherwise rays test every triangle
  * in input order (the reference's bvh="off" path, same tie order). */
 int rsk_scene_create(rsk_ctx *ctx, const float *v0, const float *e1, const float *e2, const float *normals,
                      const int32_t *sid, int64_t n_tri, int32_t n_surf, int32_t use_bvh, rsk_scene **out);
@@ -76,7 +76,7 @@ int rsk_scene_destroy(rsk_scene *scene);
 /* info: [0]=n_tri, [1]=n_surf, [2]=use_bvh, [3]=wide nodes, [4]=node bytes, [5]=triangle bytes,
  *       [6]=wide-tree depth, [7]=build time in microseconds (device). */
 int rsk_scene_info(rsk_scene *scene, int64_t *info);
-/* Test hook: copy the wide BVH back.  nodes: n_nodes*80 bytes; tri_index: int32[n_tri] = input index of the
+/* Test hook: copy the wide BVH back.  nodes: n_nodes*96 bytes; tri_index: int32[n_tri] = input index of the
  * triangle stored at each slot of the traversal-order triangle array.  Either pointer may be NULL. */
 int rsk_scene_download_bvh(rsk_scene *scene, void *nodes, int32_t *tri_index);
 

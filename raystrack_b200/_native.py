@@ -164,7 +164,7 @@ class DeviceScene:
 
     def download_bvh(self):
         inf = self.info()
-        nodes = np.empty((inf["n_nodes"], 80), np.uint8)
+        nodes = np.empty((inf["n_nodes"], 96), np.uint8)
         order = np.empty(inf["n_tri"], np.int32)
         check(self.ctx.lib.rsk_scene_download_bvh(self.handle, ptr(nodes), ptr(order)))
         return nodes, order

@@ -353,10 +353,11 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
     const int64_t tiles[2] = {0, n_tiles};
     const int32_t zero = 0;
     const int64_t range[2] = {first_ray, first_ray + n_rays};
+    const int32_t msid1 = mode == MODE_MATRIX ? min_sid : 0;
 
-    uint32_t *d_mask = nullptr; float *d_cp = nullptr; int32_t *d_ids = nullptr, *d_zero = nullptr; int64_t *d_tiles = nullptr, *d_range = nullptr;
+    uint32_t *d_mask = nullptr; float *d_cp = nullptr; int32_t *d_ids = nullptr, *d_zero = nullptr; int64_t *d_tiles = nullptr, *d_range = nullptr; int32_t *d_msid = nullptr;
     float *d_orig = nullptr, *d_dirs = nullptr; int32_t *d_hit = nullptr; uint8_t *d_front = nullptr;
-    auto cleanup = [&]() { rsk_dev_free(d_mask); rsk_dev_free(d_cp); rsk_dev_free(d_ids); rsk_dev_free(d_zero); rsk_dev_free(d_tiles); rsk_dev_free(d_range);
+    auto cleanup = [&]() { rsk_dev_free(d_mask); rsk_dev_free(d_cp); rsk_dev_free(d_ids); rsk_dev_free(d_zero); rsk_dev_free(d_tiles); rsk_dev_free(d_range); rsk_dev_free(d_msid);
                            rsk_dev_free(d_orig); rsk_dev_free(d_dirs); rsk_dev_free(d_hit); rsk_dev_free(d_front); };
     int rc = RSK_OK;
 #define T_TRY(expr) do { rc = (expr); if (rc != RSK_OK) { cleanup(); return rc; } } while (0)
@@ -367,6 +368,7 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
     T_TRY(rsk_upload(ctx, &d_zero, &zero, 1));
     T_TRY(rsk_upload(ctx, &d_tiles, tiles, 2));
     T_TRY(rsk_upload(ctx, &d_range, range, 2));
+    T_TRY(rsk_upload(ctx, &d_msid, &msid1, 1));
     if (orig) T_TRY(rsk_dev_alloc(&d_orig, (size_t)n_rays * 3));
     if (dirs) T_TRY(rsk_dev_alloc(&d_dirs, (size_t)n_rays * 3));
     if (hit_sid) T_TRY(rsk_dev_alloc(&d_hit, (size_t)n_rays));
@@ -379,7 +381,7 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
     a.emit_ids = d_ids; a.tile_start = d_tiles; a.n_local = 1; a.surf_mask = d_mask;
     a.cp_table = d_cp; a.rot_base = d_zero; a.iters_done = d_zero; a.done = nullptr; a.tally = nullptr;
     a.n_hist = mode == MODE_MATRIX ? 2 * scene->n_surf : RSK_TREGENZA_BINS;
-    a.ray_begin = d_range; a.ray_end = d_range + 1; a.dbg_base = first_ray;
+    a.ray_begin = d_range; a.ray_end = d_range + 1; a.dbg_base = first_ray; a.min_sid = d_msid;
     a.dbg_orig = d_orig; a.dbg_dirs = d_dirs; a.dbg_hit = d_hit; a.dbg_front = d_front;
     T_TRY(rsk_launch_trace(ctx, a, mode, n_tiles));
     if (orig) T_CUDA(cudaMemcpyAsync(orig, d_orig, (size_t)n_rays * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -405,6 +407,7 @@ struct rsk_solve {
     rsk_solve_params p{};
     int64_t n_tiles = 0;
     // device state
+    int32_t *min_sid = nullptr;
     int32_t *emit_ids = nullptr, *rot_base = nullptr, *iters_done = nullptr, *done = nullptr, *not_conv = nullptr, *have_prev = nullptr;
     int64_t *tile_start = nullptr, *n_rays_once = nullptr, *total_rays = nullptr, *ray_begin = nullptr, *ray_end = nullptr;
     uint32_t *mask = nullptr;
@@ -437,11 +440,13 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
     const int nw = std::max((scene->n_surf + 31) / 32, 1);
     std::vector<uint32_t> mask((size_t)n_local * nw);
     std::vector<int64_t> tiles(n_local + 1, 0), once(n_local), rbeg(n_local), rend(n_local);
+    std::vector<int32_t> msid(n_local, 0);
     int rc = RSK_OK;
     for (int k = 0; k < n_local; ++k) {
         if (emit_ids[k] < 0 || emit_ids[k] >= em->n_emit) { rsk_set_error("solve begin: emitter id out of range"); rc = RSK_ERR_INVALID; break; }
         if (rot_base[k] < 0 || (int64_t)rot_base[k] + std::max(params->max_iters, 0) > n_rot) { rsk_set_error("solve begin: rotation table too short"); rc = RSK_ERR_INVALID; break; }
         const int es = emit_sid ? emit_sid[k] : emit_ids[k], ms = min_sid ? min_sid[k] : 0;
+        msid[k] = ms;
         rsk_pack_mask(surf_active + (size_t)k * scene->n_surf, scene->n_surf, es, ms, mask.data() + (size_t)k * nw);
         once[k] = em->h_desc[emit_ids[k]].n_rays_once;
         rbeg[k] = ray_range ? ray_range[2 * k] : 0;
@@ -457,6 +462,7 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
 #define S_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rsk_set_error("%s failed: %s", #call, cudaGetErrorString(e__)); return fail(e__ == cudaErrorMemoryAllocation ? RSK_ERR_OOM : RSK_ERR_CUDA); } } while (0)
     S_TRY(rsk_upload(ctx, &s->emit_ids, emit_ids, n_local));
     S_TRY(rsk_upload(ctx, &s->rot_base, rot_base, n_local));
+    S_TRY(rsk_upload(ctx, &s->min_sid, msid.data(), msid.size()));
     S_TRY(rsk_upload(ctx, &s->tile_start, tiles.data(), tiles.size()));
     S_TRY(rsk_upload(ctx, &s->n_rays_once, once.data(), once.size()));
     S_TRY(rsk_upload(ctx, &s->ray_begin, rbeg.data(), rbeg.size()));
@@ -505,7 +511,7 @@ static int rsk_solve_enqueue_trace_impl(rsk_solve *s) {
     a.ev = s->em->view();
     a.emit_ids = s->emit_ids; a.tile_start = s->tile_start; a.n_local = s->n_local; a.surf_mask = s->mask;
     a.cp_table = s->cp_table; a.rot_base = s->rot_base; a.iters_done = s->iters_done; a.done = s->done;
-    a.tally = s->iter_tally; a.n_hist = s->n_hist; a.ray_begin = s->ray_begin; a.ray_end = s->ray_end;
+    a.tally = s->iter_tally; a.n_hist = s->n_hist; a.ray_begin = s->ray_begin; a.ray_end = s->ray_end; a.min_sid = s->min_sid;
     return rsk_launch_trace(ctx, a, s->mode, s->n_tiles);
 }
 
@@ -706,7 +712,7 @@ extern "C" int rsk_solve_rays_traced(rsk_solve *s, int64_t *rays) {
 extern "C" int rsk_solve_destroy(rsk_solve *s) {
     if (!s) return RSK_OK;
     RskScope scope(s->ctx);
-    rsk_dev_free(s->emit_ids); rsk_dev_free(s->rot_base); rsk_dev_free(s->iters_done); rsk_dev_free(s->done); rsk_dev_free(s->not_conv);
+    rsk_dev_free(s->emit_ids); rsk_dev_free(s->min_sid); rsk_dev_free(s->rot_base); rsk_dev_free(s->iters_done); rsk_dev_free(s->done); rsk_dev_free(s->not_conv);
     rsk_dev_free(s->have_prev); rsk_dev_free(s->tile_start); rsk_dev_free(s->n_rays_once); rsk_dev_free(s->total_rays); rsk_dev_free(s->ray_begin); rsk_dev_free(s->ray_end); rsk_dev_free(s->mask);
     rsk_dev_free(s->cp_table); if (!s->external_tally) rsk_dev_free(s->iter_tally); rsk_dev_free(s->rays_traced); rsk_dev_free(s->total); rsk_dev_free(s->mean);
     rsk_dev_free(s->m2); rsk_dev_free(s->prev); rsk_dev_free(s->n_active);

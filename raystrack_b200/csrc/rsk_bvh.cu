@@ -1,4 +1,4 @@
-// rsk_bvh.cu -- GPU BVH builder: Morton-code LBVH (Karras 2012) collapsed into 80-byte 8-wide quantised nodes.
+// rsk_bvh.cu -- GPU BVH builder: Morton-code LBVH (Karras 2012) collapsed into 96-byte 8-wide quantised nodes.
 //
 // Replaces utils/bvh.py:14-72 (`build_bvh`, a recursive median split in Python: 20 s for 1M triangles) and the
 // permutation step of utils/prepared.py:223-228.  The tree is a different one (closest hits do not depend on
@@ -42,8 +42,8 @@ __global__ void k_tri_boxes(const float4 *__restrict__ tri, int n, float4 *blo, 
         const float3 p2 = make_float3(a.x + e2.x, a.y + e2.y, a.z + e2.z);
         lo = make_float3(fminf(a.x, fminf(p1.x, p2.x)), fminf(a.y, fminf(p1.y, p2.y)), fminf(a.z, fminf(p1.z, p2.z)));
         hi = make_float3(fmaxf(a.x, fmaxf(p1.x, p2.x)), fmaxf(a.y, fmaxf(p1.y, p2.y)), fmaxf(a.z, fmaxf(p1.z, p2.z)));
-        blo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
-        bhi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
+        blo[i] = make_float4(lo.x, lo.y, lo.z, a.w);     // .w carries the mesh id (min / max of the sub-tree later)
+        bhi[i] = make_float4(hi.x, hi.y, hi.z, a.w);
     }
     typedef cub::BlockReduce<float, 256> BR;
     __shared__ typename BR::TempStorage tmp;
@@ -77,7 +77,16 @@ __global__ void k_morton(const float4 *blo, const float4 *bhi, int n, const unsi
     const float3 smin = make_float3(float_from_ord(bounds[0]), float_from_ord(bounds[1]), float_from_ord(bounds[2]));
     const float3 smax = make_float3(float_from_ord(bounds[3]), float_from_ord(bounds[4]), float_from_ord(bounds[5]));
     const float4 lo = blo[i], hi = bhi[i];
+#ifndef RSK_MORTON_UNIFORM
+#define RSK_MORTON_UNIFORM 1
+#endif
+#if RSK_MORTON_UNIFORM
+    // one scale for the three axes: Morton cells stay cubic even when the scene is flat (a city is 7x wider than tall)
+    const float ext = fmaxf(fmaxf(smax.x - smin.x, smax.y - smin.y), fmaxf(smax.z - smin.z, 1e-30f));
+    const float ex = ext, ey = ext, ez = ext;
+#else
     const float ex = fmaxf(smax.x - smin.x, 1e-30f), ey = fmaxf(smax.y - smin.y, 1e-30f), ez = fmaxf(smax.z - smin.z, 1e-30f);
+#endif
     const float cx = (0.5f * (lo.x + hi.x) - smin.x) / ex, cy = (0.5f * (lo.y + hi.y) - smin.y) / ey, cz = (0.5f * (lo.z + hi.z) - smin.z) / ez;
     const float s = 2097151.0f;
     const unsigned long long qx = (unsigned long long)fminf(fmaxf(cx * s, 0.f), s);
@@ -139,8 +148,10 @@ __global__ void k_refit(const unsigned *ids, const float4 *tlo, const float4 *th
         __threadfence();
         const int l = left[p], r = right[p];
         const float4 a = __ldcg(nlo + l), b = __ldcg(nlo + r), c = __ldcg(nhi + l), e = __ldcg(nhi + r);
-        nlo[p] = make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z), 0.f);
-        nhi[p] = make_float4(fmaxf(c.x, e.x), fmaxf(c.y, e.y), fmaxf(c.z, e.z), 0.f);
+        nlo[p] = make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z),
+                             __int_as_float(min(__float_as_int(a.w), __float_as_int(b.w))));
+        nhi[p] = make_float4(fmaxf(c.x, e.x), fmaxf(c.y, e.y), fmaxf(c.z, e.z),
+                             __int_as_float(max(__float_as_int(c.w), __float_as_int(e.w))));
         __threadfence();
         p = parent[p];
     }
@@ -247,6 +258,9 @@ __global__ void k_collapse(const CollapseArgs a) {
     int out_base = n_inner ? atomicAdd(a.n_out, n_inner) : 0;
 
     WideNode node;
+    node.sid_min = __float_as_int(a.nlo[bnode].w);
+    node.sid_max = __float_as_int(a.nhi[bnode].w);
+    node.reserved[0] = node.reserved[1] = 0u;
     node.ox = lo.x; node.oy = lo.y; node.oz = lo.z;
     const int ex = quant_exp(hi.x - lo.x, a.min_exp), ey = quant_exp(hi.y - lo.y, a.min_exp), ez = quant_exp(hi.z - lo.z, a.min_exp);
     node.ex = (uint8_t)(ex + 127); node.ey = (uint8_t)(ey + 127); node.ez = (uint8_t)(ez + 127);
@@ -304,12 +318,17 @@ __global__ void k_iota(int *p, int n) {
 // tiny scenes (<= RSK_LEAF_MAX triangles): a root whose only child is a leaf with every triangle
 __global__ void k_tiny_root(const float4 *tlo, const float4 *thi, int n, WideNode *nodes, float pad, int min_exp) {
     float3 lo = make_float3(3e38f, 3e38f, 3e38f), hi = make_float3(-3e38f, -3e38f, -3e38f);
+    int smin = 0x7fffffff, smax = -1;
     for (int i = 0; i < n; ++i) {
         lo = make_float3(fminf(lo.x, tlo[i].x - pad), fminf(lo.y, tlo[i].y - pad), fminf(lo.z, tlo[i].z - pad));
         hi = make_float3(fmaxf(hi.x, thi[i].x + pad), fmaxf(hi.y, thi[i].y + pad), fmaxf(hi.z, thi[i].z + pad));
+        smin = min(smin, __float_as_int(tlo[i].w));
+        smax = max(smax, __float_as_int(tlo[i].w));
     }
     WideNode node;
     memset(&node, 0, sizeof(node));
+    node.sid_min = smin;
+    node.sid_max = smax;
     node.ox = lo.x; node.oy = lo.y; node.oz = lo.z;
     const int e[3] = {quant_exp(hi.x - lo.x, min_exp), quant_exp(hi.y - lo.y, min_exp), quant_exp(hi.z - lo.z, min_exp)};
     node.ex = (uint8_t)(e[0] + 127); node.ey = (uint8_t)(e[1] + 127); node.ez = (uint8_t)(e[2] + 127);
@@ -445,7 +464,7 @@ int rsk_bvh_build(rsk_scene *sc, const float4 *tri_in, const float4 *nrm_in) {
     k_gather<<<rsk_blocks(n, 256), 256, 0, s>>>(tri_in, nrm_in, sc->tri_index, n, sc->tri, sc->nrm);
     ctx->launches++;
     uint4 *packed = nullptr;
-    B_TRY(rsk_dev_alloc(&packed, (size_t)n_nodes * 5));
+    B_TRY(rsk_dev_alloc(&packed, (size_t)n_nodes * RSK_NODE_WORDS));
     B_CUDA(cudaMemcpyAsync(packed, nodes, (size_t)n_nodes * sizeof(WideNode), cudaMemcpyDeviceToDevice, s));
     B_CUDA(cudaEventRecord(t1, s));
     B_CUDA(cudaStreamSynchronize(s));

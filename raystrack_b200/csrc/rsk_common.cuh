@@ -63,7 +63,8 @@ struct EmitterDesc {
     int64_t n_rays_once;     // g*g*rays_per_cell
 };
 
-// 80-byte compressed 8-wide BVH node (five 16-byte words, 16-byte aligned).
+// 96-byte compressed 8-wide BVH node (six 16-byte words, 32-byte aligned): the 80-byte compressed-wide-BVH record
+// plus the range of mesh ids below the node, which lets a ray drop whole sub-trees of surfaces it must ignore.
 struct __align__(16) WideNode {
     float ox, oy, oz;        // quantisation origin = node box minimum
     uint8_t ex, ey, ez;      // biased float exponents: cell size = 2^(e-127) per axis
@@ -73,14 +74,17 @@ struct __align__(16) WideNode {
     uint8_t meta[8];         // inner: 0x20|(24+s); leaf: (unary tri count)<<5 | first tri bit; empty: 0
     uint8_t qlo[3][8];       // quantised child boxes, [axis][slot]
     uint8_t qhi[3][8];
+    int32_t sid_min, sid_max;   // smallest / largest mesh id of the triangles below this node
+    uint32_t reserved[2];
 };
-static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
+static_assert(sizeof(WideNode) == 96, "WideNode must be 96 bytes");
+constexpr int RSK_NODE_WORDS = sizeof(WideNode) / 16;
 
 // Scene as the trace kernels see it.
 struct SceneView {
     const float4 *tri;       // 3 float4 per triangle: (v0, sid bits) (e1, -) (e2, -); traversal order
     const float4 *nrm;       // (unit normal, -) per triangle, same order
-    const uint4 *nodes;      // WideNode array as 5 x uint4 (null without BVH)
+    const uint4 *nodes;      // WideNode array as RSK_NODE_WORDS x uint4 (null without BVH)
     int32_t n_tri;
     int32_t n_surf;
     int32_t use_bvh;
@@ -164,6 +168,7 @@ struct TraceArgs {
     const int32_t *rot_base;        // [n_local]
     const int32_t *iters_done;      // [n_local] (device state)
     const int32_t *done;            // [n_local] (device state), may be null
+    const int32_t *min_sid;         // [n_local] surfaces with a smaller id are ignored (reciprocity), may be null (= 0)
     unsigned long long *tally;      // [n_local][n_hist]
     int32_t n_hist;                 // matrix: 2*n_surf; sky: 145 or 1
     int32_t hist_in_smem;

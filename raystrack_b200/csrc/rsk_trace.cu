@@ -14,6 +14,9 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef RSK_MIN_CTAS_PER_SM
 #define RSK_MIN_CTAS_PER_SM 4
 #endif
+#ifndef RSK_RAY_PERMUTE
+#define RSK_RAY_PERMUTE 0       // measured: no gain on B200 (profiles/kernel_variants_r1.md)
+#endif
 #ifndef RSK_REFILL_BELOW
 #define RSK_REFILL_BELOW 20
 #endif
@@ -91,11 +94,22 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
     for (int i = tid; i < hist_words; i += RSK_TILE_THREADS) s_hist[i] = 0;
     __syncthreads();
 
+    const int job_min_sid = a.min_sid ? a.min_sid[job] : 0;
     unsigned long long *g_tally = a.tally ? a.tally + (int64_t)job * a.n_hist : nullptr;
 
+    // Each warp owns 512 consecutive *positions* of the tile.  Position p maps to ray begin + c + STRIDE*m with
+    // (c, m) enumerating the residue classes mod STRIDE = 77 = 7*11 one after the other: rays of one class share the
+    // leading base-7 and base-11 Halton digits, i.e. the same elevation band and azimuth sector (ray_builder.py:75-80
+    // draws r1, r2 from bases 7 and 11), so the 32 rays a warp holds at a time point the same way from neighbouring
+    // cells -- coherent node visits instead of 32 unrelated directions.  Tallies do not depend on the order.
     constexpr int WARP_RAYS = RSK_TILE_RAYS / (RSK_TILE_THREADS / 32);
-    int64_t next = begin + (int64_t)warp * WARP_RAYS;
-    const int64_t wend = min(next + WARP_RAYS, end);
+    const int tile_n = (int)(end - begin);
+    int next = warp * WARP_RAYS;
+    const int wend = min(next + WARP_RAYS, tile_n);
+#if RSK_RAY_PERMUTE
+    constexpr int STRIDE = 77;
+    const int cls_q = tile_n / STRIDE, cls_r = tile_n % STRIDE, cls_split = cls_r * (cls_q + 1);
+#endif
 
     Walk w;
     bool active = false;
@@ -117,8 +131,17 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
         // ---- refill idle lanes with fresh rays
         const unsigned need = __ballot_sync(FULL, !active);
         if (need) {
-            const int64_t idx = next + __popc(need & ((1u << lane) - 1u));
-            if (!active && idx < wend) {
+            const int pos = next + __popc(need & ((1u << lane) - 1u));
+            if (!active && pos < wend) {
+                int local = pos;
+#if RSK_RAY_PERMUTE
+                if (cls_q > 0) {
+                    const bool big = pos < cls_split;
+                    const int p2 = big ? pos : pos - cls_split, len = big ? cls_q + 1 : cls_q;
+                    local = (big ? 0 : cls_r) + p2 / len + STRIDE * (p2 % len);
+                }
+#endif
+                const int64_t idx = begin + local;
                 my_k = idx;
                 const Ray r = rsk_make_ray(a.ev, e, idx, cp);
                 rsk_walk_begin(w, r);
@@ -135,26 +158,32 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
             // B200 -- profiles/kernel_variants_r1.md -- because lanes idle through other lanes' node steps.)
             while (active) {
                 bool finished = false, any_hit = false;
-                if (w.ng.y <= 0x00ffffffu) {
-                    if (w.sp == 0) finished = true;
-                    else {
+                uint32_t node = 0;
+                // next node worth testing: children whose whole sub-tree is ignorable for this emitter are dropped
+                // here for the price of one 8-byte load instead of a full 8-box test and a descent
+                for (;;) {
+                    if (w.ng.y <= 0x00ffffffu) {
+                        if (w.sp == 0) { finished = true; break; }
                         --w.sp;
                         w.ng = w.sp < RSK_SMEM_STACK ? s_stack[w.sp * RSK_TILE_THREADS + tid] : spill[w.sp - RSK_SMEM_STACK];
                     }
-                }
-                if (!finished) {
                     const int bit = 31 - __clz(w.ng.y);
                     w.ng.y &= ~(1u << bit);
-                    const uint32_t imask = w.ng.y & 0xffu;
+                    const uint32_t slot = (uint32_t)(bit - 24) ^ w.octinv;
+                    node = w.ng.x + __popc(w.ng.y & 0xffu & ((1u << slot) - 1u));
+#if RSK_SUBTREE_SKIP == 1
+                    if (rsk_node_ignorable(a.sc.nodes, node, s_mask, job_min_sid)) continue;
+#endif
+                    break;
+                }
+                if (!finished) {
                     if (w.ng.y > 0x00ffffffu) {
                         if (w.sp < RSK_SMEM_STACK) s_stack[w.sp * RSK_TILE_THREADS + tid] = w.ng;
                         else if (w.sp < RSK_MAX_DEPTH) spill[w.sp - RSK_SMEM_STACK] = w.ng;
                         if (w.sp < RSK_MAX_DEPTH) ++w.sp;
                     }
-                    const uint32_t slot = (uint32_t)(bit - 24) ^ w.octinv;
-                    const uint32_t rel = __popc(imask & ((1u << slot) - 1u));
                     uint2 ng2, tg;
-                    rsk_test_node(a.sc.nodes, w.ng.x + rel, w, MODE == MODE_MATRIX ? w.best : RSK_INF, ng2, tg);
+                    rsk_test_node(a.sc.nodes, node, w, MODE == MODE_MATRIX ? w.best : RSK_INF, ng2, tg, s_mask, job_min_sid);
                     while (tg.y) {
                         const int b = __ffs(tg.y) - 1;
                         tg.y &= tg.y - 1u;

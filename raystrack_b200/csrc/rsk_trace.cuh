@@ -44,6 +44,7 @@ struct Walk {
     uint2 ng;                // current node group: x = first inner child, y = hit bits<<24 | imask
     int sp;
     uint32_t octinv;         // bit a set: direction component a >= 0
+    uint32_t octinv4;        // octinv replicated into four bytes
 };
 
 __device__ __forceinline__ float rsk_safe_inv(float d) {
@@ -56,6 +57,7 @@ __device__ __forceinline__ void rsk_walk_begin(Walk &w, const Ray &r) {
     w.ix = rsk_safe_inv(r.dx); w.iy = rsk_safe_inv(r.dy); w.iz = rsk_safe_inv(r.dz);
     w.best = RSK_INF; w.best_tri = -1;
     w.octinv = (r.dx >= 0.0f ? 1u : 0u) | (r.dy >= 0.0f ? 2u : 0u) | (r.dz >= 0.0f ? 4u : 0u);
+    w.octinv4 = w.octinv * 0x01010101u;
     w.ng = make_uint2(0u, 0x80000000u);     // pseudo group whose only child is the root
     w.sp = 0;
 }
@@ -67,12 +69,33 @@ __device__ __forceinline__ void rsk_walk_begin(Walk &w, const Ray &r) {
 // are the busy ones.
 __device__ __forceinline__ float rsk_byte(uint32_t word, int j) { return (float)((word >> (8 * j)) & 0xffu); }
 
+#ifndef RSK_SUBTREE_SKIP
+#define RSK_SUBTREE_SKIP 2
+#endif
+// True when no triangle below node `idx` can matter to this ray: every mesh id there is below the job's `min_sid`
+// (reciprocity: receivers j <= i are ignored, main.py:1181-1182), or the sub-tree belongs to a single mesh that is
+// switched off for this emitter (its own mesh, or a mesh behind its plane, main.py:167-204).  One 8-byte load.
+__device__ __forceinline__ bool rsk_node_ignorable(const uint4 *__restrict__ nodes, uint32_t idx, const uint32_t *mask, int min_sid) {
+    const int2 r = __ldg(reinterpret_cast<const int2 *>(nodes + RSK_NODE_WORDS * (size_t)idx + 5));
+    return r.y < min_sid || (r.x == r.y && !rsk_surface_on(mask, r.x));
+}
+
 // Slab test of the 8 quantised child boxes of node `idx` against the ray over [0, tmax].
 // Returns the new node group (inner children hit, priority-permuted) and the 24-bit triangle mask.
 __device__ __forceinline__ void rsk_test_node(const uint4 *__restrict__ nodes, uint32_t idx, const Walk &w, float tmax,
-                                              uint2 &ng, uint2 &tg) {
-    const uint4 *p = nodes + 5 * (size_t)idx;
+                                              uint2 &ng, uint2 &tg, const uint32_t *mask, int min_sid) {
+    const uint4 *p = nodes + RSK_NODE_WORDS * (size_t)idx;
     const uint4 n0 = __ldg(p), n1 = __ldg(p + 1), n2 = __ldg(p + 2), n3 = __ldg(p + 3), n4 = __ldg(p + 4);
+#if RSK_SUBTREE_SKIP == 2
+    {   // all six words are requested together; an ignorable sub-tree costs the loads but no test and no descent
+        const int2 r = __ldg(reinterpret_cast<const int2 *>(p + 5));
+        if (r.y < min_sid || (r.x == r.y && !rsk_surface_on(mask, r.x))) {
+            ng = make_uint2(0u, 0u);
+            tg = make_uint2(0u, 0u);
+            return;
+        }
+    }
+#endif
     const uint32_t imask = n0.w >> 24;
     const float adx = __uint_as_float((n0.w & 0xffu) << 23) * w.ix;
     const float ady = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * w.iy;
@@ -83,6 +106,9 @@ __device__ __forceinline__ void rsk_test_node(const uint4 *__restrict__ nodes, u
     // byte planes: n2 = qlo.x[0..7] qlo.y[0..7]; n3 = qlo.z[0..7] qhi.x[0..7]; n4 = qhi.y[0..7] qhi.z[0..7]
     const bool px = w.octinv & 1u, py = w.octinv & 2u, pz = w.octinv & 4u;
     uint32_t hits = 0;
+#ifndef RSK_MASK4
+#define RSK_MASK4 1
+#endif
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const uint32_t meta = half ? n1.w : n1.z;
@@ -91,19 +117,30 @@ __device__ __forceinline__ void rsk_test_node(const uint4 *__restrict__ nodes, u
         const uint32_t nxw = px ? lox : hix, fxw = px ? hix : lox;
         const uint32_t nyw = py ? loy : hiy, fyw = py ? hiy : loy;
         const uint32_t nzw = pz ? loz : hiz, fzw = pz ? hiz : loz;
+#if RSK_MASK4
+        // four meta bytes at once: inner children (meta = 0b001_11sss) get their slot XOR-ed with the octant
+        // permutation, leaf children keep their first-triangle bit; empty slots have no bits to contribute
+        const uint32_t inner4 = (((meta & (meta << 1)) & 0x10101010u) >> 4) * 0xffu;
+        const uint32_t index4 = (meta ^ (w.octinv4 & inner4)) & 0x1f1f1f1fu;
+        const uint32_t bits4 = (meta >> 5) & 0x07070707u;
+#endif
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t m = (meta >> (8 * j)) & 0xffu;
             const float tnx = fmaf(rsk_byte(nxw, j), adx, bx), tfx = fmaf(rsk_byte(fxw, j), adx, bx);
             const float tny = fmaf(rsk_byte(nyw, j), ady, by), tfy = fmaf(rsk_byte(fyw, j), ady, by);
             const float tnz = fmaf(rsk_byte(nzw, j), adz, bz), tfz = fmaf(rsk_byte(fzw, j), adz, bz);
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+#if RSK_MASK4
+            if (tn <= tf) hits |= ((bits4 >> (8 * j)) & 0xffu) << ((index4 >> (8 * j)) & 0xffu);
+#else
+            const uint32_t m = (meta >> (8 * j)) & 0xffu;
             if (m != 0u && tn <= tf) {
                 uint32_t shift = m & 31u;
                 if (shift >= 24u) shift ^= w.octinv;     // inner child: priority = slot ^ octinv
                 hits |= (m >> 5) << shift;
             }
+#endif
         }
     }
     ng = make_uint2(n1.x, (hits & 0xff000000u) | imask);

@@ -10,11 +10,14 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
-VARIANTS = {
-    "regs64_refill20": ("RSK_MIN_CTAS_PER_SM=4", "RSK_REFILL_BELOW=20"),      # the shipped configuration
-    "regs80_refill20": ("RSK_MIN_CTAS_PER_SM=3", "RSK_REFILL_BELOW=20"),
-    "regs51_refill20": ("RSK_MIN_CTAS_PER_SM=5", "RSK_REFILL_BELOW=20"),
-    "regs64_refill24": ("RSK_MIN_CTAS_PER_SM=4", "RSK_REFILL_BELOW=24"),
+VARIANTS = {      # compile-time knobs of csrc/rsk_trace.cu(h) and csrc/rsk_bvh.cu; the product is built with the defaults
+    "shipped": (),
+    "no_subtree_skip": ("RSK_SUBTREE_SKIP=0",),
+    "skip_before_load": ("RSK_SUBTREE_SKIP=1",),
+    "scalar_hit_mask": ("RSK_MASK4=0",),
+    "ray_permute": ("RSK_RAY_PERMUTE=1",),
+    "morton_per_axis": ("RSK_MORTON_UNIFORM=0",),
+    "regs80": ("RSK_MIN_CTAS_PER_SM=3",),
 }
 OUT = ROOT / "raystrack_b200" / "_lib" / "variants"
 
@@ -27,7 +30,7 @@ if __name__ == "__main__":
         for name, defs in VARIANTS.items():
             if only and name not in only:
                 continue
-            print(name, _build.build(force=True, defines=defs, out=OUT / f"librsk_{name}.so"), flush=True)
+            print(name, _build.build(force=True, defines=defs or ("RSK_VARIANT_BUILD=1",), out=OUT / f"librsk_{name}.so"), flush=True)
     else:
         extra = sys.argv[2:] or ["--iters", "3"]
         for name in VARIANTS:

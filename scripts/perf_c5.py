@@ -17,6 +17,7 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--samples", type=int, default=4)
 ap.add_argument("--rays", type=int, default=64)
 ap.add_argument("--sky", action="store_true")
+ap.add_argument("--recip", action="store_true", help="reciprocity schedule: emitter i ignores meshes j <= i")
 args = ap.parse_args()
 
 t = time.time()
@@ -40,7 +41,7 @@ active = _surface_masks(ems, centers, extents)
 ids = np.arange(n, dtype=np.int32)
 table = _rotation_table(1, n, args.iters + 2)
 solve = _native.Solve(ctx, sc, em, ids, active, table, ids.copy(), max_iters=args.iters + 2, min_iters=args.iters + 2, interval=1,
-                      tol_mode="stderr", tol=0.0, emit_sid=ids, min_sid=np.zeros(n, np.int32), sky=args.sky, discrete=True)
+                      tol_mode="stderr", tol=0.0, emit_sid=ids, min_sid=(ids + 1) if args.recip else np.zeros(n, np.int32), sky=args.sky, discrete=True)
 solve.step(1)
 r0 = solve.rays_traced()
 ctx.timer_start()

@@ -133,6 +133,10 @@ def test_bvh_structure(ctx):
     seen = np.zeros(n_tri, np.int32)
     reach = np.zeros(nodes.shape[0], np.int32)
     reach[0] = 1
+    assert nodes.shape[1] == 96
+    sid_sorted = hs.sid[order]
+    node_sids = [set() for _ in range(nodes.shape[0])]
+    children = [[] for _ in range(nodes.shape[0])]
     for ni in range(nodes.shape[0]):
         raw = nodes[ni]
         o = raw[:12].view(np.float32)
@@ -152,6 +156,7 @@ def test_bvh_structure(ctx):
             if (imask >> s) & 1:
                 assert m == (0x20 | (24 + s))
                 reach[int(child_base) + rank] += 1
+                children[ni].append(int(child_base) + rank)
                 rank += 1
             else:
                 cnt = bin(m >> 5).count("1")
@@ -159,9 +164,16 @@ def test_bvh_structure(ctx):
                 for t in range(cnt):
                     ti = int(tri_base) + off + t
                     seen[ti] += 1
+                    node_sids[ni].add(int(sid_sorted[ti]))
                     assert np.all(lo_t[ti] >= lo - 1e-6) and np.all(hi_t[ti] <= hi + 1e-6), (ni, s, ti)
     assert np.all(seen == 1)
     assert np.all(reach == 1)
+    # mesh-id range stored in every node == range of the triangles below it (children have larger indices)
+    for ni in range(nodes.shape[0] - 1, -1, -1):
+        for c in children[ni]:
+            node_sids[ni] |= node_sids[c]
+        smin, smax = nodes[ni][80:88].view(np.int32)
+        assert (int(smin), int(smax)) == (min(node_sids[ni]), max(node_sids[ni])), ni
 
 
 SOLVE_CASES = ["C1_readme_squares", "C2_canyon_ex01", "C2b_canyon_delta_norecip", "C3_canyon_sky_discrete",
