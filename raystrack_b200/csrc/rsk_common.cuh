@@ -51,7 +51,10 @@ constexpr int RSK_TILE_RAYS = 4096;        // rays per CTA (one tile = 16 rays p
 constexpr int RSK_TREGENZA_BINS = 145;     // utils/cuda_trace.py:12
 constexpr float RSK_INF = 1.0e20f;         // utils/cpu_trace.py:8
 constexpr int RSK_WIDE = 8;                // fan-out of the wide BVH
-constexpr int RSK_LEAF_MAX = 3;            // triangles per leaf child (24 triangle bits per node)
+#ifndef RSK_LEAF_MAX_TRIS
+#define RSK_LEAF_MAX_TRIS 3
+#endif
+constexpr int RSK_LEAF_MAX = RSK_LEAF_MAX_TRIS;   // triangles per leaf child (<= 3: 24 triangle bits per node)
 constexpr int RSK_MAX_DEPTH_HOST = 32;     // traversal stack entries per ray (wide-tree depth limit)
 
 // One emitter mesh.  Triangle rows live in EmitterSet::tri[5][*] starting at tri_off.

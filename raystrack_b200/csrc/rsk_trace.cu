@@ -178,8 +178,11 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
                 }
                 if (!finished) {
                     if (w.ng.y > 0x00ffffffu) {
-                        if (w.sp < RSK_SMEM_STACK) s_stack[w.sp * RSK_TILE_THREADS + tid] = w.ng;
-                        else if (w.sp < RSK_MAX_DEPTH) spill[w.sp - RSK_SMEM_STACK] = w.ng;
+                        if (w.sp < RSK_SMEM_STACK) {
+                            s_stack[w.sp * RSK_TILE_THREADS + tid] = w.ng;
+                        } else if (w.sp < RSK_MAX_DEPTH) {
+                            spill[w.sp - RSK_SMEM_STACK] = w.ng;
+                        }
                         if (w.sp < RSK_MAX_DEPTH) ++w.sp;
                     }
                     uint2 ng2, tg;

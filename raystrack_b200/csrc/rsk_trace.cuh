@@ -64,10 +64,15 @@ __device__ __forceinline__ void rsk_walk_begin(Walk &w, const Ray &r) {
 
 // Byte j of `word` as a float without the (slow) integer->float conversion pipe: PRMT builds the bit pattern of
 // 2^23 + byte, one full-rate FADD removes the bias (exact).
-// Byte j of `word` as a float (shift + mask + I2F).  PRMT-based extraction and the 2^23-bias trick were measured
-// 5-7 % slower on B200 (profiles/kernel_variants_r1.md): the conversion pipe is otherwise idle, the ALU/FMA pipes
-// are the busy ones.
-__device__ __forceinline__ float rsk_byte(uint32_t word, int j) { return (float)((word >> (8 * j)) & 0xffu); }
+// How the quantised plane bytes become ray parameters.
+//   RSK_BYTE_MODE 0: t = float(byte) * (cell * 1/d) + (origin - o) * 1/d           -- one I2F (XU pipe) + one FFMA per plane
+//   RSK_BYTE_MODE 3: one PRMT drops the byte into mantissa bits 8..15 of the float 2.0, i.e. f = 2 + byte * 2^-14 exactly;
+//                    t = f * A + B with A = cell * 2^14 / d and B = (origin - o)/d - 2A            -- PRMT (ALU) + FFMA, no XU.
+//                    B carries a rounding error of <= 2^-9 cell, so the near/far biases are moved outwards by 2^-8 cell.
+// Measured equal within 1.5 % on B200 (profiles/kernel_variants_r1.md); mode 0 ships because it needs no error margin.
+#ifndef RSK_BYTE_MODE
+#define RSK_BYTE_MODE 0
+#endif
 
 #ifndef RSK_SUBTREE_SKIP
 #define RSK_SUBTREE_SKIP 2
@@ -97,18 +102,28 @@ __device__ __forceinline__ void rsk_test_node(const uint4 *__restrict__ nodes, u
     }
 #endif
     const uint32_t imask = n0.w >> 24;
-    const float adx = __uint_as_float((n0.w & 0xffu) << 23) * w.ix;
-    const float ady = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * w.iy;
-    const float adz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * w.iz;
-    const float bx = (__uint_as_float(n0.x) - w.ox) * w.ix;
-    const float by = (__uint_as_float(n0.y) - w.oy) * w.iy;
-    const float bz = (__uint_as_float(n0.z) - w.oz) * w.iz;
+#if RSK_BYTE_MODE == 3
+    const float ax = __uint_as_float(((n0.w & 0xffu) + 14u) << 23) * w.ix;          // cell * 2^14 / d
+    const float ay = __uint_as_float((((n0.w >> 8) & 0xffu) + 14u) << 23) * w.iy;
+    const float az = __uint_as_float((((n0.w >> 16) & 0xffu) + 14u) << 23) * w.iz;
+    const float cx = fmaf(-2.0f, ax, (__uint_as_float(n0.x) - w.ox) * w.ix);
+    const float cy = fmaf(-2.0f, ay, (__uint_as_float(n0.y) - w.oy) * w.iy);
+    const float cz = fmaf(-2.0f, az, (__uint_as_float(n0.z) - w.oz) * w.iz);
+    const float ex = fabsf(ax) * 0x1p-22f, ey = fabsf(ay) * 0x1p-22f, ez = fabsf(az) * 0x1p-22f;   // 2^-8 cell in t
+    const float bnx = cx - ex, bfx = cx + ex, bny = cy - ey, bfy = cy + ey, bnz = cz - ez, bfz = cz + ez;
+#define RSK_PLANE(word, j) __uint_as_float(__byte_perm(word, 0x40000000u, 0x7404u | ((unsigned)(j) << 4)))
+#else
+    const float ax = __uint_as_float((n0.w & 0xffu) << 23) * w.ix;
+    const float ay = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * w.iy;
+    const float az = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * w.iz;
+    const float bnx = (__uint_as_float(n0.x) - w.ox) * w.ix, bfx = bnx;
+    const float bny = (__uint_as_float(n0.y) - w.oy) * w.iy, bfy = bny;
+    const float bnz = (__uint_as_float(n0.z) - w.oz) * w.iz, bfz = bnz;
+#define RSK_PLANE(word, j) ((float)(((word) >> (8 * (j))) & 0xffu))
+#endif
     // byte planes: n2 = qlo.x[0..7] qlo.y[0..7]; n3 = qlo.z[0..7] qhi.x[0..7]; n4 = qhi.y[0..7] qhi.z[0..7]
     const bool px = w.octinv & 1u, py = w.octinv & 2u, pz = w.octinv & 4u;
     uint32_t hits = 0;
-#ifndef RSK_MASK4
-#define RSK_MASK4 1
-#endif
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const uint32_t meta = half ? n1.w : n1.z;
@@ -117,32 +132,22 @@ __device__ __forceinline__ void rsk_test_node(const uint4 *__restrict__ nodes, u
         const uint32_t nxw = px ? lox : hix, fxw = px ? hix : lox;
         const uint32_t nyw = py ? loy : hiy, fyw = py ? hiy : loy;
         const uint32_t nzw = pz ? loz : hiz, fzw = pz ? hiz : loz;
-#if RSK_MASK4
         // four meta bytes at once: inner children (meta = 0b001_11sss) get their slot XOR-ed with the octant
         // permutation, leaf children keep their first-triangle bit; empty slots have no bits to contribute
         const uint32_t inner4 = (((meta & (meta << 1)) & 0x10101010u) >> 4) * 0xffu;
         const uint32_t index4 = (meta ^ (w.octinv4 & inner4)) & 0x1f1f1f1fu;
         const uint32_t bits4 = (meta >> 5) & 0x07070707u;
-#endif
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float tnx = fmaf(rsk_byte(nxw, j), adx, bx), tfx = fmaf(rsk_byte(fxw, j), adx, bx);
-            const float tny = fmaf(rsk_byte(nyw, j), ady, by), tfy = fmaf(rsk_byte(fyw, j), ady, by);
-            const float tnz = fmaf(rsk_byte(nzw, j), adz, bz), tfz = fmaf(rsk_byte(fzw, j), adz, bz);
+            const float tnx = fmaf(RSK_PLANE(nxw, j), ax, bnx), tfx = fmaf(RSK_PLANE(fxw, j), ax, bfx);
+            const float tny = fmaf(RSK_PLANE(nyw, j), ay, bny), tfy = fmaf(RSK_PLANE(fyw, j), ay, bfy);
+            const float tnz = fmaf(RSK_PLANE(nzw, j), az, bnz), tfz = fmaf(RSK_PLANE(fzw, j), az, bfz);
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-#if RSK_MASK4
             if (tn <= tf) hits |= ((bits4 >> (8 * j)) & 0xffu) << ((index4 >> (8 * j)) & 0xffu);
-#else
-            const uint32_t m = (meta >> (8 * j)) & 0xffu;
-            if (m != 0u && tn <= tf) {
-                uint32_t shift = m & 31u;
-                if (shift >= 24u) shift ^= w.octinv;     // inner child: priority = slot ^ octinv
-                hits |= (m >> 5) << shift;
-            }
-#endif
         }
     }
+#undef RSK_PLANE
     ng = make_uint2(n1.x, (hits & 0xff000000u) | imask);
     tg = make_uint2(n1.y, hits & 0x00ffffffu);
 }

@@ -13,10 +13,11 @@ sys.path.insert(0, str(ROOT))
 VARIANTS = {      # compile-time knobs of csrc/rsk_trace.cu(h) and csrc/rsk_bvh.cu; the product is built with the defaults
     "shipped": (),
     "no_subtree_skip": ("RSK_SUBTREE_SKIP=0",),
-    "skip_before_load": ("RSK_SUBTREE_SKIP=1",),
-    "scalar_hit_mask": ("RSK_MASK4=0",),
+    "byte_prmt_mantissa": ("RSK_BYTE_MODE=3",),
     "ray_permute": ("RSK_RAY_PERMUTE=1",),
     "morton_per_axis": ("RSK_MORTON_UNIFORM=0",),
+    "ploc_r16": ("RSK_PLOC=1", "RSK_PLOC_RADIUS=16"),
+    "bottom16": ("RSK_BOTTOM_MAX=16",),
     "regs80": ("RSK_MIN_CTAS_PER_SM=3",),
 }
 OUT = ROOT / "raystrack_b200" / "_lib" / "variants"
