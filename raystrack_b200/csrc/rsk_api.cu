@@ -55,6 +55,7 @@ extern "C" int rsk_ctx_create(int device, void *stream, rsk_ctx **out) {
     }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
+    cudaMallocHost((void **)&ctx->h_pinned, 16 * sizeof(int32_t));
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -73,6 +74,7 @@ extern "C" int rsk_ctx_destroy(rsk_ctx *ctx) {
     rsk_dev_free(ctx->halton);
     rsk_dev_free(ctx->grid);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -476,7 +478,8 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
     S_TRY(rsk_dev_alloc(&s->mean, nh)); S_TRY(rsk_dev_alloc(&s->m2, nh));
     if (params->tol_mode == 1) S_TRY(rsk_dev_alloc(&s->prev, nh));
     S_TRY(rsk_dev_alloc(&s->n_active, 1)); S_TRY(rsk_dev_alloc(&s->rays_traced, 1));
-    S_CUDA(cudaMallocHost((void **)&s->h_pinned, 4 * sizeof(int32_t)));
+    s->h_pinned = ctx->h_pinned;
+    if (!s->h_pinned) { rsk_set_error("solve begin: context has no pinned scratch"); return fail(RSK_ERR_OOM); }
     cudaStream_t st = ctx->stream;
     const size_t nl = std::max(n_local, 1);
     S_CUDA(cudaMemsetAsync(s->iters_done, 0, nl * sizeof(int32_t), st));
@@ -716,7 +719,6 @@ extern "C" int rsk_solve_destroy(rsk_solve *s) {
     rsk_dev_free(s->have_prev); rsk_dev_free(s->tile_start); rsk_dev_free(s->n_rays_once); rsk_dev_free(s->total_rays); rsk_dev_free(s->ray_begin); rsk_dev_free(s->ray_end); rsk_dev_free(s->mask);
     rsk_dev_free(s->cp_table); if (!s->external_tally) rsk_dev_free(s->iter_tally); rsk_dev_free(s->rays_traced); rsk_dev_free(s->total); rsk_dev_free(s->mean);
     rsk_dev_free(s->m2); rsk_dev_free(s->prev); rsk_dev_free(s->n_active);
-    if (s->h_pinned) cudaFreeHost(s->h_pinned);
     delete s;
     return RSK_OK;
 }

@@ -113,6 +113,8 @@ struct rsk_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     int sm_count = 0;
+    int32_t *h_pinned = nullptr;      // small pinned scratch for asynchronous read-backs (allocated once: cudaFreeHost
+                                      // synchronises the whole device, so it must not sit on the per-solve path)
     // QMC caches (device)
     float *halton = nullptr;          // [5][halton_cap]
     int64_t halton_cap = 0;
