@@ -340,6 +340,22 @@ def run_ours(args):
             agree += int(np.sum((hit == hs) & (front == fr)))
             tot += cnt
         line["parity"] = {"per_ray_agreement": agree / tot, "rays_compared": tot}
+    # ---- the metric's second half: VF max abs error vs the reference, on the reference's own example config (C2:
+    # examples/ex01 street canyon, golden result generated by the reference itself: tests/golden/solves.json)
+    try:
+        from raystrack_b200 import synthetic
+        gold = json.loads((ROOT / "tests" / "golden" / "solves.json").read_text())["C2_canyon_ex01"]
+        M._log = lambda msg: None
+        res = view_factor_matrix(synthetic.street_canyon(), MatrixParams(**gold["params"]))
+        M._log = old_log
+        err = 0.0
+        for name, row in gold["result"].items():
+            for key in set(row) | set(res[name]):
+                err = max(err, abs(res[name].get(key, 0.0) - row.get(key, 0.0)))
+        line["vf_max_abs_err"] = {"value": err, "config": "C2 street canyon, ex01 params (11 meshes, reciprocity, stderr tol 1e-4)",
+                                  "against": "reference CPU result (tests/golden/solves.json), tolerance 1e-4"}
+    except Exception as e:      # noqa: BLE001
+        line["vf_max_abs_err"] = {"value": None, "error": str(e)[:200]}
     peak, peak_src = measured_peaks()
     achieved = my_rays * bytes_per_ray / (trace_avg_ms * 1e-3) / 1e9
     line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
