@@ -175,6 +175,21 @@ int rsk_solve_device_iter_tallies(rsk_solve *solve, void **device_ptr, int64_t *
  * buffer alive until rsk_solve_destroy. */
 int rsk_solve_set_iter_tally_buffer(rsk_solve *solve, void *device_ptr, int64_t n_elements);
 
+/* ------------------------------------------------------------------------------------------- shared-ray solve
+ * Replaces the loops of view_factor_matrix_and_sky (main.py:1277-1660) and trace_cpu_[bvh_]combined
+ * (utils/cpu_trace.py:280-522): per iteration ONE traversal per ray yields the closest receiver hit (matrix) and
+ * the any-hit flag (sky).  Both sides keep their own statistics and stop independently; when one side has
+ * converged the jobs degrade to the other side's plain walk.  rsk_dual_step = n_iters x (trace, matrix fold, sky
+ * fold); n_active counts running (job, side) pairs.  Results: rsk_solve_read_block on the returned handle (matrix
+ * side) and on the handle from rsk_dual_sky_part (sky side); rsk_solve_destroy on the returned handle frees both. */
+int rsk_dual_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, const int32_t *emit_ids, int32_t n_local,
+                   const uint8_t *surf_active, const int32_t *emit_sid, const int32_t *min_sid,
+                   const float *cp_table, int32_t n_rot, const int32_t *rot_base,
+                   const rsk_solve_params *matrix_params, const rsk_solve_params *sky_params, int32_t discrete,
+                   rsk_solve **out);
+int rsk_dual_step(rsk_solve *solve, int32_t n_iters, int32_t *n_active);
+int rsk_dual_sky_part(rsk_solve *solve, rsk_solve **sky);
+
 int rsk_solve_destroy(rsk_solve *solve);
 /* Rays traced so far by this solve (all emitters, all iterations). */
 int rsk_solve_rays_traced(rsk_solve *solve, int64_t *rays);

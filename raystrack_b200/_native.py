@@ -28,7 +28,7 @@ EXPORTS = (
     "rsk_emitters_create", "rsk_emitters_destroy", "rsk_emitters_download_tables",
     "rsk_trace_rays",
     "rsk_matrix_begin", "rsk_matrix_step", "rsk_matrix_read", "rsk_solve_read_block", "rsk_matrix_device_tallies",
-    "rsk_sky_begin", "rsk_sky_step", "rsk_sky_read",
+    "rsk_sky_begin", "rsk_sky_step", "rsk_sky_read", "rsk_dual_begin", "rsk_dual_step", "rsk_dual_sky_part",
     "rsk_solve_enqueue_trace", "rsk_solve_enqueue_fold", "rsk_solve_poll", "rsk_solve_device_iter_tallies", "rsk_solve_set_iter_tally_buffer",
     "rsk_solve_destroy", "rsk_solve_rays_traced", "rsk_reciprocity_rowsum",
 )
@@ -328,6 +328,62 @@ class Solve:
         n = C.c_int64(0)
         check(self.ctx.lib.rsk_solve_rays_traced(self.handle, C.byref(n)))
         return int(n.value)
+
+    def close(self) -> None:
+        if self.handle:
+            self.ctx.lib.rsk_solve_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _SolvePart:
+    """Read-only view of one side of a dual solve (shares Solve.read_block)."""
+
+    def __init__(self, ctx, scene, handle, n_local, sky, discrete):
+        self.ctx, self.scene, self.handle, self.n_local, self.sky, self.discrete = ctx, scene, handle, n_local, sky, discrete
+
+    read_block = Solve.read_block
+
+
+class DualSolve:
+    """Wraps a shared-ray solve (``rsk_dual_*``): one traversal per ray feeds the matrix and the sky tallies."""
+
+    def __init__(self, ctx: Context, scene: DeviceScene, em: DeviceEmitters, emit_ids, surf_active, cp_table, rot_base,
+                 emit_sid, min_sid, matrix: dict, sky: dict, discrete: bool):
+        for side in (matrix, sky):
+            if side["tol_mode"] not in ("stderr", "delta"):
+                raise ValueError(f"Unknown tol_mode: {side['tol_mode']}")
+        self.ctx, self.scene = ctx, scene
+        self.handle = C.c_void_p()
+        ids = np.ascontiguousarray(emit_ids, np.int32)
+        self.n_local = int(ids.shape[0])
+        act = np.ascontiguousarray(surf_active, np.uint8).reshape(self.n_local, scene.n_surf)
+        cpt = np.ascontiguousarray(cp_table, np.float32).reshape(-1, 7)
+        rb = np.ascontiguousarray(rot_base, np.int32)
+        es = np.ascontiguousarray(emit_sid, np.int32)
+        ms = np.ascontiguousarray(min_sid, np.int32)
+
+        def pack(d):
+            return SolveParams(int(d["max_iters"]), int(d["min_iters"]), int(d["interval"]), 0 if d["tol_mode"] == "stderr" else 1, float(d["tol"]))
+
+        pm, pk = pack(matrix), pack(sky)
+        check(ctx.lib.rsk_dual_begin(ctx.handle, scene.handle, em.handle, ptr(ids), C.c_int32(self.n_local), ptr(act), ptr(es), ptr(ms),
+                                     ptr(cpt), C.c_int32(cpt.shape[0]), ptr(rb), C.byref(pm), C.byref(pk),
+                                     C.c_int32(1 if discrete else 0), C.byref(self.handle)), "rsk_dual_begin")
+        sky_handle = C.c_void_p()
+        check(ctx.lib.rsk_dual_sky_part(self.handle, C.byref(sky_handle)), "rsk_dual_sky_part")
+        self.matrix_part = _SolvePart(ctx, scene, self.handle, self.n_local, False, False)
+        self.sky_part = _SolvePart(ctx, scene, sky_handle, self.n_local, True, bool(discrete))
+
+    def step(self, n_iters: int) -> int:
+        n_active = C.c_int32(0)
+        check(self.ctx.lib.rsk_dual_step(self.handle, C.c_int32(n_iters), C.byref(n_active)), "rsk_dual_step")
+        return int(n_active.value)
 
     def close(self) -> None:
         if self.handle:

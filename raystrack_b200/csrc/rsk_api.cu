@@ -422,6 +422,7 @@ struct rsk_solve {
     int32_t last_active = 0;
     bool stepped = false;
     bool external_tally = false;     // iter_tally belongs to the caller (rsk_solve_set_iter_tally_buffer)
+    rsk_solve *twin = nullptr;       // dual solves: the sky side (this object is the matrix side)
 };
 
 static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int mode, int discrete,
@@ -507,7 +508,7 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
 // so that a multi-GPU caller can all-reduce the iteration tallies of ray-split emitters in between.
 static int rsk_solve_enqueue_trace_impl(rsk_solve *s) {
     rsk_ctx *ctx = s->ctx;
-    if (s->n_local == 0 || s->p.max_iters <= 0) return RSK_OK;
+    if (s->n_local == 0 || (s->p.max_iters <= 0 && !(s->twin && s->twin->p.max_iters > 0))) return RSK_OK;
     TraceArgs a;
     memset(&a, 0, sizeof(a));
     a.sc = s->scene->view();
@@ -515,6 +516,11 @@ static int rsk_solve_enqueue_trace_impl(rsk_solve *s) {
     a.emit_ids = s->emit_ids; a.tile_start = s->tile_start; a.n_local = s->n_local; a.surf_mask = s->mask;
     a.cp_table = s->cp_table; a.rot_base = s->rot_base; a.iters_done = s->iters_done; a.done = s->done;
     a.tally = s->iter_tally; a.n_hist = s->n_hist; a.ray_begin = s->ray_begin; a.ray_end = s->ray_end; a.min_sid = s->min_sid;
+    if (s->twin) {
+        const rsk_solve *k = s->twin;
+        a.surf_mask2 = k->mask; a.iters_done2 = k->iters_done; a.done2 = k->done; a.tally2 = k->iter_tally; a.n_hist2 = k->n_hist;
+        return rsk_launch_trace(ctx, a, MODE_DUAL, s->n_tiles);
+    }
     return rsk_launch_trace(ctx, a, s->mode, s->n_tiles);
 }
 
@@ -680,6 +686,69 @@ extern "C" int rsk_matrix_device_tallies(rsk_solve *s, void **device_ptr, int64_
     return RSK_OK;
 }
 
+// ----------------------------------------------------------------------------- dual (shared-ray) solve
+extern "C" int rsk_dual_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, const int32_t *emit_ids, int32_t n_local,
+                              const uint8_t *surf_active, const int32_t *emit_sid, const int32_t *min_sid,
+                              const float *cp_table, int32_t n_rot, const int32_t *rot_base,
+                              const rsk_solve_params *matrix_params, const rsk_solve_params *sky_params, int32_t discrete,
+                              rsk_solve **out) {
+    RSK_REQUIRE(out && matrix_params && sky_params, "rsk_dual_begin: null argument");
+    RSK_REQUIRE(n_local == 0 || (emit_sid && min_sid), "rsk_dual_begin: null emit_sid/min_sid");
+    *out = nullptr;
+    rsk_solve *m = nullptr, *k = nullptr;
+    RSK_TRY(rsk_solve_begin(ctx, scene, em, MODE_MATRIX, 0, emit_ids, n_local, surf_active, emit_sid, min_sid, cp_table, n_rot, rot_base,
+                            nullptr, matrix_params, &m));
+    int rc = rsk_solve_begin(ctx, scene, em, MODE_SKY, discrete ? 1 : 0, emit_ids, n_local, surf_active, nullptr, nullptr, cp_table, n_rot,
+                             rot_base, nullptr, sky_params, &k);
+    if (rc != RSK_OK) { rsk_solve_destroy(m); return rc; }
+    m->twin = k;
+    // an emitter without receivers never starts its matrix side (main.py:1285-1287): mark it done up front
+    RskScope scope(ctx);
+    std::vector<int32_t> done(std::max(n_local, 1), 0);
+    int n_running = 0;
+    for (int j = 0; j < n_local; ++j) {
+        const int es = emit_sid[j], ms = min_sid[j];
+        bool any = false;
+        const uint8_t *row = surf_active + (size_t)j * scene->n_surf;
+        for (int s = std::max(ms, 0); s < scene->n_surf && !any; ++s) any = row[s] != 0 && s != es;
+        done[j] = (any && matrix_params->max_iters > 0) ? 0 : 1;
+        n_running += done[j] ? 0 : 1;
+    }
+    if (n_local > 0) {
+        cudaError_t e = cudaMemcpyAsync(m->done, done.data(), n_local * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { rsk_set_error("rsk_dual_begin: %s", cudaGetErrorString(e)); rsk_solve_destroy(m); return RSK_ERR_CUDA; }
+    }
+    m->last_active = n_running;
+    *out = m;
+    return RSK_OK;
+}
+
+extern "C" int rsk_dual_step(rsk_solve *s, int32_t n_iters, int32_t *n_active) {
+    RSK_REQUIRE(s && s->twin && n_iters >= 0, "rsk_dual_step: not a dual solve");
+    rsk_solve *k = s->twin;
+    RskScope scope(s->ctx);
+    if (s->last_active + k->last_active > 0) {
+        for (int it = 0; it < n_iters; ++it) {
+            RSK_TRY(rsk_solve_enqueue_trace_impl(s));
+            RSK_TRY(rsk_solve_enqueue_fold_impl(s));
+            RSK_TRY(rsk_solve_enqueue_fold_impl(k));
+            s->stepped = k->stepped = true;
+        }
+    }
+    int32_t am = 0, ak = 0;
+    RSK_TRY(rsk_solve_poll_impl(s, &am));
+    RSK_TRY(rsk_solve_poll_impl(k, &ak));
+    if (n_active) *n_active = am + ak;
+    return RSK_OK;
+}
+
+extern "C" int rsk_dual_sky_part(rsk_solve *s, rsk_solve **sky) {
+    RSK_REQUIRE(s && s->twin && sky, "rsk_dual_sky_part: not a dual solve");
+    *sky = s->twin;
+    return RSK_OK;
+}
+
 extern "C" int rsk_sky_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, const int32_t *emit_ids, int32_t n_local,
                              const uint8_t *surf_active, const float *cp_table, int32_t n_rot, const int32_t *rot_base,
                              const int64_t *ray_range, const rsk_solve_params *params, int32_t discrete, rsk_solve **out) {
@@ -714,6 +783,7 @@ extern "C" int rsk_solve_rays_traced(rsk_solve *s, int64_t *rays) {
 
 extern "C" int rsk_solve_destroy(rsk_solve *s) {
     if (!s) return RSK_OK;
+    if (s->twin) { rsk_solve_destroy(s->twin); s->twin = nullptr; }
     RskScope scope(s->ctx);
     rsk_dev_free(s->emit_ids); rsk_dev_free(s->min_sid); rsk_dev_free(s->rot_base); rsk_dev_free(s->iters_done); rsk_dev_free(s->done); rsk_dev_free(s->not_conv);
     rsk_dev_free(s->have_prev); rsk_dev_free(s->tile_start); rsk_dev_free(s->n_rays_once); rsk_dev_free(s->total_rays); rsk_dev_free(s->ray_begin); rsk_dev_free(s->ray_end); rsk_dev_free(s->mask);

@@ -175,6 +175,12 @@ struct TraceArgs {
     const int32_t *done;            // [n_local] (device state), may be null
     const int32_t *min_sid;         // [n_local] surfaces with a smaller id are ignored (reciprocity), may be null (= 0)
     unsigned long long *tally;      // [n_local][n_hist]
+    // MODE_DUAL only: the sky side of the same jobs (any-hit occluder mask, its own progress and tallies)
+    const uint32_t *surf_mask2;     // [n_local][mask_words], bit set = active non-emitter surface
+    const int32_t *iters_done2;     // [n_local]
+    const int32_t *done2;           // [n_local]
+    unsigned long long *tally2;     // [n_local][n_hist2]
+    int32_t n_hist2;                // 145 or 1
     int32_t n_hist;                 // matrix: 2*n_surf; sky: 145 or 1
     int32_t hist_in_smem;
     const int64_t *ray_begin;       // [n_local] first ray of each job's slice (null: 0)
@@ -185,7 +191,7 @@ struct TraceArgs {
     uint8_t *dbg_front;
 };
 
-enum { MODE_MATRIX = 0, MODE_SKY = 1 };
+enum { MODE_MATRIX = 0, MODE_SKY = 1, MODE_DUAL = 2 };
 
 // internal entry points shared between translation units
 int rsk_launch_trace(rsk_ctx *ctx, TraceArgs &a, int mode, int64_t n_tiles);

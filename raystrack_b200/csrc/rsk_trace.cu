@@ -14,9 +14,6 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef RSK_MIN_CTAS_PER_SM
 #define RSK_MIN_CTAS_PER_SM 4
 #endif
-#ifndef RSK_RAY_PERMUTE
-#define RSK_RAY_PERMUTE 0       // measured: no gain on B200 (profiles/kernel_variants_r1.md)
-#endif
 #ifndef RSK_REFILL_BELOW
 #define RSK_REFILL_BELOW 20
 #endif
@@ -24,19 +21,21 @@ constexpr int RSK_MIN_CTAS = RSK_MIN_CTAS_PER_SM;   // 4 CTAs x 256 threads per 
 constexpr int REFILL_BELOW = RSK_REFILL_BELOW;     // leave the traversal loop to fetch new rays when fewer lanes are busy
 
 
-template <int MODE>
-__device__ __forceinline__ int rsk_result_key(const TraceArgs &a, const Walk &w, bool any_hit) {
-    if (MODE == MODE_MATRIX) {
-        if (w.best_tri < 0) return -1;
+// Result bin of a finished ray, -1 = nothing to tally.  Matrix bins: 2*receiver + (front ? 0 : 1) (cpu_trace.py:114);
+// sky bins (after the matrix bins in MODE_DUAL): Tregenza patch or the single "Sky" counter (cpu_trace.py:735-798).
+__device__ __forceinline__ int rsk_result_key(const TraceArgs &a, const Walk &w, bool want_m, bool want_s, bool any_hit,
+                                              int sky_base, int n_sky) {
+    if (want_m && w.best_tri >= 0) {
         const float4 n = __ldg(a.sc.nrm + w.best_tri);
         const int sid = __float_as_int(n.w);
-        const bool front = -(w.dx * n.x + w.dy * n.y + w.dz * n.z) > 0.0f;     // cpu_trace.py:114
-        return 2 * sid + (front ? 0 : 1);                                       // interleaved (front, back) per receiver
-    } else {
-        if (any_hit) return -1;
-        if (a.n_hist == 1) return w.dz > 0.0f ? 0 : -1;                       // cpu_trace.py:796
-        return rsk_tregenza_patch(w.dx, w.dy, w.dz);
+        const bool front = -(w.dx * n.x + w.dy * n.y + w.dz * n.z) > 0.0f;
+        return 2 * sid + (front ? 0 : 1);
     }
+    if (want_s && !any_hit && w.best_tri < 0) {
+        const int patch = n_sky == 1 ? (w.dz > 0.0f ? 0 : -1) : rsk_tregenza_patch(w.dx, w.dy, w.dz);
+        return patch < 0 ? -1 : sky_base + patch;
+    }
+    return -1;
 }
 
 template <int MODE>
@@ -53,6 +52,11 @@ __device__ __forceinline__ void rsk_debug_store(const TraceArgs &a, int64_t k, c
     }
 }
 
+// MODE_MATRIX: closest hit among the receivers of the job.  MODE_SKY: any hit among the active non-emitter meshes,
+// misses binned by direction.  MODE_DUAL: both from one traversal (reference trace_cpu_[bvh_]combined,
+// cpu_trace.py:280-522): the closest receiver hit bounds the walk, every hit of an active mesh marks the ray as
+// occluded; a job whose matrix (sky) side has converged degrades to the sky-only (matrix-only) walk, exactly as the
+// reference's shared-ray loop does (main.py:1380-1547).
 template <int MODE, bool BVH>
 __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kernel(const TraceArgs a) {
     extern __shared__ uint32_t smem[];
@@ -70,7 +74,10 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
     }
     __syncthreads();
     const int job = s_job;
-    if (a.done && a.done[job]) return;
+    const bool side1_done = a.done && a.done[job];
+    const bool want_m = MODE == MODE_MATRIX ? true : (MODE == MODE_DUAL ? !side1_done : false);
+    const bool want_s = MODE == MODE_SKY ? true : (MODE == MODE_DUAL ? !a.done2[job] : false);
+    if (MODE == MODE_DUAL ? (!want_m && !want_s) : side1_done) return;
 
     const EmitterDesc e = a.ev.desc[a.emit_ids[job]];
     const int64_t tile = (int64_t)blockIdx.x - a.tile_start[job];
@@ -81,38 +88,47 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
 
     float cp[7];
     {
-        const float *row = a.cp_table + 7 * (int64_t)(a.rot_base[job] + a.iters_done[job]);
+        // both sides of a dual job run the same iteration number while both are alive
+        const int it = (MODE == MODE_DUAL && !want_m) ? a.iters_done2[job] : a.iters_done[job];
+        const float *row = a.cp_table + 7 * (int64_t)(a.rot_base[job] + it);
 #pragma unroll
         for (int i = 0; i < 7; ++i) cp[i] = __ldg(row + i);
     }
 
-    uint32_t *s_mask = smem;
-    uint32_t *s_hist = smem + a.sc.mask_words;
-    const int hist_words = a.hist_in_smem ? a.n_hist : 0;
-    uint2 *s_stack = reinterpret_cast<uint2 *>(smem + ((a.sc.mask_words + hist_words + 1) & ~1));
-    for (int i = tid; i < a.sc.mask_words; i += RSK_TILE_THREADS) s_mask[i] = a.surf_mask[(int64_t)job * a.sc.mask_words + i];
+    // shared memory: [occluder mask][receiver mask (dual only)][histogram][traversal stacks]
+    const int mw = a.sc.mask_words;
+    const int n_hist_all = a.n_hist + (MODE == MODE_DUAL ? a.n_hist2 : 0);
+    uint32_t *s_mask = smem;                                   // surfaces that stop / receive rays
+    uint32_t *s_recv = MODE == MODE_DUAL ? smem + mw : smem;   // surfaces the matrix may tally
+    uint32_t *s_hist = smem + (MODE == MODE_DUAL ? 2 * mw : mw);
+    const int hist_words = a.hist_in_smem ? n_hist_all : 0;
+    uint2 *s_stack = reinterpret_cast<uint2 *>(smem + (((MODE == MODE_DUAL ? 2 * mw : mw) + hist_words + 1) & ~1));
+    {
+        // dual jobs whose sky side is finished walk with the receiver mask only (ineligible meshes are invisible)
+        const uint32_t *occ = (MODE == MODE_DUAL && want_s) ? a.surf_mask2 : a.surf_mask;
+        for (int i = tid; i < mw; i += RSK_TILE_THREADS) {
+            s_mask[i] = occ[(int64_t)job * mw + i];
+            if (MODE == MODE_DUAL) s_recv[i] = a.surf_mask[(int64_t)job * mw + i];
+        }
+    }
     for (int i = tid; i < hist_words; i += RSK_TILE_THREADS) s_hist[i] = 0;
     __syncthreads();
 
-    const int job_min_sid = a.min_sid ? a.min_sid[job] : 0;
+    const int job_min_sid = (a.min_sid && !(MODE == MODE_DUAL && want_s)) ? a.min_sid[job] : 0;
     unsigned long long *g_tally = a.tally ? a.tally + (int64_t)job * a.n_hist : nullptr;
+    unsigned long long *g_tally2 = (MODE == MODE_DUAL && a.tally2) ? a.tally2 + (int64_t)job * a.n_hist2 : nullptr;
+    const int sky_base = MODE == MODE_DUAL ? a.n_hist : 0;
+    const int n_sky = MODE == MODE_DUAL ? a.n_hist2 : a.n_hist;
 
-    // Each warp owns 512 consecutive *positions* of the tile.  Position p maps to ray begin + c + STRIDE*m with
-    // (c, m) enumerating the residue classes mod STRIDE = 77 = 7*11 one after the other: rays of one class share the
-    // leading base-7 and base-11 Halton digits, i.e. the same elevation band and azimuth sector (ray_builder.py:75-80
-    // draws r1, r2 from bases 7 and 11), so the 32 rays a warp holds at a time point the same way from neighbouring
-    // cells -- coherent node visits instead of 32 unrelated directions.  Tallies do not depend on the order.
+    // each warp owns 512 consecutive rays of the tile and hands them to its lanes on demand
     constexpr int WARP_RAYS = RSK_TILE_RAYS / (RSK_TILE_THREADS / 32);
     const int tile_n = (int)(end - begin);
     int next = warp * WARP_RAYS;
     const int wend = min(next + WARP_RAYS, tile_n);
-#if RSK_RAY_PERMUTE
-    constexpr int STRIDE = 77;
-    const int cls_q = tile_n / STRIDE, cls_r = tile_n % STRIDE, cls_split = cls_r * (cls_q + 1);
-#endif
 
     Walk w;
     bool active = false;
+    bool any_hit = false;     // the current ray has met an occluder (sky / dual modes); lives as long as the ray
     int key = -1;             // finished-ray result waiting to be tallied
     int64_t my_k = 0;
     uint2 spill[BVH ? RSK_LOCAL_STACK : 1];
@@ -124,7 +140,8 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
             const unsigned peers = __match_any_sync(has, key);
             if ((__ffs(peers) - 1) == lane) {
                 if (a.hist_in_smem) atomicAdd(&s_hist[key], (uint32_t)__popc(peers));
-                else if (g_tally) atomicAdd(&g_tally[key], (unsigned long long)__popc(peers));
+                else if (key < a.n_hist || MODE != MODE_DUAL) { if (g_tally) atomicAdd(&g_tally[key], (unsigned long long)__popc(peers)); }
+                else if (g_tally2) atomicAdd(&g_tally2[key - a.n_hist], (unsigned long long)__popc(peers));
             }
             key = -1;
         }
@@ -133,19 +150,11 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
         if (need) {
             const int pos = next + __popc(need & ((1u << lane) - 1u));
             if (!active && pos < wend) {
-                int local = pos;
-#if RSK_RAY_PERMUTE
-                if (cls_q > 0) {
-                    const bool big = pos < cls_split;
-                    const int p2 = big ? pos : pos - cls_split, len = big ? cls_q + 1 : cls_q;
-                    local = (big ? 0 : cls_r) + p2 / len + STRIDE * (p2 % len);
-                }
-#endif
-                const int64_t idx = begin + local;
-                my_k = idx;
-                const Ray r = rsk_make_ray(a.ev, e, idx, cp);
+                my_k = begin + pos;
+                const Ray r = rsk_make_ray(a.ev, e, my_k, cp);
                 rsk_walk_begin(w, r);
                 active = true;
+                any_hit = false;
             }
             next += __popc(need);
         }
@@ -157,83 +166,72 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
             // (A "while-while" form that postpones triangles until the warp reconverges measured 30 % slower on
             // B200 -- profiles/kernel_variants_r1.md -- because lanes idle through other lanes' node steps.)
             while (active) {
-                bool finished = false, any_hit = false;
-                uint32_t node = 0;
-                // next node worth testing: children whose whole sub-tree is ignorable for this emitter are dropped
-                // here for the price of one 8-byte load instead of a full 8-box test and a descent
-                for (;;) {
-                    if (w.ng.y <= 0x00ffffffu) {
-                        if (w.sp == 0) { finished = true; break; }
+                bool finished = false;
+                if (w.ng.y <= 0x00ffffffu) {
+                    if (w.sp == 0) finished = true;
+                    else {
                         --w.sp;
                         w.ng = w.sp < RSK_SMEM_STACK ? s_stack[w.sp * RSK_TILE_THREADS + tid] : spill[w.sp - RSK_SMEM_STACK];
                     }
+                }
+                if (!finished) {
                     const int bit = 31 - __clz(w.ng.y);
                     w.ng.y &= ~(1u << bit);
                     const uint32_t slot = (uint32_t)(bit - 24) ^ w.octinv;
-                    node = w.ng.x + __popc(w.ng.y & 0xffu & ((1u << slot) - 1u));
-#if RSK_SUBTREE_SKIP == 1
-                    if (rsk_node_ignorable(a.sc.nodes, node, s_mask, job_min_sid)) continue;
-#endif
-                    break;
-                }
-                if (!finished) {
+                    const uint32_t node = w.ng.x + __popc(w.ng.y & 0xffu & ((1u << slot) - 1u));
                     if (w.ng.y > 0x00ffffffu) {
-                        if (w.sp < RSK_SMEM_STACK) {
-                            s_stack[w.sp * RSK_TILE_THREADS + tid] = w.ng;
-                        } else if (w.sp < RSK_MAX_DEPTH) {
-                            spill[w.sp - RSK_SMEM_STACK] = w.ng;
-                        }
+                        if (w.sp < RSK_SMEM_STACK) s_stack[w.sp * RSK_TILE_THREADS + tid] = w.ng;
+                        else if (w.sp < RSK_MAX_DEPTH) spill[w.sp - RSK_SMEM_STACK] = w.ng;
                         if (w.sp < RSK_MAX_DEPTH) ++w.sp;
                     }
                     uint2 ng2, tg;
-                    rsk_test_node(a.sc.nodes, node, w, MODE == MODE_MATRIX ? w.best : RSK_INF, ng2, tg, s_mask, job_min_sid);
+                    rsk_test_node(a.sc.nodes, node, w, want_m ? w.best : RSK_INF, ng2, tg, s_mask, job_min_sid);
                     while (tg.y) {
                         const int b = __ffs(tg.y) - 1;
                         tg.y &= tg.y - 1u;
                         const int tri = (int)(tg.x + b);
                         const float4 *tp = a.sc.tri + 3 * (int64_t)tri;
                         const float4 V0 = __ldg(tp), E1 = __ldg(tp + 1), E2 = __ldg(tp + 2);
-                        if (!rsk_surface_on(s_mask, __float_as_int(V0.w))) continue;
+                        const int sid = __float_as_int(V0.w);
+                        if (!rsk_surface_on(s_mask, sid)) continue;
                         float t;
-                        if (!rsk_tri_hit(V0, E1, E2, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, t)) continue;
-                        if (MODE == MODE_MATRIX) {
-                            if (t > 1e-6f && t < w.best) { w.best = t; w.best_tri = tri; }
-                        } else if (t > 1e-6f) {
+                        if (!rsk_tri_hit(V0, E1, E2, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, t) || !(t > 1e-6f)) continue;
+                        if (want_s) {
                             any_hit = true;
-                            break;
+                            if (!want_m) break;                       // sky only: the first hit settles the ray
                         }
+                        if (want_m && t < w.best && (MODE != MODE_DUAL || rsk_surface_on(s_recv, sid))) { w.best = t; w.best_tri = tri; }
                     }
                     w.ng = ng2;
-                    if (any_hit) finished = true;
+                    if (any_hit && !want_m) finished = true;
                 }
                 if (finished) {
-                    key = rsk_result_key<MODE>(a, w, any_hit);
-                    if (a.dbg_hit || a.dbg_orig || a.dbg_dirs || a.dbg_front) rsk_debug_store<MODE>(a, my_k, w, key, any_hit);
+                    key = rsk_result_key(a, w, want_m, want_s, any_hit, sky_base, n_sky);
+                    if (MODE != MODE_DUAL && (a.dbg_hit || a.dbg_orig || a.dbg_dirs || a.dbg_front)) rsk_debug_store<MODE>(a, my_k, w, key, any_hit);
                     active = false;
                     break;
                 }
                 if (rays_left && __popc(__activemask()) < REFILL_BELOW) break;
             }
         } else {
-            // ---- no BVH: every triangle in input order, strict t<best (utils/cpu_trace.py:54-117, 540-583)
+            // ---- no BVH: every triangle in input order, strict t<best (utils/cpu_trace.py:54-117, 280-352, 540-583)
             if (active) {
-                bool any_hit = false;
                 for (int tri = 0; tri < a.sc.n_tri; ++tri) {
                     const float4 *tp = a.sc.tri + 3 * (int64_t)tri;
                     const float4 V0 = __ldg(tp);
-                    if (!rsk_surface_on(s_mask, __float_as_int(V0.w))) continue;
+                    const int sid = __float_as_int(V0.w);
+                    if (!rsk_surface_on(s_mask, sid)) continue;
                     const float4 E1 = __ldg(tp + 1), E2 = __ldg(tp + 2);
                     float t;
-                    if (!rsk_tri_hit(V0, E1, E2, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, t)) continue;
-                    if (MODE == MODE_MATRIX) {
-                        if (t > 1e-6f && t < w.best) { w.best = t; w.best_tri = tri; }
-                    } else if (t > 1e-6f) {
+                    if (!rsk_tri_hit(V0, E1, E2, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, t) || !(t > 1e-6f)) continue;
+                    if (want_s) {
                         any_hit = true;
-                        break;
+                        if (!want_m) break;
                     }
+                    if (want_m && t < w.best && (MODE != MODE_DUAL || rsk_surface_on(s_recv, sid))) { w.best = t; w.best_tri = tri; }
                 }
-                key = rsk_result_key<MODE>(a, w, any_hit);
-                if (a.dbg_hit || a.dbg_orig || a.dbg_dirs || a.dbg_front) rsk_debug_store<MODE>(a, my_k, w, key, any_hit);
+                key = rsk_result_key(a, w, want_m, want_s, any_hit, sky_base, n_sky);
+                if (MODE != MODE_DUAL && (a.dbg_hit || a.dbg_orig || a.dbg_dirs || a.dbg_front)) rsk_debug_store<MODE>(a, my_k, w, key, any_hit);
                 active = false;
             }
         }
@@ -241,25 +239,28 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
     }
 
     // ---- flush the CTA histogram: one global atomic per touched bin
-    if (a.hist_in_smem && g_tally) {
+    if (a.hist_in_smem) {
         __syncthreads();
-        for (int i = tid; i < a.n_hist; i += RSK_TILE_THREADS) {
+        for (int i = tid; i < n_hist_all; i += RSK_TILE_THREADS) {
             const uint32_t v = s_hist[i];
-            if (v) atomicAdd(&g_tally[i], (unsigned long long)v);
+            if (!v) continue;
+            if (i < a.n_hist) { if (g_tally) atomicAdd(&g_tally[i], (unsigned long long)v); }
+            else if (g_tally2) atomicAdd(&g_tally2[i - a.n_hist], (unsigned long long)v);
         }
     }
 }
 
 // ----------------------------------------------------------------------------- host launcher
 
-static size_t rsk_trace_smem(const TraceArgs &a, bool bvh) {
-    size_t words = ((size_t)a.sc.mask_words + (a.hist_in_smem ? a.n_hist : 0) + 1) & ~(size_t)1;
+static size_t rsk_trace_smem(const TraceArgs &a, bool bvh, bool dual) {
+    const size_t hist = (size_t)a.n_hist + (dual ? a.n_hist2 : 0);
+    size_t words = ((size_t)a.sc.mask_words * (dual ? 2 : 1) + (a.hist_in_smem ? hist : 0) + 1) & ~(size_t)1;
     return words * 4 + (bvh ? (size_t)RSK_SMEM_STACK * RSK_TILE_THREADS * sizeof(uint2) : 0);
 }
 
 template <int MODE, bool BVH>
 static int rsk_launch_one(rsk_ctx *ctx, const TraceArgs &a, int64_t n_tiles) {
-    const size_t smem = rsk_trace_smem(a, BVH);
+    const size_t smem = rsk_trace_smem(a, BVH, MODE == MODE_DUAL);
     if (smem > 48 * 1024)
         RSK_CUDA(cudaFuncSetAttribute(rsk_trace_kernel<MODE, BVH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rsk_trace_kernel<MODE, BVH><<<(unsigned)n_tiles, RSK_TILE_THREADS, smem, ctx->stream>>>(a);
@@ -272,8 +273,9 @@ int rsk_launch_trace(rsk_ctx *ctx, TraceArgs &a, int mode, int64_t n_tiles) {
     if (n_tiles <= 0) return RSK_OK;
     RSK_REQUIRE(n_tiles < ((int64_t)1 << 31), "too many ray tiles in one launch");
     // shared-memory histogram when it leaves room for >= 2 CTAs per SM, else warp-aggregated global atomics
-    a.hist_in_smem = ((size_t)a.n_hist * 4 <= 96 * 1024) ? 1 : 0;
+    a.hist_in_smem = (((size_t)a.n_hist + (mode == MODE_DUAL ? a.n_hist2 : 0)) * 4 <= 96 * 1024) ? 1 : 0;
     const bool bvh = a.sc.use_bvh != 0;
+    if (mode == MODE_DUAL) return bvh ? rsk_launch_one<MODE_DUAL, true>(ctx, a, n_tiles) : rsk_launch_one<MODE_DUAL, false>(ctx, a, n_tiles);
     if (mode == MODE_MATRIX) return bvh ? rsk_launch_one<MODE_MATRIX, true>(ctx, a, n_tiles) : rsk_launch_one<MODE_MATRIX, false>(ctx, a, n_tiles);
     return bvh ? rsk_launch_one<MODE_SKY, true>(ctx, a, n_tiles) : rsk_launch_one<MODE_SKY, false>(ctx, a, n_tiles);
 }

@@ -75,7 +75,7 @@ __device__ __forceinline__ void rsk_walk_begin(Walk &w, const Ray &r) {
 #endif
 
 #ifndef RSK_SUBTREE_SKIP
-#define RSK_SUBTREE_SKIP 2
+#define RSK_SUBTREE_SKIP 2      // 0 = off, 2 = range word loaded together with the node (shipped)
 #endif
 // True when no triangle below node `idx` can matter to this ray: every mesh id there is below the job's `min_sid`
 // (reciprocity: receivers j <= i are ignored, main.py:1181-1182), or the sub-tree belongs to a single mesh that is

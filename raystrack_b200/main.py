@@ -323,11 +323,14 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
 
     weights = [float(em.n_cells * rays) for em in emitters]
     n_once = [int(em.n_cells * rays) for em in emitters]
-    with _Phase("rotations"):
-        table = _rotation_table(seed, n_surf, max_iters)
-    tallies, iters, totals = _solve_sharded(ctx, d_scene, d_em, todo, n_once, active, table, max_iters=max_iters,
-                                            min_iters=min_iters, interval=interval if schedule == "gpu" else 1,
-                                            tol_mode=tol_mode, tol=tol, emit_sid=emit_sid, min_sid=min_sid)
+    if _hook is not None and "precomputed" in _hook:
+        tallies, iters, totals = _hook["precomputed"]            # shared-ray solve already ran (view_factor_matrix_and_sky)
+    else:
+        with _Phase("rotations"):
+            table = _rotation_table(seed, n_surf, max_iters)
+        tallies, iters, totals = _solve_sharded(ctx, d_scene, d_em, todo, n_once, active, table, max_iters=max_iters,
+                                                min_iters=min_iters, interval=interval if schedule == "gpu" else 1,
+                                                tol_mode=tol_mode, tol=tol, emit_sid=emit_sid, min_sid=min_sid)
     elapsed = time.time() - t0
     t_asm = time.perf_counter()
 
@@ -410,10 +413,13 @@ def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepar
     active = _surface_masks(emitters, centers, extents)
     weights = [float(em.n_cells * rays) for em in emitters]
     n_once = [int(em.n_cells * rays) for em in emitters]
-    table = _rotation_table(seed, n_surf, max_iters)
-    counts, iters, totals = _solve_sharded(ctx, d_scene, d_em, list(range(n_surf)), n_once, active, table, max_iters=max_iters,
-                                           min_iters=min_iters, interval=interval if schedule == "gpu" else 1,
-                                           tol_mode=tol_mode, tol=tol, sky=True, discrete=discrete)
+    if _hook is not None and "precomputed" in _hook:
+        counts, iters, totals = _hook["precomputed"]
+    else:
+        table = _rotation_table(seed, n_surf, max_iters)
+        counts, iters, totals = _solve_sharded(ctx, d_scene, d_em, list(range(n_surf)), n_once, active, table, max_iters=max_iters,
+                                               min_iters=min_iters, interval=interval if schedule == "gpu" else 1,
+                                               tol_mode=tol_mode, tol=tol, sky=True, discrete=discrete)
     elapsed = time.time() - t0
 
     label = "builtin" if use_bvh else "off"
@@ -443,13 +449,53 @@ def outside_workflow_shareable(matrix_params: MatrixParams, sky_params: SkyParam
     return all(getattr(matrix_params, k) == getattr(sky_params, k) for k in fields)
 
 
+def _shared_ray_solve(meshes, matrix_params: MatrixParams, sky_params: SkyParams, solver: PreparedSolver):
+    """One dual device solve (csrc: MODE_DUAL): every ray is traced once, the closest receiver hit feeds the matrix
+    tallies and the any-hit flag the sky bins (reference trace_cpu_[bvh_]combined, cpu_trace.py:280-522)."""
+    mp, sp = matrix_params.as_dict(), sky_params.as_dict()
+    schedule = _resolve_device(mp["device"])
+    use_bvh = _select_bvh(mp["bvh"], solver.total_faces)
+    n_surf = len(meshes)
+    emitters = solver.get_emitters(samples=mp["samples"], rays=mp["rays"], flip_faces=False)
+    centers, extents = solver.get_mesh_bounds()
+    ctx = _context()
+    d_scene = solver.get_device_scene(use_bvh=use_bvh, ctx=ctx)
+    d_em = solver.get_device_emitters(samples=mp["samples"], rays=mp["rays"], flip_faces=False, ctx=ctx)
+    active = _surface_masks(emitters, centers, extents)
+    ids = np.arange(n_surf, dtype=np.int32)
+    min_sid = (ids + 1) if mp["reciprocity"] else np.zeros(n_surf, np.int32)
+    table = _rotation_table(mp["seed"], n_surf, max(int(mp["max_iters"]), int(sp["max_iters"])))
+
+    def side(p):
+        return dict(max_iters=p["max_iters"], min_iters=p["min_iters"], tol=p["tol"], tol_mode=p["tol_mode"],
+                    interval=max(1, int(p["convergence_interval"])) if schedule == "gpu" else 1)
+
+    solve = _native.DualSolve(ctx, d_scene.native, d_em.native, ids, active, table, ids.copy(), ids, min_sid,
+                              side(mp), side(sp), bool(sp["discrete"]))
+    try:
+        limit = max(int(mp["max_iters"]), int(sp["max_iters"]))
+        first = max(1, min(limit, max(1, min(int(mp["min_iters"]), int(sp["min_iters"])))))
+        running = solve.step(first) if limit > 0 else 0
+        done = first
+        while running > 0 and done < limit:
+            chunk = min(4, limit - done)
+            running = solve.step(chunk)
+            done += chunk
+        m_t, m_i, m_r = solve.matrix_part.read_block()
+        s_t, s_i, s_r = solve.sky_part.read_block()
+    finally:
+        solve.close()
+    return (m_t, m_i.astype(np.int64), m_r), (s_t, s_i.astype(np.int64), s_r)
+
+
 def view_factor_matrix_and_sky(meshes: List[Mesh], *, matrix_params: MatrixParams, sky_params: SkyParams,
                                prepared: Optional[PreparedSolver] = None):
     """Scene view factors and sky view factors from the same per-iteration ray samples (reference
     main.py:1209-1686).  Both sides converge independently and use, per emitter and iteration, exactly the rays the
     separate solves would use, so the results equal ``view_factor_matrix`` + ``view_factor_to_tregenza_sky``
-    (the reference documents the same equivalence, main.py:1231-1234); the device runs the closest-hit and the
-    any-hit kernel of an iteration back to back on one stream, sharing scene, BVH, emitter tables and uploads.
+    (the reference documents the same equivalence, main.py:1231-1234).  On one GPU every ray is traced ONCE by the
+    dual kernel (closest receiver hit + any-hit flag); under torch.distributed the two sharded solves run one after
+    the other on the shared scene, BVH and emitter tables.
     ``enforce_reciprocity_rowsum`` is not applied here (main.py never does in this function)."""
     if not isinstance(matrix_params, MatrixParams):
         raise TypeError("matrix_params must be a MatrixParams instance")
@@ -460,6 +506,8 @@ def view_factor_matrix_and_sky(meshes: List[Mesh], *, matrix_params: MatrixParam
     solver = _ensure_prepared(meshes, prepared)
     mh: dict = {}
     sh: dict = {}
+    if _dist_env()[1] == 1 and len(meshes) > 0:
+        mh["precomputed"], sh["precomputed"] = _shared_ray_solve(meshes, matrix_params, sky_params, solver)
     vf_scene = view_factor_matrix(meshes, matrix_params, prepared=solver, _hook=mh)
     sky_vf = view_factor_to_tregenza_sky(meshes, sky_params, prepared=solver, _hook=sh)
     n = len(meshes)

@@ -348,3 +348,33 @@ def test_matrix_and_sky_single_mesh(rb, workflow_golden):
     assert vf == {"east_side_0": {}}
     assert abs(sky["east_side_0"]["Sky"] - g["sky_vf"]["east_side_0"]["Sky"]) <= 2e-5
     assert "traced" in logs[0] and "scene=0 iter" in logs[0]
+
+
+@pytest.mark.parametrize("scene,bvh,recip,discrete", [("canyon", "off", True, False), ("canyon", "builtin", False, True),
+                                                       ("urban", "builtin", True, True), ("urban", "builtin", False, False)])
+def test_shared_ray_solve_equals_separate_solves(rb, scene, bvh, recip, discrete):
+    """The dual kernel (one traversal -> closest receiver hit + any-hit flag, reference trace_cpu_[bvh_]combined)
+    must give exactly the tallies and iteration counts of the separate matrix and sky solves (main.py:1231-1234)."""
+    import raystrack_b200.main as M
+    from raystrack_b200 import synthetic
+    meshes = synthetic.street_canyon() if scene == "canyon" else synthetic.urban_block(3, 4, 8, 0)
+    mp = rb.MatrixParams(samples=4, rays=32, seed=6, bvh=bvh, max_iters=25, min_iters=4, tol=2e-3, reciprocity=recip)
+    sp = rb.SkyParams(samples=4, rays=32, seed=6, bvh=bvh, max_iters=14, min_iters=7, tol=1e-3, discrete=discrete, tol_mode="delta")
+    logs_shared, logs_m, logs_s = [], [], []
+    old = M._log
+    try:
+        M._log = logs_shared.append
+        vf, sky = M.view_factor_matrix_and_sky(meshes, matrix_params=mp, sky_params=sp)
+        M._log = logs_m.append
+        vf2 = rb.view_factor_matrix(meshes, mp)
+        M._log = logs_s.append
+        sky2 = rb.view_factor_to_tregenza_sky(meshes, sp)
+    finally:
+        M._log = old
+    assert vf == vf2
+    assert sky == sky2
+    import re
+    for line, lm, ls in zip(logs_shared, logs_m, logs_s):
+        m = re.search(r"scene=(\d+) iter, sky=(\d+) iter", line)
+        assert int(m.group(1)) == int(re.search(r"\] (\d+) iter", lm).group(1))
+        assert int(m.group(2)) == int(re.search(r"\] (\d+) iter", ls).group(1))
