@@ -14,7 +14,6 @@ VARIANTS = {      # compile-time knobs of csrc/rsk_trace.cu(h) and csrc/rsk_bvh.
     "shipped": (),
     "no_subtree_skip": ("RSK_SUBTREE_SKIP=0",),
     "byte_prmt_mantissa": ("RSK_BYTE_MODE=3",),
-    "ray_permute": ("RSK_RAY_PERMUTE=1",),
     "morton_per_axis": ("RSK_MORTON_UNIFORM=0",),
     "ploc_r16": ("RSK_PLOC=1", "RSK_PLOC_RADIUS=16"),
     "bottom16": ("RSK_BOTTOM_MAX=16",),
