@@ -14,8 +14,11 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef RSK_MIN_CTAS_PER_SM
 #define RSK_MIN_CTAS_PER_SM 4
 #endif
+#ifndef RSK_RAY_BUFFER
+#define RSK_RAY_BUFFER 1
+#endif
 #ifndef RSK_REFILL_BELOW
-#define RSK_REFILL_BELOW 20
+#define RSK_REFILL_BELOW 24     // with the warp-wide ray buffer a refill is cheap: 24-27 measured best, 20 without it
 #endif
 constexpr int RSK_MIN_CTAS = RSK_MIN_CTAS_PER_SM;   // 4 CTAs x 256 threads per SM -> at most 64 registers per thread
 constexpr int REFILL_BELOW = RSK_REFILL_BELOW;     // leave the traversal loop to fetch new rays when fewer lanes are busy
@@ -126,6 +129,11 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
     int next = warp * WARP_RAYS;
     const int wend = min(next + WARP_RAYS, tile_n);
 
+#if RSK_RAY_BUFFER
+    constexpr int RAY_SLOTS = 64;        // a top-up adds <= 32 rays to < 32 leftovers
+    float *s_rays = reinterpret_cast<float *>(s_stack + (BVH ? RSK_SMEM_STACK * RSK_TILE_THREADS : 0)) + warp * (7 * RAY_SLOTS);
+    int buf_n = 0;
+#endif
     Walk w;
     bool active = false;
     bool any_hit = false;     // the current ray has met an occluder (sky / dual modes); lives as long as the ray
@@ -147,6 +155,41 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
         }
         // ---- refill idle lanes with fresh rays
         const unsigned need = __ballot_sync(FULL, !active);
+#if RSK_RAY_BUFFER
+        // Rays are generated 32 at a time by the whole warp (the float64 sampler then runs with every lane busy and
+        // the Halton rows are read coalesced) into a small per-warp buffer; idle lanes take their next ray from it.
+        if (need) {
+            const int n_need = __popc(need);
+            if (buf_n < n_need && next < wend) {
+                const int pos = next + lane;
+                if (pos < wend) {
+                    const Ray r = rsk_make_ray(a.ev, e, begin + pos, cp);
+                    float *slot = s_rays + buf_n + lane;
+                    slot[0 * RAY_SLOTS] = r.ox; slot[1 * RAY_SLOTS] = r.oy; slot[2 * RAY_SLOTS] = r.oz;
+                    slot[3 * RAY_SLOTS] = r.dx; slot[4 * RAY_SLOTS] = r.dy; slot[5 * RAY_SLOTS] = r.dz;
+                    slot[6 * RAY_SLOTS] = __int_as_float(pos);
+                }
+                const int made = min(32, wend - next);
+                next += made;
+                buf_n += made;
+                __syncwarp();
+            }
+            const int rank = __popc(need & ((1u << lane) - 1u));
+            if (!active && rank < buf_n) {
+                const float *slot = s_rays + (buf_n - 1 - rank);
+                Ray r;
+                r.ox = slot[0 * RAY_SLOTS]; r.oy = slot[1 * RAY_SLOTS]; r.oz = slot[2 * RAY_SLOTS];
+                r.dx = slot[3 * RAY_SLOTS]; r.dy = slot[4 * RAY_SLOTS]; r.dz = slot[5 * RAY_SLOTS];
+                my_k = begin + __float_as_int(slot[6 * RAY_SLOTS]);
+                rsk_walk_begin(w, r);
+                active = true;
+                any_hit = false;
+            }
+            buf_n -= min(n_need, buf_n);
+        }
+        if (!__any_sync(FULL, active)) break;
+        const bool rays_left = buf_n > 0 || next < wend;
+#else
         if (need) {
             const int pos = next + __popc(need & ((1u << lane) - 1u));
             if (!active && pos < wend) {
@@ -160,6 +203,7 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
         }
         if (!__any_sync(FULL, active)) break;
         const bool rays_left = next < wend;
+#endif
 
         if (BVH) {
             // ---- 8-wide BVH walk, one node step per loop trip; the triangles a step uncovers are tested at once.
@@ -255,7 +299,8 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
 static size_t rsk_trace_smem(const TraceArgs &a, bool bvh, bool dual) {
     const size_t hist = (size_t)a.n_hist + (dual ? a.n_hist2 : 0);
     size_t words = ((size_t)a.sc.mask_words * (dual ? 2 : 1) + (a.hist_in_smem ? hist : 0) + 1) & ~(size_t)1;
-    return words * 4 + (bvh ? (size_t)RSK_SMEM_STACK * RSK_TILE_THREADS * sizeof(uint2) : 0);
+    return words * 4 + (bvh ? (size_t)RSK_SMEM_STACK * RSK_TILE_THREADS * sizeof(uint2) : 0)
+           + (RSK_RAY_BUFFER ? (size_t)(RSK_TILE_THREADS / 32) * 7 * 64 * sizeof(float) : 0);
 }
 
 template <int MODE, bool BVH>
