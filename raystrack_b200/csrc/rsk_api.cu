@@ -351,7 +351,8 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
     const int nw = (scene->n_surf + 31) / 32;
     std::vector<uint32_t> mask(std::max(nw, 1));
     rsk_pack_mask(surf_active, scene->n_surf, emit_sid, min_sid, mask.data());
-    const int64_t n_tiles = (n_rays + RSK_TILE_RAYS - 1) / RSK_TILE_RAYS;
+    const int tile_rays = rsk_pick_tile_rays(n_rays, ctx->sm_count);
+    const int64_t n_tiles = (n_rays + tile_rays - 1) / tile_rays;
     const int64_t tiles[2] = {0, n_tiles};
     const int32_t zero = 0;
     const int64_t range[2] = {first_ray, first_ray + n_rays};
@@ -380,7 +381,7 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
     memset(&a, 0, sizeof(a));
     a.sc = scene->view();
     a.ev = em->view();
-    a.emit_ids = d_ids; a.tile_start = d_tiles; a.n_local = 1; a.surf_mask = d_mask;
+    a.emit_ids = d_ids; a.tile_start = d_tiles; a.n_local = 1; a.tile_rays = tile_rays; a.surf_mask = d_mask;
     a.cp_table = d_cp; a.rot_base = d_zero; a.iters_done = d_zero; a.done = nullptr; a.tally = nullptr;
     a.n_hist = mode == MODE_MATRIX ? 2 * scene->n_surf : RSK_TREGENZA_BINS;
     a.ray_begin = d_range; a.ray_end = d_range + 1; a.dbg_base = first_ray; a.min_sid = d_msid;
@@ -408,6 +409,7 @@ struct rsk_solve {
     int32_t n_local = 0, n_hist = 0, discrete = 0;
     rsk_solve_params p{};
     int64_t n_tiles = 0;
+    int32_t tile_rays = RSK_TILE_RAYS_MAX;
     // device state
     int32_t *min_sid = nullptr;
     int32_t *emit_ids = nullptr, *rot_base = nullptr, *iters_done = nullptr, *done = nullptr, *not_conv = nullptr, *have_prev = nullptr;
@@ -455,7 +457,12 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
         rbeg[k] = ray_range ? ray_range[2 * k] : 0;
         rend[k] = ray_range ? ray_range[2 * k + 1] : once[k];
         if (rbeg[k] < 0 || rend[k] < rbeg[k] || rend[k] > once[k]) { rsk_set_error("solve begin: ray range out of bounds"); rc = RSK_ERR_INVALID; break; }
-        tiles[k + 1] = tiles[k] + (rend[k] - rbeg[k] + RSK_TILE_RAYS - 1) / RSK_TILE_RAYS;
+    }
+    if (rc == RSK_OK) {
+        int64_t total = 0;
+        for (int k = 0; k < n_local; ++k) total += rend[k] - rbeg[k];
+        s->tile_rays = rsk_pick_tile_rays(total, ctx->sm_count);
+        for (int k = 0; k < n_local; ++k) tiles[k + 1] = tiles[k] + (rend[k] - rbeg[k] + s->tile_rays - 1) / s->tile_rays;
     }
     s->n_tiles = tiles[n_local];
     const size_t nh = (size_t)n_local * s->n_hist;
@@ -513,7 +520,7 @@ static int rsk_solve_enqueue_trace_impl(rsk_solve *s) {
     memset(&a, 0, sizeof(a));
     a.sc = s->scene->view();
     a.ev = s->em->view();
-    a.emit_ids = s->emit_ids; a.tile_start = s->tile_start; a.n_local = s->n_local; a.surf_mask = s->mask;
+    a.emit_ids = s->emit_ids; a.tile_start = s->tile_start; a.n_local = s->n_local; a.tile_rays = s->tile_rays; a.surf_mask = s->mask;
     a.cp_table = s->cp_table; a.rot_base = s->rot_base; a.iters_done = s->iters_done; a.done = s->done;
     a.tally = s->iter_tally; a.n_hist = s->n_hist; a.ray_begin = s->ray_begin; a.ray_end = s->ray_end; a.min_sid = s->min_sid;
     if (s->twin) {

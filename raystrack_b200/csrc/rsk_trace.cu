@@ -17,6 +17,9 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef RSK_RAY_BUFFER
 #define RSK_RAY_BUFFER 1
 #endif
+#ifndef RSK_CTA_POOL
+#define RSK_CTA_POOL 1        // needs RSK_RAY_BUFFER
+#endif
 #ifndef RSK_REFILL_BELOW
 #define RSK_REFILL_BELOW 24     // with the warp-wide ray buffer a refill is cheap: 24-27 measured best, 20 without it
 #endif
@@ -64,6 +67,7 @@ template <int MODE, bool BVH>
 __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kernel(const TraceArgs a) {
     extern __shared__ uint32_t smem[];
     __shared__ int s_job;
+    __shared__ int s_next;      // next unclaimed ray of the tile (RSK_CTA_POOL)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {           // job lookup: last k with tile_start[k] <= blockIdx.x
@@ -74,6 +78,7 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
             if (a.tile_start[mid] <= b) lo = mid; else hi = mid - 1;
         }
         s_job = lo;
+        s_next = 0;
     }
     __syncthreads();
     const int job = s_job;
@@ -86,8 +91,8 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
     const int64_t tile = (int64_t)blockIdx.x - a.tile_start[job];
     const int64_t range_begin = a.ray_begin ? a.ray_begin[job] : 0;
     const int64_t range_end = a.ray_end ? a.ray_end[job] : e.n_rays_once;
-    const int64_t begin = range_begin + tile * RSK_TILE_RAYS;
-    const int64_t end = min(begin + (int64_t)RSK_TILE_RAYS, range_end);
+    const int64_t begin = range_begin + tile * a.tile_rays;
+    const int64_t end = min(begin + (int64_t)a.tile_rays, range_end);
 
     float cp[7];
     {
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
     const int n_sky = MODE == MODE_DUAL ? a.n_hist2 : a.n_hist;
 
     // each warp owns 512 consecutive rays of the tile and hands them to its lanes on demand
-    constexpr int WARP_RAYS = RSK_TILE_RAYS / (RSK_TILE_THREADS / 32);
+    const int WARP_RAYS = a.tile_rays / (RSK_TILE_THREADS / 32);
     const int tile_n = (int)(end - begin);
     int next = warp * WARP_RAYS;
     const int wend = min(next + WARP_RAYS, tile_n);
@@ -133,6 +138,9 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
     constexpr int RAY_SLOTS = 64;        // a top-up adds <= 32 rays to < 32 leftovers
     float *s_rays = reinterpret_cast<float *>(s_stack + (BVH ? RSK_SMEM_STACK * RSK_TILE_THREADS : 0)) + warp * (7 * RAY_SLOTS);
     int buf_n = 0;
+#if RSK_CTA_POOL
+    bool pool_empty = tile_n <= 0;
+#endif
 #endif
     Walk w;
     bool active = false;
@@ -160,17 +168,35 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
         // the Halton rows are read coalesced) into a small per-warp buffer; idle lanes take their next ray from it.
         if (need) {
             const int n_need = __popc(need);
+#if RSK_CTA_POOL
+            if (buf_n < n_need && !pool_empty) {
+                // the 4096 rays of the tile are one pool: a warp that runs out takes the next 32, whichever warp it is
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_next, 32);
+                base = __shfl_sync(FULL, base, 0);
+                const int made = max(0, min(32, tile_n - base));
+                if (lane < made) {
+                    const int pos = base + lane;
+#else
             if (buf_n < n_need && next < wend) {
-                const int pos = next + lane;
-                if (pos < wend) {
+                const int made = min(32, wend - next);
+                {
+                    const int pos = next + lane;
+                    if (pos < wend) {
+#endif
                     const Ray r = rsk_make_ray(a.ev, e, begin + pos, cp);
                     float *slot = s_rays + buf_n + lane;
                     slot[0 * RAY_SLOTS] = r.ox; slot[1 * RAY_SLOTS] = r.oy; slot[2 * RAY_SLOTS] = r.oz;
                     slot[3 * RAY_SLOTS] = r.dx; slot[4 * RAY_SLOTS] = r.dy; slot[5 * RAY_SLOTS] = r.dz;
                     slot[6 * RAY_SLOTS] = __int_as_float(pos);
+#if RSK_CTA_POOL
                 }
-                const int made = min(32, wend - next);
+                pool_empty = base + 32 >= tile_n;
+#else
+                    }
+                }
                 next += made;
+#endif
                 buf_n += made;
                 __syncwarp();
             }
@@ -188,7 +214,11 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
             buf_n -= min(n_need, buf_n);
         }
         if (!__any_sync(FULL, active)) break;
+#if RSK_CTA_POOL
+        const bool rays_left = buf_n > 0 || !pool_empty;
+#else
         const bool rays_left = buf_n > 0 || next < wend;
+#endif
 #else
         if (need) {
             const int pos = next + __popc(need & ((1u << lane) - 1u));

@@ -12,6 +12,7 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 VARIANTS = {      # compile-time knobs of csrc/rsk_trace.cu(h) and csrc/rsk_bvh.cu; the product is built with the defaults
     "shipped": (),
+    "warp_slices": ("RSK_CTA_POOL=0",),
     "per_lane_raygen": ("RSK_RAY_BUFFER=0", "RSK_REFILL_BELOW=20"),
     "no_subtree_skip": ("RSK_SUBTREE_SKIP=0",),
     "byte_prmt_mantissa": ("RSK_BYTE_MODE=3",),
