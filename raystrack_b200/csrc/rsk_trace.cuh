@@ -3,8 +3,11 @@
 #include "rsk_common.cuh"
 #include "rsk_raygen.cuh"
 
-constexpr int RSK_SMEM_STACK = 8;      // stack entries per thread kept in shared memory
-constexpr int RSK_LOCAL_STACK = 24;    // spill entries per thread (local memory)
+#ifndef RSK_SMEM_STACK_N
+#define RSK_SMEM_STACK_N 8
+#endif
+constexpr int RSK_SMEM_STACK = RSK_SMEM_STACK_N;        // stack entries per thread kept in shared memory
+constexpr int RSK_LOCAL_STACK = 32 - RSK_SMEM_STACK_N;   // spill entries per thread (local memory)
 constexpr int RSK_MAX_DEPTH = RSK_SMEM_STACK + RSK_LOCAL_STACK;
 static_assert(RSK_MAX_DEPTH == RSK_MAX_DEPTH_HOST, "stack size mismatch");
 
