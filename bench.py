@@ -45,6 +45,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner to stdout) must not add to it:
+# file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a private copy of the real stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -153,7 +164,7 @@ def run_reference(args):
             "config": {"workload": WORKLOAD, "sample": cpu.describe()},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu.describe()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
@@ -365,7 +376,7 @@ def run_ours(args):
     traffic_file = ROOT / "profiles" / "c5_trace_dram_bytes.json"
     if traffic_file.exists():
         line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch")
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
