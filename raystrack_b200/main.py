@@ -110,6 +110,17 @@ def _surface_masks(emitters: Sequence[PreparedEmitter], centers: np.ndarray, ext
     return active
 
 
+def _cached_masks(solver: PreparedSolver, emitters, centers, extents, flip_faces: bool) -> np.ndarray:
+    """Surface masks depend only on the emitter planes and the mesh bounds, so a PreparedSolver keeps them."""
+    key = ("surface_masks", bool(flip_faces))
+    got = solver._derived_cache.get(key)
+    if got is None:
+        got = _surface_masks(emitters, centers, extents)
+        got.setflags(write=False)
+        solver._derived_cache[key] = got
+    return got
+
+
 def _rotation_table(seed: int, n_emit: int, max_iters: int) -> np.ndarray:
     """Cranley-Patterson offsets.  The reference draws ``default_rng(seed + idx_emit + itr)`` per emitter and
     iteration (main.py:1810-1812); only the sum matters, so one row per distinct sum: row s = rotation of
@@ -310,7 +321,7 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
 
     t0 = time.time()
     with _Phase("masks"):
-        active = _surface_masks(emitters, centers, extents)
+        active = _cached_masks(solver, emitters, centers, extents, flip_faces)
     # receivers of emitter i (main.py:161-164, 207-214): active meshes j > i (reciprocity) or j != i
     emit_sid = np.arange(n_surf, dtype=np.int32)
     min_sid = (emit_sid + 1) if reciprocity else np.zeros(n_surf, np.int32)
@@ -340,15 +351,18 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
     keys = [f"{name}{suffix}" for name, _, _ in meshes for suffix in ("_front", "_back")]
     work = np.asarray(weights) * np.maximum(iters, 1)
     work_sum = max(1.0, float(work.sum()))
+    nz_rows, nz_cols = np.nonzero(tallies)                      # row-major: already grouped by emitter, keys in order
+    with np.errstate(divide="ignore", invalid="ignore"):
+        nz_vals = tallies[nz_rows, nz_cols] / totals[nz_rows].astype(np.float64)         # main.py:1922-1923
+    bounds = np.searchsorted(nz_rows, np.arange(n_surf + 1))
+    cols_all, vals_all = nz_cols.tolist(), nz_vals.tolist()
     for i, (name_e, _, _) in enumerate(meshes):
         if not has_recv[i]:
             if _hook is None:
                 _log(f"({i+1}/{n_surf}) [{name_e}] 0 iter, 0 rays -> 0.000s  (BVH={label}, device=gpu)")
             continue
-        cols = np.nonzero(tallies[i])[0]
-        with np.errstate(divide="ignore", invalid="ignore"):
-            vals = tallies[i, cols] / float(totals[i])                                  # main.py:1922-1923
-        cols_l = cols.tolist()
+        lo, hi = int(bounds[i]), int(bounds[i + 1])
+        cols_l, vals = cols_all[lo:hi], vals_all[lo:hi]
         row = dict(zip([keys[c] for c in cols_l], vals))
         if reciprocity and areas is not None:
             for c, f in zip(cols_l, vals):
@@ -410,7 +424,7 @@ def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepar
     d_scene = solver.get_device_scene(use_bvh=use_bvh, ctx=ctx)
     d_em = solver.get_device_emitters(samples=samples, rays=rays, flip_faces=False, ctx=ctx)
     t0 = time.time()
-    active = _surface_masks(emitters, centers, extents)
+    active = _cached_masks(solver, emitters, centers, extents, False)
     weights = [float(em.n_cells * rays) for em in emitters]
     n_once = [int(em.n_cells * rays) for em in emitters]
     if _hook is not None and "precomputed" in _hook:
@@ -461,7 +475,7 @@ def _shared_ray_solve(meshes, matrix_params: MatrixParams, sky_params: SkyParams
     ctx = _context()
     d_scene = solver.get_device_scene(use_bvh=use_bvh, ctx=ctx)
     d_em = solver.get_device_emitters(samples=mp["samples"], rays=mp["rays"], flip_faces=False, ctx=ctx)
-    active = _surface_masks(emitters, centers, extents)
+    active = _cached_masks(solver, emitters, centers, extents, False)
     ids = np.arange(n_surf, dtype=np.int32)
     min_sid = (ids + 1) if mp["reciprocity"] else np.zeros(n_surf, np.int32)
     table = _rotation_table(mp["seed"], n_surf, max(int(mp["max_iters"]), int(sp["max_iters"])))

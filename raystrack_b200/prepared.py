@@ -258,6 +258,7 @@ class PreparedSolver:
         self._device_emitter_cache: Dict[Tuple[int, int, int, bool], PreparedDeviceEmitters] = {}
         self._mesh_bounds_cache: Optional[Tuple[np.ndarray, np.ndarray]] = None
         self._emitter_pack_cache: Dict[Tuple[int, int, bool], tuple] = {}
+        self._derived_cache: Dict[Any, Any] = {}      # host-side results derived from the prepared state (surface masks)
 
     def get_scene(self, *, use_bvh: bool) -> PreparedScene:
         key = bool(use_bvh)
