@@ -1,6 +1,6 @@
 // rsk_trace.cu -- fused ray generation + closest-hit / any-hit traversal + tally kernels.
 //
-// One CTA processes one tile of RSK_TILE_RAYS consecutive rays of one (emitter, iteration) job.  Rays are
+// One CTA processes one tile (512..8192 consecutive rays, chosen per launch) of one (emitter, iteration) job.  Rays are
 // generated in registers (rsk_raygen.cuh), traced against the 8-wide quantised BVH (or, without BVH, against all
 // triangles in input order) and tallied into a per-CTA shared-memory histogram that is flushed with one global
 // atomic per touched bin.  Rays never touch HBM.
@@ -128,11 +128,13 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
     const int sky_base = MODE == MODE_DUAL ? a.n_hist : 0;
     const int n_sky = MODE == MODE_DUAL ? a.n_hist2 : a.n_hist;
 
-    // each warp owns 512 consecutive rays of the tile and hands them to its lanes on demand
-    const int WARP_RAYS = a.tile_rays / (RSK_TILE_THREADS / 32);
     const int tile_n = (int)(end - begin);
+#if !(RSK_RAY_BUFFER && RSK_CTA_POOL)
+    // fixed slices: each warp owns tile_rays/8 consecutive rays of the tile and hands them to its lanes on demand
+    const int WARP_RAYS = a.tile_rays / (RSK_TILE_THREADS / 32);
     int next = warp * WARP_RAYS;
     const int wend = min(next + WARP_RAYS, tile_n);
+#endif
 
 #if RSK_RAY_BUFFER
     constexpr int RAY_SLOTS = 64;        // a top-up adds <= 32 rays to < 32 leftovers
