@@ -299,7 +299,7 @@ __global__ void k_collapse(const CollapseArgs a) {
     cand[0] = a.left[bnode];
     cand[1] = a.right[bnode];
     const bool bottom = sub_count(a, bnode) <= RSK_BOTTOM_MAX;
-    while (nc < RSK_WIDE) {
+    while (nc < RSK_FANOUT) {
         int best = -1;
         float best_score = -1.f;
         for (int c = 0; c < nc; ++c) {
@@ -335,7 +335,7 @@ __global__ void k_collapse(const CollapseArgs a) {
         for (int c = 0; c < nc; ++c) {
             if (slot_of[c] >= 0) continue;
             const float vx = 0.5f * (clo[c].x + chi[c].x) - ctr.x, vy = 0.5f * (clo[c].y + chi[c].y) - ctr.y, vz = 0.5f * (clo[c].z + chi[c].z) - ctr.z;
-            for (int s = 0; s < RSK_WIDE; ++s) {
+            for (int s = 0; s < RSK_FANOUT; ++s) {
                 if (child_in[s] >= 0) continue;
                 const float v = ((s & 1) ? vx : -vx) + ((s & 2) ? vy : -vy) + ((s & 4) ? vz : -vz);
                 if (v > bestv) { bestv = v; bc = c; bs = s; }

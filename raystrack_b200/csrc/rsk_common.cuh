@@ -50,7 +50,10 @@ constexpr int RSK_TILE_THREADS = 256;      // threads per CTA of the trace kerne
 constexpr int RSK_TILE_RAYS_MAX = 8192;    // rays per CTA tile: chosen per launch between 512 and this (rsk_pick_tile_rays)
 constexpr int RSK_TREGENZA_BINS = 145;     // utils/cuda_trace.py:12
 constexpr float RSK_INF = 1.0e20f;         // utils/cpu_trace.py:8
-constexpr int RSK_WIDE = 8;                // fan-out of the wide BVH
+constexpr int RSK_WIDE = 8;                // slots of a wide node
+#ifndef RSK_FANOUT
+#define RSK_FANOUT 8                        // children actually used per node (8, or 4 = slots 0..3 only: experiment)
+#endif
 #ifndef RSK_LEAF_MAX_TRIS
 #define RSK_LEAF_MAX_TRIS 3
 #endif

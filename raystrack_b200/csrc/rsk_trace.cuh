@@ -128,7 +128,7 @@ __device__ __forceinline__ void rsk_test_node(const uint4 *__restrict__ nodes, u
     const bool px = w.octinv & 1u, py = w.octinv & 2u, pz = w.octinv & 4u;
     uint32_t hits = 0;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 0; half < RSK_FANOUT / 4; ++half) {
         const uint32_t meta = half ? n1.w : n1.z;
         const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
         const uint32_t hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;

@@ -20,6 +20,7 @@ VARIANTS = {      # compile-time knobs of csrc/rsk_trace.cu(h) and csrc/rsk_bvh.
     "ploc_r16": ("RSK_PLOC=1", "RSK_PLOC_RADIUS=16"),
     "bottom16": ("RSK_BOTTOM_MAX=16",),
     "regs80": ("RSK_MIN_CTAS_PER_SM=3",),
+    "fanout4": ("RSK_FANOUT=4",),
 }
 OUT = ROOT / "raystrack_b200" / "_lib" / "variants"
 
