@@ -10,6 +10,7 @@ reads "how many emitters are still running".
 from __future__ import annotations
 
 import functools
+import os
 import time
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -244,41 +245,60 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
     n_emit = active.shape[0]
     n_surf = active.shape[1]
     rank, world = _dist_env()
-    plan = plan_shards(todo, n_rays_once, world)[rank]
-    ids = np.asarray([j[0] for j in plan], np.int32)
-    ranges = np.asarray([[j[1], j[2]] for j in plan], np.int64).reshape(-1, 2)
-    n_shared = sum(1 for j in plan if j[3])
-    any_shared = world > 1 and any(j[3] for shard in plan_shards(todo, n_rays_once, world) for j in shard)
-    kw = {}
-    if not sky:
-        kw = dict(emit_sid=np.asarray(emit_sid)[ids], min_sid=np.asarray(min_sid)[ids])
-    with _Phase("solve_begin"):
-        solve = _native.Solve(ctx, d_scene.native, d_em.native, ids,
-                              active[ids] if len(plan) else np.zeros((0, n_surf), np.uint8),
-                              table, ids.copy(), max_iters=max_iters, min_iters=min_iters, interval=interval,
-                              tol_mode=tol_mode, tol=tol, sky=sky, discrete=discrete, ray_range=ranges, **kw)
-    try:
-        with _Phase("iterate"):
-            if any_shared:
-                _run_solve_shared(solve, n_shared, min_iters, max_iters, ctx.device)
-            else:
-                _run_solve(solve, min_iters, max_iters)
-        with _Phase("download"):
-            loc, it_loc, tot_loc = solve.read_block()
-    finally:
-        with _Phase("solve_end"):
-            solve.close()
+    all_plans = plan_shards(todo, n_rays_once, world)
+    plan = all_plans[rank]
+    any_shared = world > 1 and any(j[3] for shard in all_plans for j in shard)
     n_hist = (145 if discrete else 1) if sky else 2 * n_surf
-    if world == 1 and len(plan) == n_emit:
-        return loc, it_loc.astype(np.int64), tot_loc          # every emitter, in order: no scatter needed
-    tallies = np.zeros((n_emit, n_hist), np.int64)
-    iters = np.zeros(n_emit, np.int64)
-    totals = np.zeros(n_emit, np.int64)
-    keep = np.asarray([not (j[3] and rank != 0) for j in plan], bool)      # replicated (ray-split) jobs count once
-    if keep.any():
-        tallies[ids[keep]] = loc[keep]
-        iters[ids[keep]] = it_loc[keep]
-        totals[ids[keep]] = tot_loc[keep]
+
+    # The device keeps ~40 bytes per (job, bin): iteration tally, total, Welford mean/M2 (+ previous estimate).  Jobs
+    # are solved in chunks that fit a memory budget; emitters are independent, so chunking cannot change any result.
+    # Ray-split jobs (first in every rank's list, same order everywhere) stay together in the first chunk.
+    budget = max(1.0, float(os.environ.get("RSK_SOLVE_MEMORY_MB", "16384")) * (1 << 20))
+    per_job = 40 * max(1, n_hist)
+    max_jobs = max(1, int(budget // per_job))
+    n_shared = sum(1 for j in plan if j[3])
+    chunks: List[List[Tuple[int, int, int, bool]]] = []
+    head = plan[:max(n_shared, min(len(plan), max_jobs))] if plan else []
+    if head or not plan:
+        chunks.append(head)
+    for lo in range(len(head), len(plan), max_jobs):
+        chunks.append(plan[lo:lo + max_jobs])
+
+    single = world == 1 and len(chunks) == 1 and len(plan) == n_emit
+    tallies = iters = totals = None
+    if not single:
+        tallies = np.zeros((n_emit, n_hist), np.int64)
+        iters = np.zeros(n_emit, np.int64)
+        totals = np.zeros(n_emit, np.int64)
+    for c, chunk in enumerate(chunks):
+        ids = np.asarray([j[0] for j in chunk], np.int32)
+        ranges = np.asarray([[j[1], j[2]] for j in chunk], np.int64).reshape(-1, 2)
+        kw = {}
+        if not sky:
+            kw = dict(emit_sid=np.asarray(emit_sid)[ids], min_sid=np.asarray(min_sid)[ids])
+        with _Phase("solve_begin"):
+            solve = _native.Solve(ctx, d_scene.native, d_em.native, ids,
+                                  active[ids] if len(chunk) else np.zeros((0, n_surf), np.uint8),
+                                  table, ids.copy(), max_iters=max_iters, min_iters=min_iters, interval=interval,
+                                  tol_mode=tol_mode, tol=tol, sky=sky, discrete=discrete, ray_range=ranges, **kw)
+        try:
+            with _Phase("iterate"):
+                if any_shared and c == 0:
+                    _run_solve_shared(solve, sum(1 for j in chunk if j[3]), min_iters, max_iters, ctx.device)
+                else:
+                    _run_solve(solve, min_iters, max_iters)
+            with _Phase("download"):
+                loc, it_loc, tot_loc = solve.read_block()
+        finally:
+            with _Phase("solve_end"):
+                solve.close()
+        if single:
+            return loc, it_loc.astype(np.int64), tot_loc      # every emitter, in order: no scatter needed
+        keep = np.asarray([not (j[3] and rank != 0) for j in chunk], bool)     # replicated (ray-split) jobs count once
+        if keep.any():
+            tallies[ids[keep]] = loc[keep]
+            iters[ids[keep]] = it_loc[keep]
+            totals[ids[keep]] = tot_loc[keep]
     if world > 1:
         from .dist import allreduce_sum_
         allreduce_sum_([tallies, iters, totals], device=ctx.device)

@@ -157,3 +157,17 @@ def test_convergence_interval_and_max_iters_edge(rb):
             assert y >= x and (y - 5) % 7 == 0 or y == 60
     empty = rb.view_factor_matrix(meshes, rb.MatrixParams(samples=8, rays=32, max_iters=0))
     assert all(row == {} for row in empty.values())
+
+
+def test_chunked_solve_equals_single_solve(rb, monkeypatch):
+    """RSK_SOLVE_MEMORY_MB bounds the per-solve device state; emitters are then solved in chunks.  Emitters are
+    independent, so the result must not change by a single bit."""
+    from raystrack_b200 import synthetic
+    meshes = synthetic.urban_block(3, 4, 8, 0)
+    p = rb.MatrixParams(samples=2, rays=16, seed=3, bvh="builtin", max_iters=20, min_iters=4, tol=2e-3, reciprocity=True)
+    sp = rb.SkyParams(samples=2, rays=16, seed=3, bvh="builtin", max_iters=9, min_iters=4, tol=1e-3, discrete=True)
+    whole = rb.view_factor_matrix(meshes, p)
+    whole_sky = rb.view_factor_to_tregenza_sky(meshes, sp)
+    monkeypatch.setenv("RSK_SOLVE_MEMORY_MB", "0.02")            # ~5 emitters per chunk
+    assert rb.view_factor_matrix(meshes, p) == whole
+    assert rb.view_factor_to_tregenza_sky(meshes, sp) == whole_sky
