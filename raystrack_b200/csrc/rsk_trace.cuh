@@ -16,21 +16,28 @@ static_assert(RSK_MAX_DEPTH == RSK_MAX_DEPTH_HOST, "stack size mismatch");
 // inv_det,u,v,t to float64; measured per-ray disagreement of the float32 form is ~3e-7).
 __device__ __forceinline__ bool rsk_tri_hit(const float4 &V0, const float4 &E1, const float4 &E2,
                                             float ox, float oy, float oz, float dx, float dy, float dz, float &t) {
-    const float px = dy * E2.z - dz * E2.y;
-    const float py = dz * E2.x - dx * E2.z;
-    const float pz = dx * E2.y - dy * E2.x;
-    const float det = E1.x * px + E1.y * py + E1.z * pz;
+    // Every product/sum is written as an explicit multiply or fused multiply-add: the compiler may not re-associate
+    // or contract them differently in different instantiations of the kernel, so a ray on a triangle's edge gets
+    // the same verdict in the matrix, sky and dual kernels.
+#define RSK_CROSS(a, b, c, d) __fmaf_rn(a, b, -__fmul_rn(c, d))                       /* a*b - c*d */
+#define RSK_DOT(ax, ay, az, bx, by, bz) __fmaf_rn(az, bz, __fmaf_rn(ay, by, __fmul_rn(ax, bx)))
+    const float px = RSK_CROSS(dy, E2.z, dz, E2.y);
+    const float py = RSK_CROSS(dz, E2.x, dx, E2.z);
+    const float pz = RSK_CROSS(dx, E2.y, dy, E2.x);
+    const float det = RSK_DOT(E1.x, E1.y, E1.z, px, py, pz);
     if (fabsf(det) < 1e-7f) return false;
-    const float inv_det = 1.0f / det;
-    const float tx = ox - V0.x, ty = oy - V0.y, tz = oz - V0.z;
-    const float u = (tx * px + ty * py + tz * pz) * inv_det;
+    const float inv_det = __fdiv_rn(1.0f, det);
+    const float tx = __fsub_rn(ox, V0.x), ty = __fsub_rn(oy, V0.y), tz = __fsub_rn(oz, V0.z);
+    const float u = __fmul_rn(RSK_DOT(tx, ty, tz, px, py, pz), inv_det);
     if (u < 0.0f || u > 1.0f) return false;
-    const float qx = ty * E1.z - tz * E1.y;
-    const float qy = tz * E1.x - tx * E1.z;
-    const float qz = tx * E1.y - ty * E1.x;
-    const float v = (dx * qx + dy * qy + dz * qz) * inv_det;
-    if (v < 0.0f || u + v > 1.0f) return false;
-    t = (E2.x * qx + E2.y * qy + E2.z * qz) * inv_det;
+    const float qx = RSK_CROSS(ty, E1.z, tz, E1.y);
+    const float qy = RSK_CROSS(tz, E1.x, tx, E1.z);
+    const float qz = RSK_CROSS(tx, E1.y, ty, E1.x);
+    const float v = __fmul_rn(RSK_DOT(dx, dy, dz, qx, qy, qz), inv_det);
+    if (v < 0.0f || __fadd_rn(u, v) > 1.0f) return false;
+    t = __fmul_rn(RSK_DOT(E2.x, E2.y, E2.z, qx, qy, qz), inv_det);
+#undef RSK_CROSS
+#undef RSK_DOT
     return true;
 }
 

@@ -21,6 +21,15 @@ VARIANTS = {      # compile-time knobs of csrc/rsk_trace.cu(h) and csrc/rsk_bvh.
     "bottom16": ("RSK_BOTTOM_MAX=16",),
     "regs80": ("RSK_MIN_CTAS_PER_SM=3",),
     "fanout4": ("RSK_FANOUT=4",),
+    "tris_at_once": ("RSK_POSTPONE=0",),
+    "p6i3": ("RSK_POSTPONE=6", "RSK_POSTPONE_IDLE=3"),
+    "p10i2": ("RSK_POSTPONE=10", "RSK_POSTPONE_IDLE=2"),
+    "p10i8": ("RSK_POSTPONE=10", "RSK_POSTPONE_IDLE=8"),
+    "p16i4": ("RSK_POSTPONE=16", "RSK_POSTPONE_IDLE=4"),
+    "p16i8": ("RSK_POSTPONE=16", "RSK_POSTPONE_IDLE=8"),
+    "p32i6": ("RSK_POSTPONE=32", "RSK_POSTPONE_IDLE=6"),
+    "p10i4_refill20": ("RSK_REFILL_BELOW=20",),
+    "p10i4_refill28": ("RSK_REFILL_BELOW=28",),
 }
 OUT = ROOT / "raystrack_b200" / "_lib" / "variants"
 
@@ -36,7 +45,10 @@ if __name__ == "__main__":
             print(name, _build.build(force=True, defines=defs or ("RSK_VARIANT_BUILD=1",), out=OUT / f"librsk_{name}.so"), flush=True)
     else:
         extra = sys.argv[2:] or ["--iters", "3"]
+        only_run = os.environ.get("RSK_VARIANTS", "").split(",") if os.environ.get("RSK_VARIANTS") else None
         for name in VARIANTS:
+            if only_run and name not in only_run:
+                continue
             lib = OUT / f"librsk_{name}.so"
             if not lib.exists():
                 continue

@@ -48,7 +48,11 @@ ctx.timer_start()
 solve.step(args.iters)
 ms = ctx.timer_stop()
 rays = solve.rays_traced() - r0
-print(f"{rays} rays in {ms:.1f} ms -> {rays/ms/1e6:.4f} Grays/s", flush=True)
+crc = ""
 if not args.sky:
+    import zlib
     hf, hb, it, tot, _, _ = solve.read_matrix()
+    crc = f"  tallies crc32 {zlib.crc32(hf.tobytes() + hb.tobytes()):08x}"
+print(f"{rays} rays in {ms:.1f} ms -> {rays/ms/1e6:.4f} Grays/s{crc}", flush=True)
+if not args.sky:
     print("hit fraction", (hf.sum() + hb.sum()) / tot.sum(), "iters", it[:3], "launches", ctx.launch_count())
