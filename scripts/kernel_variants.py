@@ -23,13 +23,7 @@ VARIANTS = {      # compile-time knobs of csrc/rsk_trace.cu(h) and csrc/rsk_bvh.
     "fanout4": ("RSK_FANOUT=4",),
     "tris_at_once": ("RSK_POSTPONE=0",),
     "p6i3": ("RSK_POSTPONE=6", "RSK_POSTPONE_IDLE=3"),
-    "p10i2": ("RSK_POSTPONE=10", "RSK_POSTPONE_IDLE=2"),
-    "p10i8": ("RSK_POSTPONE=10", "RSK_POSTPONE_IDLE=8"),
-    "p16i4": ("RSK_POSTPONE=16", "RSK_POSTPONE_IDLE=4"),
-    "p16i8": ("RSK_POSTPONE=16", "RSK_POSTPONE_IDLE=8"),
     "p32i6": ("RSK_POSTPONE=32", "RSK_POSTPONE_IDLE=6"),
-    "p10i4_refill20": ("RSK_REFILL_BELOW=20",),
-    "p10i4_refill28": ("RSK_REFILL_BELOW=28",),
 }
 OUT = ROOT / "raystrack_b200" / "_lib" / "variants"
 
