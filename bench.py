@@ -11,7 +11,8 @@ followed by the on-device statistics/convergence pass.  Prints ONE JSON line (ra
   value     closest-hit Grays/s of the whole job, inputs resident in HBM, timed with CUDA events on the launching
             stream, max over ranks; L2 is flushed between timed steps
   e2e       the same metric through the public API ``view_factor_matrix`` (C ABI underneath) with HOST buffers:
-            scene + emitter upload, GPU BVH build, one iteration, tally download and result assembly per step
+            every call starts from the mesh list alone -- vertices + faces uploaded, triangle/emitter records and the
+            BVH built on the GPU, 40 iterations, tally download and result assembly
   roofline  memory roofline of the dominant kernel (rsk_trace_kernel<matrix,bvh>): algorithmic bytes per ray
             (reference data layout, counted by the oracle's instrumented replay) x rays / kernel time
   cpu_baseline / --impl reference: the CPU oracle port of the reference's Numba kernels (oracle/), all host threads,
@@ -185,13 +186,12 @@ def run_ours(args):
     meshes = build_scene(args.side)
     ps = PreparedSolver(meshes)
     t = time.time()
-    ems = ps.get_emitters(samples=args.samples, rays=args.rays, flip_faces=False)
-    ps.get_scene(use_bvh=True)
-    prep_s = time.time() - t
-    t = time.time()
-    sc = ps.get_device_scene(use_bvh=True, ctx=ctx)
+    sc = ps.get_device_scene(use_bvh=True, ctx=ctx)            # raw meshes up, records + BVH built on the GPU
     em = ps.get_device_emitters(samples=args.samples, rays=args.rays, flip_faces=False, ctx=ctx)
-    upload_s = time.time() - t
+    ems = ps.get_emitter_summaries(samples=args.samples, rays=args.rays, flip_faces=False, ctx=ctx)
+    ctx.synchronize()
+    prep_s = time.time() - t
+    geometry_bytes = ps._geometry(ctx).h2d_bytes
     info = sc.info()
     n = len(meshes)
     centers, extents = ps.get_mesh_bounds()
@@ -258,22 +258,19 @@ def run_ours(args):
     solve.close()
 
     # ---- e2e through the public API with host buffers: the BASELINE config-#5 call (fixed iteration count so every
-    # implementation traces identical rays), device copies rebuilt from the host arrays inside every timed call
-    ps2 = PreparedSolver(meshes)          # shares nothing on the device with `ps`; host preparation is cached
-    ps2._scene_cache, ps2._emitter_cache, ps2._mesh_bounds_cache, ps2._emitter_pack_cache = \
-        ps._scene_cache, ps._emitter_cache, ps._mesh_bounds_cache, ps._emitter_pack_cache
+    # implementation traces identical rays).  Every timed call starts from the caller's mesh list alone: flattening,
+    # upload, device-side preparation, BVH build, masks, the iterations, tally download and the result dict.
     old_log = M._log
     M._log = lambda msg: None
 
     def timed_call(iters):
         prm = MatrixParams(samples=args.samples, rays=args.rays, seed=args.seed, bvh="builtin", reciprocity=False,
                            max_iters=iters, min_iters=iters, tol=0.0)
-        ps2.clear_device_cache()
         torch.cuda.synchronize()
         if world > 1:
             D.barrier()
         t0 = time.perf_counter()
-        view_factor_matrix(meshes, prm, prepared=ps2)
+        view_factor_matrix(meshes, prm)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         phases.append({k: round(1e3 * v, 1) for k, v in M.LAST_TIMING.items()})
@@ -287,11 +284,10 @@ def run_ours(args):
             e2e_single = [timed_call(1) for _ in range(3)]
     finally:
         M._log = old_log
-        ps2.clear_device_cache()
     e2e_value = rays_per_step * args.e2e_iters / float(np.mean(e2e_times)) / 1e9 if e2e_times else None
     e2e_single_value = rays_per_step / float(np.mean(e2e_single)) / 1e9 if e2e_single else None
     n_tri = ps.total_faces
-    h2d = n_tri * 52 + n_tri * 80 + n * n + table.nbytes       # scene arrays + emitter arrays + surf_active + rotations
+    h2d = geometry_bytes + n * n + table.nbytes                # vertices + faces + offsets, surf_active, rotations
     d2h = len(ids) * 2 * n * 8 + len(ids) * 12                 # int64 tally block + iteration/ray counters
 
     if world > 1:
@@ -306,12 +302,12 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "step": "one Monte-Carlo iteration of all 2001 emitters", "rays_per_step": rays_per_step,
                        "bvh": f"GPU LBVH -> 8-wide quantised, {info['n_nodes']} nodes, depth {info['depth']}, built in {info['build_us']/1e3:.1f} ms",
                        "l2": "flushed between timed steps (256 MB write)", "sharding": f"emitters over {world} GPU(s), {n_shared} ray-split",
-                       "host_prep_s": round(prep_s, 3), "upload_build_s": round(upload_s, 3)},
+                       "upload_prepare_build_s": round(prep_s, 3)},
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "call": f"view_factor_matrix(meshes, MatrixParams(samples=4, rays=64, bvh='builtin', reciprocity=False, "
-                            f"min_iters=max_iters={args.e2e_iters}, tol=0)): upload of scene+emitters, GPU BVH build, "
-                            f"{args.e2e_iters} iterations, tally download, result dict",
+                            f"min_iters=max_iters={args.e2e_iters}, tol=0)) from the mesh list alone: upload of vertices+faces, "
+                            f"device-side preparation, GPU BVH build, {args.e2e_iters} iterations, tally download, result dict",
                     "ms_per_step": 1e3 * float(np.mean(e2e_times)) if e2e_times else None,
                     "phases_ms_last_call": phases[args.e2e_steps] if len(phases) > args.e2e_steps else None,
                     "single_iteration_call": {"value": e2e_single_value, "unit": UNIT,

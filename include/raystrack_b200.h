@@ -40,6 +40,7 @@ typedef struct rsk_ctx rsk_ctx;
 typedef struct rsk_scene rsk_scene;
 typedef struct rsk_emitters rsk_emitters;
 typedef struct rsk_solve rsk_solve;
+typedef struct rsk_geometry rsk_geometry;
 
 /* ------------------------------------------------------------------------------------------- library */
 
@@ -96,6 +97,46 @@ int rsk_emitters_destroy(rsk_emitters *em);
 /* Test hook: the cached tables.  dims: float32[5][n] (rows: bases 5,2,3,7,11), n <= max rays/iteration;
  * grid_u/grid_v: float32[g*g] for a grid side used by one of the emitters. */
 int rsk_emitters_download_tables(rsk_emitters *em, int64_t n, float *dims, int32_t g, float *grid_u, float *grid_v);
+
+/* ------------------------------------------------------------------------------------------- device-side preparation
+ * Replaces prepare_scene / prepare_emitters (utils/prepared.py:93-321: `_unit_rows`, `_triangle_frames`,
+ * `_triangle_origin_eps`, the area CDF, `grid_from_density`, the statistics of `_emitter_plane`) for callers that
+ * hold raw meshes: only vertices and faces are uploaded, the per-triangle records are computed on the GPU with
+ * NumPy's float32 operation order (bit-identical to the host arrays rsk_scene_create / rsk_emitters_create take).
+ * verts: float32[n_vert][3] of all meshes back to back (the reference casts vertices to float32 first,
+ * prepared.py:182-188); faces: int32[n_tri][3] with indices local to their mesh; mesh i owns vertices
+ * [vert_offset[i], vert_offset[i+1]) and triangles [tri_offset[i], tri_offset[i+1]).  Mesh i becomes surface i. */
+int rsk_geometry_create(rsk_ctx *ctx, int32_t n_mesh, const float *verts, const int64_t *vert_offset,
+                        const int32_t *faces, const int64_t *tri_offset, rsk_geometry **out);
+int rsk_geometry_destroy(rsk_geometry *geometry);
+/* Same result as rsk_scene_create on prepare_scene's arrays. */
+int rsk_scene_from_geometry(rsk_geometry *geometry, int32_t use_bvh, rsk_scene **out);
+/* Per-mesh by-products of the emitter preparation.  total_area = float(areas.sum()) in NumPy's pairwise float32
+ * order (it fixes the grid side g = max(ceil(sqrt(total_area * density)), 4)); origin / normal0 = first corner and
+ * unit normal of the first triangle; eps_max = largest ray-origin offset.  min_dot, worst, worst_mag are float64
+ * statistics for the planarity test of `_emitter_plane` (prepared.py:133-167): min over triangles of n.normal0; max
+ * over corners p of |(p - origin).normal0|; and the size of the terms of that dot product (its rounding scale). */
+typedef struct rsk_mesh_summary {
+    double total_area;
+    float origin[3];
+    float normal0[3];
+    float eps_max;
+    float reserved;
+    double min_dot;
+    double worst;
+    double worst_mag;
+} rsk_mesh_summary;
+/* Same device object as rsk_emitters_create on prepare_emitters' arrays (faces flipped to [0,2,1] if flip_faces);
+ * density is the `samples` parameter.  summary: rsk_mesh_summary[n_mesh], filled on return. */
+int rsk_emitters_from_geometry(rsk_geometry *geometry, double density, int32_t rays_per_cell, int32_t flip_faces,
+                               rsk_emitters **out, rsk_mesh_summary *summary);
+/* g: int32[n_emit] grid sides, n_rays_once: int64[n_emit]; either may be NULL. */
+int rsk_emitters_info(rsk_emitters *em, int32_t *g, int64_t *n_rays_once);
+/* Test hooks: the packed device records.  records: float32[n_tri][20] = (a,eps)(e1,n.x)(e2,n.y)(u,n.z)(v,0) per
+ * emitter triangle, cdf: float32[n_tri];  tri: float32[n_tri][12] = (v0,sid)(e1,0)(e2,0) and normals:
+ * float32[n_tri][4] = (n,sid) in traversal order (input order for a scene without BVH). */
+int rsk_emitters_download_records(rsk_emitters *em, float *records, float *cdf);
+int rsk_scene_download_triangles(rsk_scene *scene, float *tri, float *normals);
 
 /* ------------------------------------------------------------------------------------------- per-ray hook
  * Replaces build_rays + trace_cpu_[bvh_]firsthit / trace_cpu_[bvh_]hitmask called back to back

@@ -12,7 +12,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT_DIR = PKG / "_lib"
 LIB = OUT_DIR / "librsk_b200.so"
-SOURCES = ["rsk_api.cu", "rsk_qmc.cu", "rsk_bvh.cu", "rsk_trace.cu", "rsk_stats.cu"]
+SOURCES = ["rsk_api.cu", "rsk_qmc.cu", "rsk_bvh.cu", "rsk_trace.cu", "rsk_stats.cu", "rsk_prepare.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",

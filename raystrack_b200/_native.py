@@ -26,12 +26,25 @@ EXPORTS = (
     "rsk_ctx_launch_count", "rsk_ctx_device_info",
     "rsk_scene_create", "rsk_scene_destroy", "rsk_scene_info", "rsk_scene_download_bvh",
     "rsk_emitters_create", "rsk_emitters_destroy", "rsk_emitters_download_tables",
+    "rsk_geometry_create", "rsk_geometry_destroy", "rsk_scene_from_geometry", "rsk_emitters_from_geometry",
+    "rsk_emitters_info", "rsk_emitters_download_records", "rsk_scene_download_triangles",
     "rsk_trace_rays",
     "rsk_matrix_begin", "rsk_matrix_step", "rsk_matrix_read", "rsk_solve_read_block", "rsk_matrix_device_tallies",
     "rsk_sky_begin", "rsk_sky_step", "rsk_sky_read", "rsk_dual_begin", "rsk_dual_step", "rsk_dual_sky_part",
     "rsk_solve_enqueue_trace", "rsk_solve_enqueue_fold", "rsk_solve_poll", "rsk_solve_device_iter_tallies", "rsk_solve_set_iter_tally_buffer",
     "rsk_solve_destroy", "rsk_solve_rays_traced", "rsk_reciprocity_rowsum",
 )
+
+
+class MeshSummary(C.Structure):
+    """``rsk_mesh_summary``: per-mesh by-products of the device-side emitter preparation."""
+    _fields_ = [("total_area", C.c_double), ("origin", C.c_float * 3), ("normal0", C.c_float * 3), ("eps_max", C.c_float),
+                ("reserved", C.c_float), ("min_dot", C.c_double), ("worst", C.c_double), ("worst_mag", C.c_double)]
+
+
+MESH_SUMMARY_DTYPE = np.dtype([("total_area", "<f8"), ("origin", "<f4", 3), ("normal0", "<f4", 3), ("eps_max", "<f4"),
+                               ("reserved", "<f4"), ("min_dot", "<f8"), ("worst", "<f8"), ("worst_mag", "<f8")])
+assert MESH_SUMMARY_DTYPE.itemsize == C.sizeof(MeshSummary) == 64
 
 
 class NativeError(RuntimeError):
@@ -142,6 +155,34 @@ class Context:
         return int(sweeps.value)
 
 
+class DeviceGeometry:
+    """Wraps ``rsk_geometry``: the raw meshes (float32 vertices, int32 faces) of a scene on the device."""
+
+    def __init__(self, ctx: Context, verts: np.ndarray, vert_offset: np.ndarray, faces: np.ndarray, tri_offset: np.ndarray):
+        self.ctx = ctx
+        self.handle = C.c_void_p()
+        vo = np.ascontiguousarray(vert_offset, np.int64)
+        to = np.ascontiguousarray(tri_offset, np.int64)
+        verts = np.ascontiguousarray(verts, np.float32)
+        faces = np.ascontiguousarray(faces, np.int32)
+        self.n_mesh = int(vo.shape[0]) - 1
+        self.n_tri = int(to[-1])
+        self.h2d_bytes = int(verts.nbytes + faces.nbytes + vo.nbytes + to.nbytes)
+        check(ctx.lib.rsk_geometry_create(ctx.handle, C.c_int32(self.n_mesh), ptr(verts), ptr(vo), ptr(faces), ptr(to),
+                                          C.byref(self.handle)), "rsk_geometry_create")
+
+    def close(self) -> None:
+        if self.handle:
+            self.ctx.lib.rsk_geometry_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DeviceScene:
     """Wraps ``rsk_scene`` (triangles + GPU-built wide BVH)."""
 
@@ -155,6 +196,26 @@ class DeviceScene:
         sid = np.ascontiguousarray(sid, np.int32)
         check(ctx.lib.rsk_scene_create(ctx.handle, *(ptr(a) for a in arrs), ptr(sid), C.c_int64(self.n_tri),
                                        C.c_int32(n_surf), C.c_int32(1 if use_bvh else 0), C.byref(self.handle)), "rsk_scene_create")
+
+    @classmethod
+    def from_geometry(cls, geometry: "DeviceGeometry", use_bvh: bool) -> "DeviceScene":
+        """``rsk_scene_from_geometry``: the triangle records are computed on the GPU from the raw meshes."""
+        self = cls.__new__(cls)
+        self.ctx = geometry.ctx
+        self.handle = C.c_void_p()
+        self.n_tri = geometry.n_tri
+        self.n_surf = geometry.n_mesh
+        self.use_bvh = bool(use_bvh and self.n_tri > 0)
+        check(self.ctx.lib.rsk_scene_from_geometry(geometry.handle, C.c_int32(1 if use_bvh else 0), C.byref(self.handle)),
+              "rsk_scene_from_geometry")
+        return self
+
+    def download_triangles(self):
+        """(tri float32[n,12], normals float32[n,4]) in traversal order (test hook)."""
+        tri = np.empty((self.n_tri, 12), np.float32)
+        nrm = np.empty((self.n_tri, 4), np.float32)
+        check(self.ctx.lib.rsk_scene_download_triangles(self.handle, ptr(tri), ptr(nrm)))
+        return tri, nrm
 
     def info(self) -> dict:
         info = (C.c_int64 * 8)()
@@ -195,6 +256,30 @@ class DeviceEmitters:
         self.rays = int(rays)
         check(ctx.lib.rsk_emitters_create(ctx.handle, C.c_int32(self.n_emit), ptr(off), *(ptr(a) for a in f), ptr(gs),
                                           C.c_int32(rays), C.byref(self.handle)), "rsk_emitters_create")
+
+    @classmethod
+    def from_geometry(cls, geometry: "DeviceGeometry", samples, rays: int, flip_faces: bool):
+        """``rsk_emitters_from_geometry``; returns (emitters, summary) with summary a MESH_SUMMARY_DTYPE array."""
+        self = cls.__new__(cls)
+        self.ctx = geometry.ctx
+        self.handle = C.c_void_p()
+        self.n_emit = geometry.n_mesh
+        self.rays = int(rays)
+        self.n_tri_total = geometry.n_tri
+        summary = np.zeros(self.n_emit, MESH_SUMMARY_DTYPE)
+        check(self.ctx.lib.rsk_emitters_from_geometry(geometry.handle, C.c_double(float(samples)), C.c_int32(int(rays)),
+                                                      C.c_int32(1 if flip_faces else 0), C.byref(self.handle), ptr(summary)),
+              "rsk_emitters_from_geometry")
+        self.g = np.empty(self.n_emit, np.int32)
+        check(self.ctx.lib.rsk_emitters_info(self.handle, ptr(self.g), None), "rsk_emitters_info")
+        return self, summary
+
+    def download_records(self, n_tri: int):
+        """(records float32[n_tri,20], cdf float32[n_tri]) as stored on the device (test hook)."""
+        rec = np.empty((n_tri, 20), np.float32)
+        cdf = np.empty(n_tri, np.float32)
+        check(self.ctx.lib.rsk_emitters_download_records(self.handle, ptr(rec), ptr(cdf)))
+        return rec, cdf
 
     def download_tables(self, n: int, g: int):
         dims = np.empty((5, n), np.float32)

@@ -140,14 +140,9 @@ extern "C" int rsk_scene_create(rsk_ctx *ctx, const float *v0, const float *e1, 
     *out = nullptr;
     RskScope scope(ctx);
     for (int64_t i = 0; i < n_tri; ++i) RSK_REQUIRE(sid[i] >= 0 && sid[i] < n_surf, "rsk_scene_create: sid out of range");
-    rsk_scene *sc = new rsk_scene();
-    sc->ctx = ctx;
-    sc->n_tri = n_tri;
-    sc->n_surf = n_surf;
-    sc->use_bvh = (use_bvh && n_tri > 0) ? 1 : 0;
     // the caller's five arrays go to the device as they are; records are packed there
     float *raw = nullptr; int32_t *d_sid = nullptr; float4 *d_tri = nullptr, *d_nrm = nullptr;
-    auto fail = [&](int code) { rsk_dev_free(raw); rsk_dev_free(d_sid); rsk_dev_free(d_tri); rsk_dev_free(d_nrm); delete sc; return code; };
+    auto fail = [&](int code) { rsk_dev_free(raw); rsk_dev_free(d_sid); rsk_dev_free(d_tri); rsk_dev_free(d_nrm); return code; };
     int rc = rsk_dev_alloc(&raw, (size_t)n_tri * 12);
     if (rc == RSK_OK) rc = rsk_dev_alloc(&d_sid, (size_t)n_tri);
     if (rc == RSK_OK) rc = rsk_dev_alloc(&d_tri, (size_t)n_tri * 3);
@@ -167,8 +162,18 @@ extern "C" int rsk_scene_create(rsk_ctx *ctx, const float *v0, const float *e1, 
     }
     rsk_dev_free(raw); raw = nullptr;
     rsk_dev_free(d_sid); d_sid = nullptr;
+    return rsk_scene_adopt(ctx, d_tri, d_nrm, n_tri, n_surf, use_bvh, out);
+}
+
+// Turn packed device records (ownership passes to the scene) into a scene: build the BVH or keep input order.
+int rsk_scene_adopt(rsk_ctx *ctx, float4 *d_tri, float4 *d_nrm, int64_t n_tri, int32_t n_surf, int32_t use_bvh, rsk_scene **out) {
+    rsk_scene *sc = new rsk_scene();
+    sc->ctx = ctx;
+    sc->n_tri = n_tri;
+    sc->n_surf = n_surf;
+    sc->use_bvh = (use_bvh && n_tri > 0) ? 1 : 0;
     if (sc->use_bvh) {
-        rc = rsk_bvh_build(sc, d_tri, d_nrm);
+        const int rc = rsk_bvh_build(sc, d_tri, d_nrm);
         rsk_dev_free(d_tri);
         rsk_dev_free(d_nrm);
         if (rc != RSK_OK) { rsk_scene_destroy(sc); return rc; }

@@ -210,6 +210,7 @@ static inline int rsk_pick_tile_rays(int64_t total_rays, int sm_count) {
 int rsk_qmc_ensure_halton(rsk_ctx *ctx, int64_t n);
 int rsk_qmc_ensure_grid(rsk_ctx *ctx, int g, int64_t *offset);
 int rsk_bvh_build(rsk_scene *scene, const float4 *tri_in, const float4 *nrm_in);
+int rsk_scene_adopt(rsk_ctx *ctx, float4 *d_tri, float4 *d_nrm, int64_t n_tri, int32_t n_surf, int32_t use_bvh, rsk_scene **out);
 
 // Device memory comes from the device's default stream-ordered pool (cudaMallocAsync) with an unlimited release
 // threshold: repeated solves reuse the same blocks without ever calling cudaMalloc/cudaFree (both of which

@@ -109,14 +109,17 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
         for (int i = 0; i < 7; ++i) cp[i] = __ldg(row + i);
     }
 
-    // shared memory: [occluder mask][receiver mask (dual only)][histogram][traversal stacks]
+    // shared memory: [traversal stacks][ray buffers][occluder mask][receiver mask (dual only)][histogram]
+    // (the fixed-size parts come first, so the addresses the walk loop uses are compile-time offsets)
+    constexpr int STACK_WORDS = BVH ? RSK_SMEM_STACK * RSK_TILE_THREADS * 2 : 0;
+    constexpr int RAY_WORDS = RSK_RAY_BUFFER ? (RSK_TILE_THREADS / 32) * 7 * 64 : 0;
     const int mw = a.sc.mask_words;
     const int n_hist_all = a.n_hist + (MODE == MODE_DUAL ? a.n_hist2 : 0);
-    uint32_t *s_mask = smem;                                   // surfaces that stop / receive rays
-    uint32_t *s_recv = MODE == MODE_DUAL ? smem + mw : smem;   // surfaces the matrix may tally
-    uint32_t *s_hist = smem + (MODE == MODE_DUAL ? 2 * mw : mw);
+    uint2 *s_stack = reinterpret_cast<uint2 *>(smem);
+    uint32_t *s_mask = smem + STACK_WORDS + RAY_WORDS;         // surfaces that stop / receive rays
+    uint32_t *s_recv = MODE == MODE_DUAL ? s_mask + mw : s_mask;   // surfaces the matrix may tally
+    uint32_t *s_hist = s_mask + (MODE == MODE_DUAL ? 2 * mw : mw);
     const int hist_words = a.hist_in_smem ? n_hist_all : 0;
-    uint2 *s_stack = reinterpret_cast<uint2 *>(smem + (((MODE == MODE_DUAL ? 2 * mw : mw) + hist_words + 1) & ~1));
     {
         // dual jobs whose sky side is finished walk with the receiver mask only (ineligible meshes are invisible)
         const uint32_t *occ = (MODE == MODE_DUAL && want_s) ? a.surf_mask2 : a.surf_mask;
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
 
 #if RSK_RAY_BUFFER
     constexpr int RAY_SLOTS = 64;        // a top-up adds <= 32 rays to < 32 leftovers
-    float *s_rays = reinterpret_cast<float *>(s_stack + (BVH ? RSK_SMEM_STACK * RSK_TILE_THREADS : 0)) + warp * (7 * RAY_SLOTS);
+    float *s_rays = reinterpret_cast<float *>(smem + STACK_WORDS) + warp * (7 * RAY_SLOTS);
     int buf_n = 0;
 #if RSK_CTA_POOL
     bool pool_empty = tile_n <= 0;
@@ -414,9 +417,9 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
 
 static size_t rsk_trace_smem(const TraceArgs &a, bool bvh, bool dual) {
     const size_t hist = (size_t)a.n_hist + (dual ? a.n_hist2 : 0);
-    size_t words = ((size_t)a.sc.mask_words * (dual ? 2 : 1) + (a.hist_in_smem ? hist : 0) + 1) & ~(size_t)1;
-    return words * 4 + (bvh ? (size_t)RSK_SMEM_STACK * RSK_TILE_THREADS * sizeof(uint2) : 0)
-           + (RSK_RAY_BUFFER ? (size_t)(RSK_TILE_THREADS / 32) * 7 * 64 * sizeof(float) : 0);
+    const size_t words = (size_t)a.sc.mask_words * (dual ? 2 : 1) + (a.hist_in_smem ? hist : 0);
+    return (bvh ? (size_t)RSK_SMEM_STACK * RSK_TILE_THREADS * sizeof(uint2) : 0)
+           + (RSK_RAY_BUFFER ? (size_t)(RSK_TILE_THREADS / 32) * 7 * 64 * sizeof(float) : 0) + words * 4;
 }
 
 template <int MODE, bool BVH>

@@ -330,14 +330,14 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
     result: Dict[str, Dict[str, float]] = {name: {} for name, _, _ in meshes}
     LAST_TIMING.clear()
     with _Phase("host_prepare"):
-        emitters = solver.get_emitters(samples=samples, rays=rays, flip_faces=flip_faces)
-        areas = [em.total_area for em in emitters] if reciprocity else None
         centers, extents = solver.get_mesh_bounds()
         ctx = _context()
     with _Phase("scene_upload_bvh"):
         d_scene = solver.get_device_scene(use_bvh=use_bvh, ctx=ctx)
     with _Phase("emitter_upload"):
         d_em = solver.get_device_emitters(samples=samples, rays=rays, flip_faces=flip_faces, ctx=ctx)
+        emitters = solver.get_emitter_summaries(samples=samples, rays=rays, flip_faces=flip_faces, ctx=ctx)
+        areas = [em.total_area for em in emitters] if reciprocity else None
 
     t0 = time.time()
     with _Phase("masks"):
@@ -432,8 +432,6 @@ def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepar
     use_bvh = _select_bvh(p["bvh"], solver.total_faces)
     if tol_mode not in ("stderr", "delta"):
         raise ValueError(f"Unknown tol_mode: {tol_mode}")
-    emitters = solver.get_emitters(samples=samples, rays=rays, flip_faces=False)       # main.py:1985
-    centers, extents = solver.get_mesh_bounds()
     keys = [f"Sky_Patch_{i}" for i in range(1, 146)] if discrete else ["Sky"]
     result: Dict[str, Dict[str, float]] = {name: {k: 0.0 for k in keys} for name, _, _ in meshes}
     n_surf = len(meshes)
@@ -441,8 +439,10 @@ def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepar
         return result
 
     ctx = _context()
+    centers, extents = solver.get_mesh_bounds()
     d_scene = solver.get_device_scene(use_bvh=use_bvh, ctx=ctx)
-    d_em = solver.get_device_emitters(samples=samples, rays=rays, flip_faces=False, ctx=ctx)
+    d_em = solver.get_device_emitters(samples=samples, rays=rays, flip_faces=False, ctx=ctx)     # main.py:1985
+    emitters = solver.get_emitter_summaries(samples=samples, rays=rays, flip_faces=False, ctx=ctx)
     t0 = time.time()
     active = _cached_masks(solver, emitters, centers, extents, False)
     weights = [float(em.n_cells * rays) for em in emitters]
@@ -490,11 +490,11 @@ def _shared_ray_solve(meshes, matrix_params: MatrixParams, sky_params: SkyParams
     schedule = _resolve_device(mp["device"])
     use_bvh = _select_bvh(mp["bvh"], solver.total_faces)
     n_surf = len(meshes)
-    emitters = solver.get_emitters(samples=mp["samples"], rays=mp["rays"], flip_faces=False)
     centers, extents = solver.get_mesh_bounds()
     ctx = _context()
     d_scene = solver.get_device_scene(use_bvh=use_bvh, ctx=ctx)
     d_em = solver.get_device_emitters(samples=mp["samples"], rays=mp["rays"], flip_faces=False, ctx=ctx)
+    emitters = solver.get_emitter_summaries(samples=mp["samples"], rays=mp["rays"], flip_faces=False, ctx=ctx)
     active = _cached_masks(solver, emitters, centers, extents, False)
     ids = np.arange(n_surf, dtype=np.int32)
     min_sid = (ids + 1) if mp["reciprocity"] else np.zeros(n_surf, np.int32)

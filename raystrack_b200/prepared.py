@@ -9,6 +9,7 @@ NumPy that yields the same float32 arrays; the BVH and the Halton tables are bui
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -226,6 +227,84 @@ def prepare_emitters(meshes: List[Mesh], *, samples: int, rays: int, flip_faces:
     return out
 
 
+@dataclass(frozen=True)
+class EmitterSummary:
+    """What the solve drivers need to know about an emitter besides its device records: the fields of
+    ``PreparedEmitter`` that are per mesh, not per triangle."""
+    plane_origin: np.ndarray
+    plane_normal: np.ndarray
+    plane_tol: float
+    plane_is_planar: bool
+    total_area: float
+    g: int
+    rays: int = 0
+
+    @property
+    def n_cells(self) -> int:
+        return int(self.g) * int(self.g)
+
+
+def flatten_meshes(meshes: List[Mesh]):
+    """All meshes back to back: (verts float32[nv,3], vert_offset int64[n+1], faces int32[nt,3], tri_offset int64[n+1])
+    -- the input of the device-side preparation (csrc/rsk_prepare.cu)."""
+    n = len(meshes)
+    vo = np.zeros(n + 1, np.int64)
+    to = np.zeros(n + 1, np.int64)
+    if n == 0:
+        return np.empty((0, 3), np.float32), vo, np.empty((0, 3), np.int32), to
+    np.cumsum([np.shape(V)[0] for _, V, _ in meshes], out=vo[1:])
+    np.cumsum([np.shape(F)[0] for _, _, F in meshes], out=to[1:])
+    verts = np.concatenate([np.asarray(V, dtype=np.float32).reshape(-1, 3) for _, V, _ in meshes], axis=0)
+    faces64 = np.concatenate([np.asarray(F).reshape(-1, 3) for _, _, F in meshes], axis=0)
+    if faces64.size and (faces64.max() > 0x7fffffff or faces64.min() < -0x80000000):
+        raise IndexError("face index does not fit in int32")
+    return np.ascontiguousarray(verts), vo, np.ascontiguousarray(faces64.astype(np.int32, copy=False)), to
+
+
+def summaries_from_emitters(emitters: List[PreparedEmitter]) -> List[EmitterSummary]:
+    return [EmitterSummary(e.plane_origin, e.plane_normal, e.plane_tol, e.plane_is_planar, e.total_area, e.g, e.rays) for e in emitters]
+
+
+def device_plane_verdict(row, tol: float) -> Optional[bool]:
+    """Planarity of a mesh from the device's float64 statistics, or None when they lie within the rounding distance
+    of a threshold of ``_emitter_plane`` (float32 BLAS products there: ~4e-7 relative to the size of the terms)."""
+    lo = 1.0 - 1.0e-4
+    band = 1.0e-6 * float(row["worst_mag"])
+    if row["min_dot"] < lo - 2.0e-6 or row["worst"] - band > tol:
+        return False
+    if row["min_dot"] >= lo + 2.0e-6 and row["worst"] + band <= tol:
+        return True
+    return None
+
+
+def summaries_from_device(summary: np.ndarray, g: np.ndarray, meshes: List[Mesh], *, samples: int, rays: int,
+                          flip_faces: bool) -> List[EmitterSummary]:
+    """Finish the planarity record of ``_emitter_plane`` (reference prepared.py:133-167) from the float64 statistics
+    the device returns.  The reference decides with float32 BLAS products; a mesh whose statistics lie within the
+    rounding distance of a threshold is prepared once more on the host with the reference arithmetic, so the flag is
+    the reference's in every case."""
+    out: List[EmitterSummary] = []
+    for i, row in enumerate(summary):
+        nt = int(np.shape(meshes[i][2])[0])
+        tol = float(max(1.0e-7, float(row["eps_max"])))
+        origin = np.array(row["origin"], np.float32)
+        normal = np.array(row["normal0"], np.float32)
+        planar: Optional[bool] = False
+        if nt == 0:
+            origin = np.zeros(3, np.float32)
+            normal = np.zeros(3, np.float32)
+        else:
+            nl = float(np.linalg.norm(normal))
+            if nl > 1.0e-12:
+                normal = (normal / nl).astype(np.float32, copy=False)
+                planar = device_plane_verdict(row, tol)
+        if planar is None:
+            ref = prepare_emitters([meshes[i]], samples=samples, rays=rays, flip_faces=flip_faces)[0]
+            planar = ref.plane_is_planar
+        out.append(EmitterSummary(origin, normal, tol, bool(planar), float(row["total_area"]), int(g[i]), int(rays)))
+    return out
+
+
 @dataclass
 class PreparedDeviceScene:
     """Device-resident scene: triangles + wide BVH owned by librsk_b200 (reference prepared.py:58-71)."""
@@ -258,6 +337,9 @@ class PreparedSolver:
         self._device_emitter_cache: Dict[Tuple[int, int, int, bool], PreparedDeviceEmitters] = {}
         self._mesh_bounds_cache: Optional[Tuple[np.ndarray, np.ndarray]] = None
         self._emitter_pack_cache: Dict[Tuple[int, int, bool], tuple] = {}
+        self._summary_cache: Dict[Tuple[int, int, bool], List[EmitterSummary]] = {}
+        self._flat_cache: Optional[tuple] = None                       # flatten_meshes(self.meshes)
+        self._geometry_cache: Dict[int, Any] = {}                      # device -> _native.DeviceGeometry
         self._derived_cache: Dict[Any, Any] = {}      # host-side results derived from the prepared state (surface masks)
 
     def get_scene(self, *, use_bvh: bool) -> PreparedScene:
@@ -281,43 +363,101 @@ class PreparedSolver:
             n = len(self.meshes)
             centers = np.zeros((n, 3), np.float32)
             extents = np.zeros((n, 3), np.float32)
-            for i, (_, V, _) in enumerate(self.meshes):
-                if V.size == 0:
-                    continue
-                v = np.asarray(V, dtype=np.float32)
-                lo, hi = np.min(v, axis=0), np.max(v, axis=0)
-                centers[i] = 0.5 * (lo + hi)
-                extents[i] = 0.5 * (hi - lo)
+            verts, vo, _, _ = self._flat()
+            if n and np.all(vo[1:] > vo[:-1]):              # every mesh has vertices: one segmented min/max
+                lo = np.minimum.reduceat(verts, vo[:-1], axis=0)
+                hi = np.maximum.reduceat(verts, vo[:-1], axis=0)
+                centers[:] = 0.5 * (lo + hi)
+                extents[:] = 0.5 * (hi - lo)
+            else:
+                for i in range(n):
+                    v = verts[vo[i]:vo[i + 1]]
+                    if v.size == 0:
+                        continue
+                    lo, hi = np.min(v, axis=0), np.max(v, axis=0)
+                    centers[i] = 0.5 * (lo + hi)
+                    extents[i] = 0.5 * (hi - lo)
             self._mesh_bounds_cache = (centers, extents)
         return self._mesh_bounds_cache
+
+    def _flat(self) -> tuple:
+        if self._flat_cache is None:
+            self._flat_cache = flatten_meshes(self.meshes)
+        return self._flat_cache
+
+    def _geometry(self, ctx: _native.Context):
+        got = self._geometry_cache.get(ctx.device)
+        if got is None:
+            verts, vo, faces, to = self._flat()
+            try:
+                got = _native.DeviceGeometry(ctx, verts, vo, faces, to)
+            except _native.NativeError as exc:
+                raise ValueError(str(exc)) from exc
+            self._geometry_cache[ctx.device] = got
+        return got
+
+    @staticmethod
+    def _host_prepare_forced() -> bool:
+        """RSK_HOST_PREPARE=1: prepare on the host with NumPy and upload the prepared arrays (A/B checks)."""
+        return os.environ.get("RSK_HOST_PREPARE", "") not in ("", "0")
 
     def clear_device_cache(self) -> None:
         for s in self._device_scene_cache.values():
             s.native.close()
         for e in self._device_emitter_cache.values():
             e.native.close()
+        for g in self._geometry_cache.values():
+            g.close()
         self._device_scene_cache.clear()
         self._device_emitter_cache.clear()
+        self._geometry_cache.clear()
 
     def get_device_scene(self, *, use_bvh: bool, ctx: Optional[_native.Context] = None) -> PreparedDeviceScene:
+        """Device scene.  Built on the GPU from the raw meshes (csrc/rsk_prepare.cu) unless the host arrays of
+        ``get_scene`` already exist, in which case those are uploaded; both give the same device records."""
         ctx = ctx or _native.Context.for_device()
         key = (ctx.device, bool(use_bvh))
         got = self._device_scene_cache.get(key)
         if got is None:
-            hs = self.get_scene(use_bvh=use_bvh)
-            nat = _native.DeviceScene(ctx, hs.v0, hs.e1, hs.e2, hs.normals, hs.sid, len(self.meshes), hs.use_bvh)
+            hs = self._scene_cache.get(bool(use_bvh)) or self._scene_cache.get(not use_bvh)
+            if hs is None and self._host_prepare_forced():
+                hs = self.get_scene(use_bvh=use_bvh)
+            if hs is not None:
+                nat = _native.DeviceScene(ctx, hs.v0, hs.e1, hs.e2, hs.normals, hs.sid, len(self.meshes), bool(use_bvh and hs.v0.shape[0] > 0))
+            else:
+                nat = self._from_geometry(lambda: _native.DeviceScene.from_geometry(self._geometry(ctx), bool(use_bvh)))
             got = PreparedDeviceScene(nat, nat.use_bvh)
             self._device_scene_cache[key] = got
         return got
 
+    @staticmethod
+    def _from_geometry(make):
+        try:
+            return make()
+        except _native.NativeError as exc:
+            if "face indices" in str(exc):            # what NumPy's V[F] raises in the reference (prepared.py:182-188)
+                raise IndexError(str(exc)) from exc
+            raise
+
     def get_device_emitters(self, *, samples: int, rays: int, flip_faces: bool,
                             ctx: Optional[_native.Context] = None) -> PreparedDeviceEmitters:
+        """Device emitter set of one (samples, rays, flip_faces) key; GPU-prepared unless ``get_emitters`` has
+        already produced the host arrays for the key."""
         ctx = ctx or _native.Context.for_device()
         key = (ctx.device, int(samples), int(rays), bool(flip_faces))
         got = self._device_emitter_cache.get(key)
         if got is None:
-            ems = self.get_emitters(samples=samples, rays=rays, flip_faces=flip_faces)
             hkey = (int(samples), int(rays), bool(flip_faces))
+            if hkey not in self._emitter_cache and not self._host_prepare_forced():
+                nat, summary = self._from_geometry(
+                    lambda: _native.DeviceEmitters.from_geometry(self._geometry(ctx), samples, int(rays), bool(flip_faces)))
+                if hkey not in self._summary_cache:
+                    self._summary_cache[hkey] = summaries_from_device(summary, nat.g, self.meshes, samples=samples,
+                                                                       rays=int(rays), flip_faces=bool(flip_faces))
+                got = PreparedDeviceEmitters(nat, nat.g.astype(np.int64) ** 2 * int(rays))
+                self._device_emitter_cache[key] = got
+                return got
+            ems = self.get_emitters(samples=samples, rays=rays, flip_faces=flip_faces)
             pack = self._emitter_pack_cache.get(hkey)
             if pack is None:                      # concatenated host arrays: host preparation, kept across device resets
                 counts = np.asarray([e.tri_a.shape[0] for e in ems], np.int64)
@@ -337,10 +477,25 @@ class PreparedSolver:
             self._device_emitter_cache[key] = got
         return got
 
+    def get_emitter_summaries(self, *, samples: int, rays: int, flip_faces: bool,
+                              ctx: Optional[_native.Context] = None) -> List[EmitterSummary]:
+        """Per-mesh emitter facts (plane record, area, grid side) without the per-triangle host arrays: taken from
+        ``get_emitters`` when that has run for the key, otherwise a by-product of the device-side preparation."""
+        hkey = (int(samples), int(rays), bool(flip_faces))
+        got = self._summary_cache.get(hkey)
+        if got is None:
+            if hkey in self._emitter_cache or self._host_prepare_forced():
+                got = summaries_from_emitters(self.get_emitters(samples=samples, rays=rays, flip_faces=flip_faces))
+                self._summary_cache[hkey] = got
+            else:
+                self.get_device_emitters(samples=samples, rays=rays, flip_faces=flip_faces, ctx=ctx)
+                got = self._summary_cache[hkey]
+        return got
+
     def get_device_emitter(self, index: int, *, samples: int, rays: int, flip_faces: bool) -> PreparedDeviceEmitters:
         """Reference signature (prepared.py:405-431); all emitters of a key share one device object."""
         return self.get_device_emitters(samples=samples, rays=rays, flip_faces=flip_faces)
 
 
-__all__ = ["PreparedScene", "PreparedEmitter", "PreparedDeviceScene", "PreparedDeviceEmitters", "PreparedSolver",
+__all__ = ["EmitterSummary", "PreparedScene", "PreparedEmitter", "PreparedDeviceScene", "PreparedDeviceEmitters", "PreparedSolver",
            "prepare_scene", "prepare_emitters", "grid_from_density"]
