@@ -72,18 +72,24 @@ __device__ __forceinline__ void rsk_walk_begin(Walk &w, const Ray &r) {
     w.sp = 0;
 }
 
-// Byte j of `word` as a float without the (slow) integer->float conversion pipe: PRMT builds the bit pattern of
-// 2^23 + byte, one full-rate FADD removes the bias (exact).
-// How the quantised plane bytes become ray parameters.
-//   RSK_BYTE_MODE 0: t = float(byte) * (cell * 1/d) + (origin - o) * 1/d           -- one I2F (XU pipe) + one FFMA per plane
-//   RSK_BYTE_MODE 3: one PRMT drops the byte into mantissa bits 8..15 of the float 2.0, i.e. f = 2 + byte * 2^-14 exactly;
-//                    t = f * A + B with A = cell * 2^14 / d and B = (origin - o)/d - 2A            -- PRMT (ALU) + FFMA, no XU.
-//                    B carries a rounding error of <= 2^-9 cell, so the near/far biases are moved outwards by 2^-8 cell.
-// Measured equal within 1.5 % on B200 (profiles/kernel_variants_r1.md); mode 0 ships because it needs no error margin.
-#ifndef RSK_BYTE_MODE
-#define RSK_BYTE_MODE 0
+// How the quantised plane bytes become ray parameters, chosen per axis by the bits of RSK_PRMT_AXES:
+//   bit clear: t = float(byte) * (cell * 1/d) + (origin - o) * 1/d           -- one I2F (XU pipe) + one FFMA per plane
+//   bit set:   one PRMT drops the byte into mantissa bits 8..15 of the float 2.0, i.e. f = 2 + byte * 2^-14 exactly;
+//              t = f * A + B with A = cell * 2^14 / d and B = (origin - o)/d - 2A            -- PRMT (ALU) + FFMA, no XU.
+//              B carries a rounding error of <= 2^-9 cell, so the near/far biases are moved outwards by 2^-8 cell.
+// All 48 conversions through I2F keep the XU pipe 67 % busy, all through PRMT load the ALU pipe instead (same speed);
+// one axis through PRMT balances the two pipes: +1.4 % rays/s, identical tallies (profiles/kernel_variants_r1.md).
+#ifndef RSK_PRMT_AXES
+#if defined(RSK_BYTE_MODE) && RSK_BYTE_MODE == 3
+#define RSK_PRMT_AXES 7
+#else
+#define RSK_PRMT_AXES 4       // z planes through PRMT, x and y through I2F
+#endif
 #endif
 
+#ifndef RSK_MASK_PIN
+#define RSK_MASK_PIN 2      // 2: hit-mask bytes extracted with PRMT from two pinned words (-14 instructions per node test)
+#endif
 #ifndef RSK_SUBTREE_SKIP
 #define RSK_SUBTREE_SKIP 2      // 0 = off, 2 = range word loaded together with the node (shipped)
 #endif
@@ -112,25 +118,26 @@ __device__ __forceinline__ void rsk_test_node(const uint4 *__restrict__ nodes, u
     }
 #endif
     const uint32_t imask = n0.w >> 24;
-#if RSK_BYTE_MODE == 3
-    const float ax = __uint_as_float(((n0.w & 0xffu) + 14u) << 23) * w.ix;          // cell * 2^14 / d
-    const float ay = __uint_as_float((((n0.w >> 8) & 0xffu) + 14u) << 23) * w.iy;
-    const float az = __uint_as_float((((n0.w >> 16) & 0xffu) + 14u) << 23) * w.iz;
-    const float cx = fmaf(-2.0f, ax, (__uint_as_float(n0.x) - w.ox) * w.ix);
-    const float cy = fmaf(-2.0f, ay, (__uint_as_float(n0.y) - w.oy) * w.iy);
-    const float cz = fmaf(-2.0f, az, (__uint_as_float(n0.z) - w.oz) * w.iz);
-    const float ex = fabsf(ax) * 0x1p-22f, ey = fabsf(ay) * 0x1p-22f, ez = fabsf(az) * 0x1p-22f;   // 2^-8 cell in t
-    const float bnx = cx - ex, bfx = cx + ex, bny = cy - ey, bfy = cy + ey, bnz = cz - ez, bfz = cz + ez;
-#define RSK_PLANE(word, j) __uint_as_float(__byte_perm(word, 0x40000000u, 0x7404u | ((unsigned)(j) << 4)))
-#else
-    const float ax = __uint_as_float((n0.w & 0xffu) << 23) * w.ix;
-    const float ay = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * w.iy;
-    const float az = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * w.iz;
-    const float bnx = (__uint_as_float(n0.x) - w.ox) * w.ix, bfx = bnx;
-    const float bny = (__uint_as_float(n0.y) - w.oy) * w.iy, bfy = bny;
-    const float bnz = (__uint_as_float(n0.z) - w.oz) * w.iz, bfz = bnz;
-#define RSK_PLANE(word, j) ((float)(((word) >> (8 * (j))) & 0xffu))
-#endif
+    // Per axis (bit a of RSK_PRMT_AXES): planes through I2F (t = float(byte) * A + B) or dropped into the mantissa of
+    // 2.0 with PRMT (f = 2 + byte * 2^-14; t = f * A' + B', near/far biases moved outwards by 2^-8 cell for B's rounding).
+#define RSK_AXIS_SETUP(AXIS, shift, org, o, inv, A, BN, BF)                                                   \
+    float A, BN, BF;                                                                                           \
+    if ((RSK_PRMT_AXES >> AXIS) & 1) {                                                                         \
+        A = __uint_as_float((((n0.w >> shift) & 0xffu) + 14u) << 23) * inv;                                    \
+        const float c = fmaf(-2.0f, A, (__uint_as_float(org) - o) * inv);                                      \
+        const float e = fabsf(A) * 0x1p-22f;                                                                   \
+        BN = c - e; BF = c + e;                                                                                \
+    } else {                                                                                                   \
+        A = __uint_as_float(((n0.w >> shift) & 0xffu) << 23) * inv;                                            \
+        BN = (__uint_as_float(org) - o) * inv; BF = BN;                                                        \
+    }
+    RSK_AXIS_SETUP(0, 0, n0.x, w.ox, w.ix, ax, bnx, bfx)
+    RSK_AXIS_SETUP(1, 8, n0.y, w.oy, w.iy, ay, bny, bfy)
+    RSK_AXIS_SETUP(2, 16, n0.z, w.oz, w.iz, az, bnz, bfz)
+#undef RSK_AXIS_SETUP
+#define RSK_PLANE_I2F(word, j) ((float)(((word) >> (8 * (j))) & 0xffu))
+#define RSK_PLANE_PRMT(word, j) __uint_as_float(__byte_perm(word, 0x40000000u, 0x7404u | ((unsigned)(j) << 4)))
+#define RSK_PLANE(AXIS, word, j) (((RSK_PRMT_AXES >> AXIS) & 1) ? RSK_PLANE_PRMT(word, j) : RSK_PLANE_I2F(word, j))
     // byte planes: n2 = qlo.x[0..7] qlo.y[0..7]; n3 = qlo.z[0..7] qhi.x[0..7]; n4 = qhi.y[0..7] qhi.z[0..7]
     const bool px = w.octinv & 1u, py = w.octinv & 2u, pz = w.octinv & 4u;
     uint32_t hits = 0;
@@ -145,19 +152,29 @@ __device__ __forceinline__ void rsk_test_node(const uint4 *__restrict__ nodes, u
         // four meta bytes at once: inner children (meta = 0b001_11sss) get their slot XOR-ed with the octant
         // permutation, leaf children keep their first-triangle bit; empty slots have no bits to contribute
         const uint32_t inner4 = (((meta & (meta << 1)) & 0x10101010u) >> 4) * 0xffu;
-        const uint32_t index4 = (meta ^ (w.octinv4 & inner4)) & 0x1f1f1f1fu;
-        const uint32_t bits4 = (meta >> 5) & 0x07070707u;
+        uint32_t index4 = (meta ^ (w.octinv4 & inner4)) & 0x1f1f1f1fu;
+        uint32_t bits4 = (meta >> 5) & 0x07070707u;
+#if RSK_MASK_PIN
+        asm volatile("" : "+r"(index4), "+r"(bits4));       // keep the two words: ptxas otherwise re-derives them per child
+#endif
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float tnx = fmaf(RSK_PLANE(nxw, j), ax, bnx), tfx = fmaf(RSK_PLANE(fxw, j), ax, bfx);
-            const float tny = fmaf(RSK_PLANE(nyw, j), ay, bny), tfy = fmaf(RSK_PLANE(fyw, j), ay, bfy);
-            const float tnz = fmaf(RSK_PLANE(nzw, j), az, bnz), tfz = fmaf(RSK_PLANE(fzw, j), az, bfz);
+            const float tnx = fmaf(RSK_PLANE(0, nxw, j), ax, bnx), tfx = fmaf(RSK_PLANE(0, fxw, j), ax, bfx);
+            const float tny = fmaf(RSK_PLANE(1, nyw, j), ay, bny), tfy = fmaf(RSK_PLANE(1, fyw, j), ay, bfy);
+            const float tnz = fmaf(RSK_PLANE(2, nzw, j), az, bnz), tfz = fmaf(RSK_PLANE(2, fzw, j), az, bfz);
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+#if RSK_MASK_PIN >= 2
+            const uint32_t contrib = __byte_perm(bits4, 0u, 0x4440u | j) << __byte_perm(index4, 0u, 0x4440u | j);
+            hits |= (tn <= tf) ? contrib : 0u;
+#else
             if (tn <= tf) hits |= ((bits4 >> (8 * j)) & 0xffu) << ((index4 >> (8 * j)) & 0xffu);
+#endif
         }
     }
 #undef RSK_PLANE
+#undef RSK_PLANE_I2F
+#undef RSK_PLANE_PRMT
     ng = make_uint2(n1.x, (hits & 0xff000000u) | imask);
     tg = make_uint2(n1.y, hits & 0x00ffffffu);
 }

@@ -15,13 +15,16 @@ VARIANTS = {      # compile-time knobs of csrc/rsk_trace.cu(h) and csrc/rsk_bvh.
     "warp_slices": ("RSK_CTA_POOL=0",),
     "per_lane_raygen": ("RSK_RAY_BUFFER=0", "RSK_REFILL_BELOW=20"),
     "no_subtree_skip": ("RSK_SUBTREE_SKIP=0",),
-    "byte_prmt_mantissa": ("RSK_BYTE_MODE=3",),
+    "byte_prmt_mantissa": ("RSK_PRMT_AXES=7",),
     "morton_per_axis": ("RSK_MORTON_UNIFORM=0",),
     "ploc_r16": ("RSK_PLOC=1", "RSK_PLOC_RADIUS=16"),
     "bottom16": ("RSK_BOTTOM_MAX=16",),
     "regs80": ("RSK_MIN_CTAS_PER_SM=3",),
     "fanout4": ("RSK_FANOUT=4",),
     "tris_at_once": ("RSK_POSTPONE=0",),
+    "all_i2f_mask_shifts": ("RSK_PRMT_AXES=0", "RSK_MASK_PIN=0"),
+    "prmt_x": ("RSK_PRMT_AXES=1",),
+    "prmt_yz": ("RSK_PRMT_AXES=6",),
     "p6i3": ("RSK_POSTPONE=6", "RSK_POSTPONE_IDLE=3"),
     "p32i6": ("RSK_POSTPONE=32", "RSK_POSTPONE_IDLE=6"),
 }
