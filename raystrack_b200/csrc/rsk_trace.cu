@@ -245,6 +245,9 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
                 rsk_walk_begin(w, r);
                 active = true;
                 any_hit = false;
+#if RSK_POSTPONE
+                ptg.y = 0u;
+#endif
             }
             next += __popc(need);
         }
