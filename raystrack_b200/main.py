@@ -144,14 +144,16 @@ def _rotation_rows(seed: int, rows: int) -> np.ndarray:
 TILE_RAYS = 4096               # rays per CTA tile (csrc/rsk_common.cuh RSK_TILE_RAYS): slices are cut on tile boundaries
 
 
-def plan_shards(todo: Sequence[int], n_rays_once: Sequence[int], world: int) -> List[List[Tuple[int, int, int, bool]]]:
+def plan_shards(todo: Sequence[int], n_rays_once: Sequence[int], world: int,
+                allow_split: bool = True) -> List[List[Tuple[int, int, int, bool]]]:
     """Partition the (emitter, ray range) work of one iteration over ``world`` GPUs.
 
     Returns, per rank, a list of jobs ``(emitter, ray_begin, ray_end, shared)``.  Emitters are independent units
     (reference main.py:1758-1939) and are assigned whole, longest first, to the least loaded rank; an emitter that
     alone exceeds an eighth of a rank's fair share is cut into ``world`` tile-aligned ray slices instead (``shared``):
     its per-iteration tallies are summed across ranks before the statistics update, so every rank takes the same
-    convergence decision for it.  Shared jobs come first in every rank's list, in the same order."""
+    convergence decision for it.  Shared jobs come first in every rank's list, in the same order.
+    ``allow_split=False`` assigns every emitter whole (no per-iteration exchange at all)."""
     world = max(1, int(world))
     plans: List[List[Tuple[int, int, int, bool]]] = [[] for _ in range(world)]
     if world == 1:
@@ -159,7 +161,7 @@ def plan_shards(todo: Sequence[int], n_rays_once: Sequence[int], world: int) -> 
         return plans
     total = float(sum(int(n_rays_once[i]) for i in todo))
     limit = total / (8.0 * world)
-    shared = [int(i) for i in todo if n_rays_once[i] > limit and n_rays_once[i] >= 2 * world * TILE_RAYS]
+    shared = [int(i) for i in todo if allow_split and n_rays_once[i] > limit and n_rays_once[i] >= 2 * world * TILE_RAYS]
     whole = [int(i) for i in todo if int(i) not in set(shared)]
     loads = [0.0] * world
     for i in shared:
@@ -504,22 +506,35 @@ def _shared_ray_solve(meshes, matrix_params: MatrixParams, sky_params: SkyParams
         return dict(max_iters=p["max_iters"], min_iters=p["min_iters"], tol=p["tol"], tol_mode=p["tol_mode"],
                     interval=max(1, int(p["convergence_interval"])) if schedule == "gpu" else 1)
 
-    solve = _native.DualSolve(ctx, d_scene.native, d_em.native, ids, active, table, ids.copy(), ids, min_sid,
-                              side(mp), side(sp), bool(sp["discrete"]))
-    try:
-        limit = max(int(mp["max_iters"]), int(sp["max_iters"]))
-        first = max(1, min(limit, max(1, min(int(mp["min_iters"]), int(sp["min_iters"])))))
-        running = solve.step(first) if limit > 0 else 0
-        done = first
-        while running > 0 and done < limit:
-            chunk = min(4, limit - done)
-            running = solve.step(chunk)
-            done += chunk
-        m_t, m_i, m_r = solve.matrix_part.read_block()
-        s_t, s_i, s_r = solve.sky_part.read_block()
-    finally:
-        solve.close()
-    return (m_t, m_i.astype(np.int64), m_r), (s_t, s_i.astype(np.int64), s_r)
+    # Emitters are independent: under torch.distributed every rank solves whole emitters (no ray slices, hence no
+    # per-iteration exchange) and the integer results are summed once at the end.
+    rank, world = _dist_env()
+    n_once = [int(em.n_cells * int(mp["rays"])) for em in emitters]
+    mine = np.asarray([j[0] for j in plan_shards(list(range(n_surf)), n_once, world, allow_split=False)[rank]], np.int32)
+    n_sky = 145 if sp["discrete"] else 1
+    out_m = (np.zeros((n_surf, 2 * n_surf), np.int64), np.zeros(n_surf, np.int64), np.zeros(n_surf, np.int64))
+    out_s = (np.zeros((n_surf, n_sky), np.int64), np.zeros(n_surf, np.int64), np.zeros(n_surf, np.int64))
+    if mine.size:
+        solve = _native.DualSolve(ctx, d_scene.native, d_em.native, mine, active[mine], table, mine.copy(), ids[mine], min_sid[mine],
+                                  side(mp), side(sp), bool(sp["discrete"]))
+        try:
+            limit = max(int(mp["max_iters"]), int(sp["max_iters"]))
+            first = max(1, min(limit, max(1, min(int(mp["min_iters"]), int(sp["min_iters"])))))
+            running = solve.step(first) if limit > 0 else 0
+            done = first
+            while running > 0 and done < limit:
+                chunk = min(4, limit - done)
+                running = solve.step(chunk)
+                done += chunk
+            for part, out in ((solve.matrix_part, out_m), (solve.sky_part, out_s)):
+                t, i, r = part.read_block()
+                out[0][mine], out[1][mine], out[2][mine] = t, i.astype(np.int64), r
+        finally:
+            solve.close()
+    if world > 1:
+        from .dist import allreduce_sum_
+        allreduce_sum_([*out_m, *out_s], device=ctx.device)
+    return out_m, out_s
 
 
 def view_factor_matrix_and_sky(meshes: List[Mesh], *, matrix_params: MatrixParams, sky_params: SkyParams,
@@ -527,9 +542,9 @@ def view_factor_matrix_and_sky(meshes: List[Mesh], *, matrix_params: MatrixParam
     """Scene view factors and sky view factors from the same per-iteration ray samples (reference
     main.py:1209-1686).  Both sides converge independently and use, per emitter and iteration, exactly the rays the
     separate solves would use, so the results equal ``view_factor_matrix`` + ``view_factor_to_tregenza_sky``
-    (the reference documents the same equivalence, main.py:1231-1234).  On one GPU every ray is traced ONCE by the
-    dual kernel (closest receiver hit + any-hit flag); under torch.distributed the two sharded solves run one after
-    the other on the shared scene, BVH and emitter tables.
+    (the reference documents the same equivalence, main.py:1231-1234).  Every ray is traced ONCE by the dual kernel
+    (closest receiver hit + any-hit flag); under torch.distributed each rank does so for its share of the emitters
+    and the integer tallies are summed once at the end.
     ``enforce_reciprocity_rowsum`` is not applied here (main.py never does in this function)."""
     if not isinstance(matrix_params, MatrixParams):
         raise TypeError("matrix_params must be a MatrixParams instance")
@@ -540,7 +555,7 @@ def view_factor_matrix_and_sky(meshes: List[Mesh], *, matrix_params: MatrixParam
     solver = _ensure_prepared(meshes, prepared)
     mh: dict = {}
     sh: dict = {}
-    if _dist_env()[1] == 1 and len(meshes) > 0:
+    if len(meshes) > 0:
         mh["precomputed"], sh["precomputed"] = _shared_ray_solve(meshes, matrix_params, sky_params, solver)
     vf_scene = view_factor_matrix(meshes, matrix_params, prepared=solver, _hook=mh)
     sky_vf = view_factor_to_tregenza_sky(meshes, sky_params, prepared=solver, _hook=sh)

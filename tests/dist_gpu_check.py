@@ -52,6 +52,14 @@ def main():
     gathered = [None] * world
     torch.distributed.all_gather_object(gathered, blob)
     assert all(b == gathered[0] for b in gathered), "ranks disagree"
+    # shared-ray workflow: each rank traces its emitters once with the dual kernel; must equal the two separate solves
+    mp_ = rb.MatrixParams(samples=4, rays=32, seed=2, bvh="builtin", reciprocity=True, max_iters=12, min_iters=3, tol=5e-4)
+    sp_ = rb.SkyParams(samples=4, rays=32, seed=2, bvh="builtin", max_iters=8, min_iters=3, tol=1e-3, discrete=True)
+    assert M.outside_workflow_shareable(mp_, sp_)
+    both = M.view_factor_matrix_and_sky(meshes, matrix_params=mp_, sky_params=sp_)
+    assert both[0] == rb.view_factor_matrix(meshes, mp_), "dual solve (matrix side) differs from the separate solve"
+    assert both[1] == rb.view_factor_to_tregenza_sky(meshes, sp_), "dual solve (sky side) differs from the separate solve"
+    print(f"[rank {rank}/{world}] shared-ray workflow == separate solves", flush=True)
     if rank == 0:
         # single-GPU run of the same solve inside this process group is not possible; compare with a saved file if present
         ref_file = ROOT / "gpurun_out" / "dist_ref_single.json"

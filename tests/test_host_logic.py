@@ -98,6 +98,16 @@ def test_plan_shards_covers_every_ray_once(world):
     assert max(loads) <= 1.05 * (sum(loads) / world) + 250000
 
 
+@pytest.mark.parametrize("world", [1, 2, 5])
+def test_plan_shards_without_splitting_assigns_whole_emitters(world):
+    """The shared-ray (dual) solve shards whole emitters only: every emitter on exactly one rank, full ray range."""
+    n_once = [4096 * k for k in (3, 1, 40, 7, 7, 2, 900, 5)]
+    plans = M.plan_shards(list(range(len(n_once))), n_once, world, allow_split=False)
+    jobs = [j for plan in plans for j in plan]
+    assert sorted(j[0] for j in jobs) == list(range(len(n_once)))
+    assert all(b == 0 and e == n_once[i] and not shared for i, b, e, shared in jobs)
+
+
 def test_select_bvh_and_errors():
     assert M._select_bvh("auto", 511) is False and M._select_bvh("auto", 512) is True
     assert M._select_bvh("builtin", 1) is True and M._select_bvh("off", 10 ** 6) is False and M._select_bvh(None, 600) is True
