@@ -18,7 +18,10 @@ VARIANTS = {      # compile-time knobs of csrc/rsk_trace.cu(h) and csrc/rsk_bvh.
     "byte_prmt_mantissa": ("RSK_PRMT_AXES=7",),
     "morton_per_axis": ("RSK_MORTON_UNIFORM=0",),
     "ploc_r16": ("RSK_PLOC=1", "RSK_PLOC_RADIUS=16"),
+    "bottom8": ("RSK_BOTTOM_MAX=8",),
+    "bottom12": ("RSK_BOTTOM_MAX=12",),
     "bottom16": ("RSK_BOTTOM_MAX=16",),
+    "bottom24": ("RSK_BOTTOM_MAX=24",),
     "regs80": ("RSK_MIN_CTAS_PER_SM=3",),
     "fanout4": ("RSK_FANOUT=4",),
     "tris_at_once": ("RSK_POSTPONE=0",),
