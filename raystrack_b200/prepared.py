@@ -283,25 +283,33 @@ def summaries_from_device(summary: np.ndarray, g: np.ndarray, meshes: List[Mesh]
     the device returns.  The reference decides with float32 BLAS products; a mesh whose statistics lie within the
     rounding distance of a threshold is prepared once more on the host with the reference arithmetic, so the flag is
     the reference's in every case."""
+    n = int(summary.shape[0])
+    n0 = np.ascontiguousarray(summary["normal0"], np.float32).reshape(n, 3)
+    origin = np.ascontiguousarray(summary["origin"], np.float32).reshape(n, 3).copy()
+    tol = np.maximum(1.0e-7, summary["eps_max"].astype(np.float64))
+    empty = np.asarray([np.shape(F)[0] == 0 for _, _, F in meshes], bool) if n else np.zeros(0, bool)
+    # nl = float(np.linalg.norm(normal)): a BLAS dot in the reference.  With at most one non-zero component the result
+    # is |component| in any summation order (sqrt(fl(a*a)) == |a|); other normals go through the same NumPy call.
+    nl = np.abs(n0).max(axis=1).astype(np.float64) if n else np.zeros(0)
+    for i in np.nonzero(((n0 != 0).sum(axis=1) > 1) & ~empty)[0]:
+        nl[i] = float(np.linalg.norm(n0[i]))
+    unit = (nl > 1.0e-12) & ~empty
+    normal = n0.copy()
+    normal[unit] = n0[unit] / nl[unit].astype(np.float32)[:, None]
+    normal[empty] = 0.0
+    origin[empty] = 0.0
+    lo = 1.0 - 1.0e-4
+    band = 1.0e-6 * summary["worst_mag"]
+    no = (summary["min_dot"] < lo - 2.0e-6) | (summary["worst"] - band > tol)
+    yes = ~no & (summary["min_dot"] >= lo + 2.0e-6) & (summary["worst"] + band <= tol)
     out: List[EmitterSummary] = []
-    for i, row in enumerate(summary):
-        nt = int(np.shape(meshes[i][2])[0])
-        tol = float(max(1.0e-7, float(row["eps_max"])))
-        origin = np.array(row["origin"], np.float32)
-        normal = np.array(row["normal0"], np.float32)
-        planar: Optional[bool] = False
-        if nt == 0:
-            origin = np.zeros(3, np.float32)
-            normal = np.zeros(3, np.float32)
-        else:
-            nl = float(np.linalg.norm(normal))
-            if nl > 1.0e-12:
-                normal = (normal / nl).astype(np.float32, copy=False)
-                planar = device_plane_verdict(row, tol)
-        if planar is None:
-            ref = prepare_emitters([meshes[i]], samples=samples, rays=rays, flip_faces=flip_faces)[0]
-            planar = ref.plane_is_planar
-        out.append(EmitterSummary(origin, normal, tol, bool(planar), float(row["total_area"]), int(g[i]), int(rays)))
+    for i in range(n):
+        planar = False
+        if unit[i]:
+            planar = bool(yes[i])
+            if not yes[i] and not no[i]:          # within rounding distance of a threshold: the reference arithmetic decides
+                planar = prepare_emitters([meshes[i]], samples=samples, rays=rays, flip_faces=flip_faces)[0].plane_is_planar
+        out.append(EmitterSummary(origin[i], normal[i], float(tol[i]), bool(planar), float(summary["total_area"][i]), int(g[i]), int(rays)))
     return out
 
 
