@@ -395,6 +395,13 @@ class Solve:
         check(self.ctx.lib.rsk_solve_read_block(self.handle, ptr(tallies), ptr(iters), ptr(total)), "rsk_solve_read_block")
         return tallies, iters, total
 
+    def read_counters(self):
+        """(iterations int32 [n_local], total rays int64 [n_local]) without the tally block."""
+        iters = np.zeros(self.n_local, np.int32)
+        total = np.zeros(self.n_local, np.int64)
+        check(self.ctx.lib.rsk_solve_read_block(self.handle, None, ptr(iters), ptr(total)), "rsk_solve_read_block")
+        return iters, total
+
     def read_sky(self):
         nb = 145 if self.discrete else 1
         counts = np.zeros((self.n_local, nb), np.int64)

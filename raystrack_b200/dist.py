@@ -47,6 +47,57 @@ def allreduce_sum_(arrays: Sequence[np.ndarray], device: int = 0) -> None:
         pos += n
 
 
+def nccl_active() -> bool:
+    """True when a torch.distributed NCCL group with more than one rank is running."""
+    try:
+        import torch.distributed as dist
+        return bool(dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl")
+    except Exception:
+        return False
+
+
+class _DeviceBlock:
+    """A raw device allocation of the library presented through ``__cuda_array_interface__`` (int64, C order)."""
+
+    def __init__(self, pointer: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": "<i8", "data": (int(pointer), False),
+                                         "version": 3, "strides": None}
+
+
+class DeviceReducer:
+    """Sums the per-rank tally blocks on the GPUs: every rank scatters the rows of its solves into a zeroed
+    ``[n_rows, n_cols]`` int64 device tensor, one NCCL all-reduce adds them up over NVLink, and the result comes back
+    to the host in a single copy into pinned memory.  (Going through NumPy costs three more 64 MB pageable copies per
+    call at the bench scene.)  Needs the library context to share torch's current stream."""
+
+    def __init__(self, n_rows: int, n_cols: int, device: int):
+        import torch
+        self.torch = torch
+        self.device = torch.device("cuda", int(device))
+        self.full = torch.zeros((int(n_rows), int(n_cols)), dtype=torch.int64, device=self.device)
+
+    def add_rows(self, rows: np.ndarray, pointer: int, n_local: int, keep: np.ndarray) -> None:
+        """full[rows[keep]] = block[keep], block = the solve's int64 [n_local, n_cols] totals at ``pointer``."""
+        torch = self.torch
+        if n_local == 0 or not keep.any():
+            return
+        block = torch.as_tensor(_DeviceBlock(pointer, (n_local, self.full.shape[1])), device=self.device)
+        dst = torch.as_tensor(np.asarray(rows, np.int64)[keep], device=self.device)
+        if keep.all():
+            self.full.index_copy_(0, dst, block)
+        else:
+            self.full.index_copy_(0, dst, block[torch.as_tensor(np.nonzero(keep)[0], device=self.device)])
+
+    def finish(self) -> np.ndarray:
+        import torch.distributed as dist
+        torch = self.torch
+        dist.all_reduce(self.full, op=dist.ReduceOp.SUM)
+        host = torch.empty(self.full.shape, dtype=torch.int64, pin_memory=True)
+        host.copy_(self.full, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy()
+
+
 def barrier() -> None:
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():

@@ -10,6 +10,7 @@ reads "how many emitters are still running".
 from __future__ import annotations
 
 import functools
+from concurrent.futures import ThreadPoolExecutor
 import os
 import time
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -96,8 +97,9 @@ def _surface_masks(emitters: Sequence[PreparedEmitter], centers: np.ndarray, ext
     c = [np.ascontiguousarray(centers[:, k]) for k in range(3)]
     x = [np.ascontiguousarray(extents[:, k]) for k in range(3)]
     rows = np.nonzero(planar)[0]
-    for lo in range(0, rows.size, 256):                    # row blocks keep the temporaries cache-sized
-        r = rows[lo:lo + 256]
+
+    def block(lo: int) -> None:                             # row blocks keep the temporaries cache-sized
+        r = rows[lo:lo + 128]
         signed = (c[0][None, :] - po[r, 0:1]) * pn[r, 0:1]
         signed += (c[1][None, :] - po[r, 1:2]) * pn[r, 1:2]
         signed += (c[2][None, :] - po[r, 2:3]) * pn[r, 2:3]
@@ -106,6 +108,14 @@ def _surface_masks(emitters: Sequence[PreparedEmitter], centers: np.ndarray, ext
         radius += an[r, 2:3] * x[2][None, :]
         signed += radius
         active[r] = ~(signed <= tol[r, None])
+
+    starts = range(0, rows.size, 128)
+    if rows.size * n >= 1 << 20:                            # NumPy releases the GIL: a few threads share the blocks
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+            list(pool.map(block, starts))
+    else:
+        for lo in starts:
+            block(lo)
     idx = np.arange(min(ne, n))
     active[idx, idx] = 0
     return active
@@ -267,9 +277,15 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
         chunks.append(plan[lo:lo + max_jobs])
 
     single = world == 1 and len(chunks) == 1 and len(plan) == n_emit
+    # Under NCCL the tally blocks never visit the host before they are summed (dist.DeviceReducer).
+    reducer = None
+    if world > 1 and hasattr(_native.Solve, "device_tallies"):
+        from . import dist as D
+        if D.nccl_active():
+            reducer = D.DeviceReducer(n_emit, n_hist, ctx.device)
     tallies = iters = totals = None
     if not single:
-        tallies = np.zeros((n_emit, n_hist), np.int64)
+        tallies = None if reducer is not None else np.zeros((n_emit, n_hist), np.int64)
         iters = np.zeros(n_emit, np.int64)
         totals = np.zeros(n_emit, np.int64)
     for c, chunk in enumerate(chunks):
@@ -289,21 +305,32 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
                     _run_solve_shared(solve, sum(1 for j in chunk if j[3]), min_iters, max_iters, ctx.device)
                 else:
                     _run_solve(solve, min_iters, max_iters)
+            keep = np.asarray([not (j[3] and rank != 0) for j in chunk], bool)     # replicated (ray-split) jobs count once
             with _Phase("download"):
-                loc, it_loc, tot_loc = solve.read_block()
+                if reducer is not None:
+                    it_loc, tot_loc = solve.read_counters()
+                    reducer.add_rows(ids, solve.device_tallies()[0], len(chunk), keep)
+                    loc = None
+                else:
+                    loc, it_loc, tot_loc = solve.read_block()
         finally:
             with _Phase("solve_end"):
                 solve.close()
         if single:
             return loc, it_loc.astype(np.int64), tot_loc      # every emitter, in order: no scatter needed
-        keep = np.asarray([not (j[3] and rank != 0) for j in chunk], bool)     # replicated (ray-split) jobs count once
         if keep.any():
-            tallies[ids[keep]] = loc[keep]
+            if loc is not None:
+                tallies[ids[keep]] = loc[keep]
             iters[ids[keep]] = it_loc[keep]
             totals[ids[keep]] = tot_loc[keep]
     if world > 1:
         from .dist import allreduce_sum_
-        allreduce_sum_([tallies, iters, totals], device=ctx.device)
+        with _Phase("all_reduce"):
+            if reducer is not None:
+                tallies = reducer.finish()
+                allreduce_sum_([iters, totals], device=ctx.device)
+            else:
+                allreduce_sum_([tallies, iters, totals], device=ctx.device)
     return tallies, iters, totals
 
 
