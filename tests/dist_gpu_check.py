@@ -52,6 +52,10 @@ def main():
     gathered = [None] * world
     torch.distributed.all_gather_object(gathered, blob)
     assert all(b == gathered[0] for b in gathered), "ranks disagree"
+    # the same solve in memory-budgeted chunks (several solves per rank feed the device-side reduction)
+    os.environ["RSK_SOLVE_MEMORY_MB"] = "0.02"
+    assert json.dumps(rb.view_factor_matrix(meshes, prm), sort_keys=True, default=float) == blob, "chunked solve differs"
+    del os.environ["RSK_SOLVE_MEMORY_MB"]
     # shared-ray workflow: each rank traces its emitters once with the dual kernel; must equal the two separate solves
     mp_ = rb.MatrixParams(samples=4, rays=32, seed=2, bvh="builtin", reciprocity=True, max_iters=12, min_iters=3, tol=5e-4)
     sp_ = rb.SkyParams(samples=4, rays=32, seed=2, bvh="builtin", max_iters=8, min_iters=3, tol=1e-3, discrete=True)
