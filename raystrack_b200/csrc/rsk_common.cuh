@@ -199,12 +199,22 @@ enum { MODE_MATRIX = 0, MODE_SKY = 1, MODE_DUAL = 2 };
 
 // internal entry points shared between translation units
 int rsk_launch_trace(rsk_ctx *ctx, TraceArgs &a, int mode, int64_t n_tiles);
-// Tile size for a launch over `total_rays` rays: large tiles amortise the per-CTA prologue/flush and shorten the tail
-// (8192: +2 % on C5), small tiles keep all SMs busy when a scene shoots few rays per iteration.
+// Tile size for a launch over `total_rays` rays: large tiles amortise the per-CTA prologue/flush (8192: +2 % on C5),
+// small tiles keep all SMs busy when a scene shoots few rays per iteration and shorten the tail of the launch.
 static inline int rsk_pick_tile_rays(int64_t total_rays, int sm_count) {
-    const int64_t want_ctas = 8 * (int64_t)(sm_count > 0 ? sm_count : 148);      // two full waves of 4 CTAs per SM
+    static int forced = -1;                 // RSK_TILE_RAYS=<512..8192, power of two>: tuning override
+    if (forced < 0) {
+        const char *e = getenv("RSK_TILE_RAYS");
+        const int v = e ? atoi(e) : 0;
+        forced = (v >= 512 && v <= RSK_TILE_RAYS_MAX && (v & (v - 1)) == 0) ? v : 0;
+    }
+    if (forced) return forced;
+    const int64_t wave = 4 * (int64_t)(sm_count > 0 ? sm_count : 148);           // CTAs resident at once (4 per SM)
     int t = RSK_TILE_RAYS_MAX;
-    while (t > 512 && total_rays / t < want_ctas) t >>= 1;
+    // The last wave leaves the SMs idle for about half a tile's run time: the largest tile only pays with >= 8 waves
+    // (a 1/8 shard of the bench scene: 4096-ray tiles +1.5 %), below that at least two full waves are kept.
+    if (t > 4096 && total_rays / t < 8 * wave) t = 4096;
+    while (t > 512 && total_rays / t < 2 * wave) t >>= 1;
     return t;
 }
 int rsk_qmc_ensure_halton(rsk_ctx *ctx, int64_t n);

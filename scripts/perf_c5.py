@@ -18,6 +18,8 @@ ap.add_argument("--samples", type=int, default=4)
 ap.add_argument("--rays", type=int, default=64)
 ap.add_argument("--sky", action="store_true")
 ap.add_argument("--recip", action="store_true", help="reciprocity schedule: emitter i ignores meshes j <= i")
+ap.add_argument("--world", type=int, default=1, help="time the shard rank --rank of plan_shards(world) would get (no collectives)")
+ap.add_argument("--rank", type=int, default=0)
 args = ap.parse_args()
 
 t = time.time()
@@ -38,10 +40,14 @@ print(f"emitters+tables {time.time()-t:.2f}s", flush=True)
 n = len(meshes)
 centers, extents = ps.get_mesh_bounds()
 active = _surface_masks(ems, centers, extents)
-ids = np.arange(n, dtype=np.int32)
+from raystrack_b200.main import plan_shards                       # noqa: E402
+plan = plan_shards(list(range(n)), [int(e.n_cells * args.rays) for e in ems], args.world)[args.rank]
+ids = np.asarray([j[0] for j in plan], np.int32)
+ranges = np.asarray([[j[1], j[2]] for j in plan], np.int64)
 table = _rotation_table(1, n, args.iters + 2)
-solve = _native.Solve(ctx, sc, em, ids, active, table, ids.copy(), max_iters=args.iters + 2, min_iters=args.iters + 2, interval=1,
-                      tol_mode="stderr", tol=0.0, emit_sid=ids, min_sid=(ids + 1) if args.recip else np.zeros(n, np.int32), sky=args.sky, discrete=True)
+solve = _native.Solve(ctx, sc, em, ids, active[ids], table, ids.copy(), max_iters=args.iters + 2, min_iters=args.iters + 2, interval=1,
+                      tol_mode="stderr", tol=0.0, emit_sid=ids, min_sid=(ids + 1) if args.recip else np.zeros(len(ids), np.int32),
+                      sky=args.sky, discrete=True, ray_range=ranges)
 solve.step(1)
 r0 = solve.rays_traced()
 ctx.timer_start()
