@@ -138,6 +138,14 @@ int rsk_emitters_info(rsk_emitters *em, int32_t *g, int64_t *n_rays_once);
 int rsk_emitters_download_records(rsk_emitters *em, float *records, float *cdf);
 int rsk_scene_download_triangles(rsk_scene *scene, float *tri, float *normals);
 
+/* surf_active of every emitter at once (replaces `_build_emitter_surface_mask`, main.py:167-204): active_out is
+ * uint8[n_emit][n_surf]; emitter e switches off its own mesh and, if planar[e], every mesh whose bounding box
+ * (centers/extents float32[n_surf][3], utils/prepared.py:359-375) lies wholly behind the plane
+ * (plane_origin/plane_normal float32[n_emit][3], plane_tol float32[n_emit]).  Same float32 operation order. */
+int rsk_surface_masks(rsk_ctx *ctx, int32_t n_emit, int32_t n_surf, const uint8_t *planar, const float *plane_origin,
+                      const float *plane_normal, const float *plane_tol, const float *centers, const float *extents,
+                      uint8_t *active_out);
+
 /* ------------------------------------------------------------------------------------------- per-ray hook
  * Replaces build_rays + trace_cpu_[bvh_]firsthit / trace_cpu_[bvh_]hitmask called back to back
  * (utils/ray_builder.py:25-94; utils/cpu_trace.py:54-277, 540-732) for ONE emitter and ONE iteration, writing

@@ -27,7 +27,7 @@ EXPORTS = (
     "rsk_scene_create", "rsk_scene_destroy", "rsk_scene_info", "rsk_scene_download_bvh",
     "rsk_emitters_create", "rsk_emitters_destroy", "rsk_emitters_download_tables",
     "rsk_geometry_create", "rsk_geometry_destroy", "rsk_scene_from_geometry", "rsk_emitters_from_geometry",
-    "rsk_emitters_info", "rsk_emitters_download_records", "rsk_scene_download_triangles",
+    "rsk_emitters_info", "rsk_emitters_download_records", "rsk_scene_download_triangles", "rsk_surface_masks",
     "rsk_trace_rays",
     "rsk_matrix_begin", "rsk_matrix_step", "rsk_matrix_read", "rsk_solve_read_block", "rsk_matrix_device_tallies",
     "rsk_sky_begin", "rsk_sky_step", "rsk_sky_read", "rsk_dual_begin", "rsk_dual_step", "rsk_dual_sky_part",
@@ -143,6 +143,18 @@ class Context:
         info = (C.c_int64 * 4)()
         check(self.lib.rsk_ctx_device_info(self.handle, name, info))
         return {"name": name.value.decode(), "sm_count": int(info[0]), "cc": (int(info[1]), int(info[2])), "mem": int(info[3])}
+
+    def surface_masks(self, planar, plane_origin, plane_normal, plane_tol, centers, extents) -> np.ndarray:
+        """``rsk_surface_masks``: uint8 [n_emit, n_surf] activity masks of all emitters."""
+        planar = np.ascontiguousarray(planar, np.uint8)
+        po, pn = np.ascontiguousarray(plane_origin, np.float32), np.ascontiguousarray(plane_normal, np.float32)
+        tol = np.ascontiguousarray(plane_tol, np.float32)
+        c, x = np.ascontiguousarray(centers, np.float32), np.ascontiguousarray(extents, np.float32)
+        ne, ns = int(planar.shape[0]), int(c.shape[0])
+        out = np.empty((ne, ns), np.uint8)
+        check(self.lib.rsk_surface_masks(self.handle, C.c_int32(ne), C.c_int32(ns), ptr(planar), ptr(po), ptr(pn), ptr(tol),
+                                         ptr(c), ptr(x), ptr(out)), "rsk_surface_masks")
+        return out
 
     def reciprocity_rowsum(self, area: np.ndarray, F: np.ndarray, target: Optional[np.ndarray] = None,
                            tol: float = 1e-10, max_iter: int = 500) -> int:

@@ -228,6 +228,31 @@ __global__ void rsk_prepare_meshes_kernel(const float4 *__restrict__ em_rec, con
     }
 }
 
+// One thread per (emitter, surface): `surf_active` of reference main.py:167-204.  A planar emitter switches off every
+// mesh whose bounding box lies wholly behind its plane; float32 operations in the reference's order
+// (dx*nx + dy*ny + dz*nz, then |n|.extent), no fused multiply-add.  The emitter's own mesh is always off.
+__global__ void rsk_surface_masks_kernel(int n_emit, int n_surf, const uint8_t *__restrict__ planar, const float *__restrict__ po,
+                                         const float *__restrict__ pn, const float *__restrict__ tol,
+                                         const float *__restrict__ centers, const float *__restrict__ extents, uint8_t *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_emit * n_surf) return;
+    const int e = (int)(i / n_surf), s = (int)(i - (int64_t)e * n_surf);
+    uint8_t on = 1;
+    if (planar[e]) {
+        const float nx = pn[3 * e], ny = pn[3 * e + 1], nz = pn[3 * e + 2];
+        float signed_d = __fmul_rn(__fsub_rn(centers[3 * s], po[3 * e]), nx);
+        signed_d = __fadd_rn(signed_d, __fmul_rn(__fsub_rn(centers[3 * s + 1], po[3 * e + 1]), ny));
+        signed_d = __fadd_rn(signed_d, __fmul_rn(__fsub_rn(centers[3 * s + 2], po[3 * e + 2]), nz));
+        float radius = __fmul_rn(fabsf(nx), extents[3 * s]);
+        radius = __fadd_rn(radius, __fmul_rn(fabsf(ny), extents[3 * s + 1]));
+        radius = __fadd_rn(radius, __fmul_rn(fabsf(nz), extents[3 * s + 2]));
+        signed_d = __fadd_rn(signed_d, radius);
+        on = (signed_d <= tol[e]) ? 0 : 1;
+    }
+    if (e == s) on = 0;
+    out[i] = on;
+}
+
 }  // namespace
 
 // ----------------------------------------------------------------------------- geometry handle
@@ -397,4 +422,42 @@ extern "C" int rsk_scene_download_triangles(rsk_scene *sc, float *tri, float *no
     if (tri && sc->n_tri) RSK_CUDA(cudaMemcpy(tri, sc->tri, (size_t)sc->n_tri * 3 * sizeof(float4), cudaMemcpyDeviceToHost));
     if (normals && sc->n_tri) RSK_CUDA(cudaMemcpy(normals, sc->nrm, (size_t)sc->n_tri * sizeof(float4), cudaMemcpyDeviceToHost));
     return RSK_OK;
+}
+
+// ----------------------------------------------------------------------------- surface masks
+
+extern "C" int rsk_surface_masks(rsk_ctx *ctx, int32_t n_emit, int32_t n_surf, const uint8_t *planar, const float *plane_origin,
+                                 const float *plane_normal, const float *plane_tol, const float *centers, const float *extents,
+                                 uint8_t *active_out) {
+    RSK_REQUIRE(ctx && n_emit >= 0 && n_surf >= 0, "rsk_surface_masks: bad arguments");
+    const int64_t total = (int64_t)n_emit * n_surf;
+    if (total == 0) return RSK_OK;
+    RSK_REQUIRE(planar && plane_origin && plane_normal && plane_tol && centers && extents && active_out, "rsk_surface_masks: null array");
+    RskScope scope(ctx);
+    uint8_t *d_planar = nullptr, *d_out = nullptr;
+    float *d_f = nullptr;                      // [po 3e][pn 3e][tol e][centers 3s][extents 3s]
+    const size_t ne = (size_t)n_emit, ns = (size_t)n_surf, nf = 7 * ne + 6 * ns;
+    int rc = rsk_dev_alloc(&d_planar, ne);
+    if (rc == RSK_OK) rc = rsk_dev_alloc(&d_f, nf);
+    if (rc == RSK_OK) rc = rsk_dev_alloc(&d_out, (size_t)total);
+    if (rc == RSK_OK) {
+        cudaError_t e = cudaMemcpyAsync(d_planar, planar, ne, cudaMemcpyHostToDevice, ctx->stream);
+        const float *src[5] = {plane_origin, plane_normal, plane_tol, centers, extents};
+        const size_t cnt[5] = {3 * ne, 3 * ne, ne, 3 * ns, 3 * ns};
+        size_t off = 0;
+        for (int k = 0; k < 5 && e == cudaSuccess; ++k) {
+            e = cudaMemcpyAsync(d_f + off, src[k], cnt[k] * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+            off += cnt[k];
+        }
+        if (e == cudaSuccess) {
+            rsk_surface_masks_kernel<<<rsk_blocks(total, 256), 256, 0, ctx->stream>>>(
+                n_emit, n_surf, d_planar, d_f, d_f + 3 * ne, d_f + 6 * ne, d_f + 7 * ne, d_f + 7 * ne + 3 * ns, d_out);
+            ctx->launches++;
+            e = cudaMemcpyAsync(active_out, d_out, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { rsk_set_error("rsk_surface_masks failed: %s", cudaGetErrorString(e)); rc = RSK_ERR_CUDA; }
+    }
+    rsk_dev_free(d_planar); rsk_dev_free(d_f); rsk_dev_free(d_out);
+    return rc;
 }

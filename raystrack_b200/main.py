@@ -121,12 +121,20 @@ def _surface_masks(emitters: Sequence[PreparedEmitter], centers: np.ndarray, ext
     return active
 
 
-def _cached_masks(solver: PreparedSolver, emitters, centers, extents, flip_faces: bool) -> np.ndarray:
-    """Surface masks depend only on the emitter planes and the mesh bounds, so a PreparedSolver keeps them."""
+def _cached_masks(solver: PreparedSolver, emitters, centers, extents, flip_faces: bool,
+                  ctx: Optional[_native.Context] = None) -> np.ndarray:
+    """Surface masks depend only on the emitter planes and the mesh bounds, so a PreparedSolver keeps them.  With a
+    context they are computed on the GPU (``rsk_surface_masks``: the same float32 operations as ``_surface_masks``)."""
     key = ("surface_masks", bool(flip_faces))
     got = solver._derived_cache.get(key)
     if got is None:
-        got = _surface_masks(emitters, centers, extents)
+        if ctx is not None and len(emitters) and centers.shape[0]:
+            ne = len(emitters)
+            got = ctx.surface_masks(np.fromiter((em.plane_is_planar for em in emitters), bool, ne),
+                                    np.stack([em.plane_origin for em in emitters]), np.stack([em.plane_normal for em in emitters]),
+                                    np.fromiter((em.plane_tol for em in emitters), np.float64, ne).astype(np.float32), centers, extents)
+        else:
+            got = _surface_masks(emitters, centers, extents)
         got.setflags(write=False)
         solver._derived_cache[key] = got
     return got
@@ -370,7 +378,7 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
 
     t0 = time.time()
     with _Phase("masks"):
-        active = _cached_masks(solver, emitters, centers, extents, flip_faces)
+        active = _cached_masks(solver, emitters, centers, extents, flip_faces, ctx)
     # receivers of emitter i (main.py:161-164, 207-214): active meshes j > i (reciprocity) or j != i
     emit_sid = np.arange(n_surf, dtype=np.int32)
     min_sid = (emit_sid + 1) if reciprocity else np.zeros(n_surf, np.int32)
@@ -473,7 +481,7 @@ def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepar
     d_em = solver.get_device_emitters(samples=samples, rays=rays, flip_faces=False, ctx=ctx)     # main.py:1985
     emitters = solver.get_emitter_summaries(samples=samples, rays=rays, flip_faces=False, ctx=ctx)
     t0 = time.time()
-    active = _cached_masks(solver, emitters, centers, extents, False)
+    active = _cached_masks(solver, emitters, centers, extents, False, ctx)
     weights = [float(em.n_cells * rays) for em in emitters]
     n_once = [int(em.n_cells * rays) for em in emitters]
     if _hook is not None and "precomputed" in _hook:
@@ -524,7 +532,7 @@ def _shared_ray_solve(meshes, matrix_params: MatrixParams, sky_params: SkyParams
     d_scene = solver.get_device_scene(use_bvh=use_bvh, ctx=ctx)
     d_em = solver.get_device_emitters(samples=mp["samples"], rays=mp["rays"], flip_faces=False, ctx=ctx)
     emitters = solver.get_emitter_summaries(samples=mp["samples"], rays=mp["rays"], flip_faces=False, ctx=ctx)
-    active = _cached_masks(solver, emitters, centers, extents, False)
+    active = _cached_masks(solver, emitters, centers, extents, False, ctx)
     ids = np.arange(n_surf, dtype=np.int32)
     min_sid = (ids + 1) if mp["reciprocity"] else np.zeros(n_surf, np.int32)
     table = _rotation_table(mp["seed"], n_surf, max(int(mp["max_iters"]), int(sp["max_iters"])))

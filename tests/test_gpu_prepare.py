@@ -160,3 +160,18 @@ def test_out_of_range_face_index_raises_index_error(rb):
     bad = [("a", V, np.array([[0, 1, 3]], np.int32)), ("b", V + 1.0, np.array([[0, 1, 2]], np.int32))]
     with pytest.raises(IndexError):
         rb.view_factor_matrix(bad, rb.MatrixParams(samples=4, rays=4, max_iters=2, min_iters=1))
+
+
+@pytest.mark.parametrize("name", ["canyon", "cube", "tilted", "urban", "soup"])
+def test_device_surface_masks_equal_host_masks(rb, name):
+    """rsk_surface_masks against main._surface_masks (itself pinned to the oracle's per-emitter loop on the host)."""
+    from raystrack_b200 import _native, main as M
+    from raystrack_b200.prepared import PreparedSolver
+    meshes = _scenes()[name]
+    ps = PreparedSolver(meshes)
+    ems = ps.get_emitters(samples=4, rays=4, flip_faces=False)
+    centers, extents = ps.get_mesh_bounds()
+    host = M._surface_masks(ems, centers, extents)
+    ctx = _native.Context.for_device(0)
+    dev = M._cached_masks(PreparedSolver(meshes), ems, centers, extents, False, ctx)
+    assert dev.dtype == np.uint8 and np.array_equal(dev, host)
