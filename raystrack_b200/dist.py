@@ -5,7 +5,7 @@ blocks are summed once at the end -- integer sums make the result independent of
 from __future__ import annotations
 
 import os
-from typing import List, Sequence
+from typing import Sequence
 
 import numpy as np
 

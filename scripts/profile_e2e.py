@@ -8,7 +8,6 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import raystrack_b200 as rb                      # noqa: E402
 from raystrack_b200 import main as M, synthetic  # noqa: E402
-from raystrack_b200.prepared import PreparedSolver  # noqa: E402
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 meshes = synthetic.urban_block(20)

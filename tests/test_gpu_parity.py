@@ -1,6 +1,5 @@
 """GPU parity tests: the CUDA path (through the C ABI, via ctypes) against the CPU oracle and the golden
 vectors produced by the reference.  Run with ``pytest -m gpu`` on a B200."""
-import json
 
 import numpy as np
 import pytest
