@@ -236,6 +236,14 @@ int rsk_dual_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, const int32
                    const float *cp_table, int32_t n_rot, const int32_t *rot_base,
                    const rsk_solve_params *matrix_params, const rsk_solve_params *sky_params, int32_t discrete,
                    rsk_solve **out);
+/* The same with ray_range[n_local][2] as in rsk_matrix_begin (multi-GPU ray slices of oversized emitters).  A sliced
+ * dual solve is stepped split-phase: rsk_solve_enqueue_trace(solve) traces both sides at once, the caller all-reduces
+ * the iteration tallies of BOTH handles, then rsk_solve_enqueue_fold on each handle; rsk_solve_poll on each. */
+int rsk_dual_begin_sliced(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, const int32_t *emit_ids, int32_t n_local,
+                          const uint8_t *surf_active, const int32_t *emit_sid, const int32_t *min_sid,
+                          const float *cp_table, int32_t n_rot, const int32_t *rot_base, const int64_t *ray_range,
+                          const rsk_solve_params *matrix_params, const rsk_solve_params *sky_params, int32_t discrete,
+                          rsk_solve **out);
 int rsk_dual_step(rsk_solve *solve, int32_t n_iters, int32_t *n_active);
 int rsk_dual_sky_part(rsk_solve *solve, rsk_solve **sky);
 

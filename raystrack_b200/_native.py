@@ -30,7 +30,7 @@ EXPORTS = (
     "rsk_emitters_info", "rsk_emitters_download_records", "rsk_scene_download_triangles", "rsk_surface_masks",
     "rsk_trace_rays",
     "rsk_matrix_begin", "rsk_matrix_step", "rsk_matrix_read", "rsk_solve_read_block", "rsk_matrix_device_tallies",
-    "rsk_sky_begin", "rsk_sky_step", "rsk_sky_read", "rsk_dual_begin", "rsk_dual_step", "rsk_dual_sky_part",
+    "rsk_sky_begin", "rsk_sky_step", "rsk_sky_read", "rsk_dual_begin", "rsk_dual_begin_sliced", "rsk_dual_step", "rsk_dual_sky_part",
     "rsk_solve_enqueue_trace", "rsk_solve_enqueue_fold", "rsk_solve_poll", "rsk_solve_device_iter_tallies", "rsk_solve_set_iter_tally_buffer",
     "rsk_solve_destroy", "rsk_solve_rays_traced", "rsk_reciprocity_rowsum",
 )
@@ -452,13 +452,18 @@ class _SolvePart:
         self.ctx, self.scene, self.handle, self.n_local, self.sky, self.discrete = ctx, scene, handle, n_local, sky, discrete
 
     read_block = Solve.read_block
+    read_counters = Solve.read_counters
+    enqueue_fold = Solve.enqueue_fold
+    poll = Solve.poll
+    device_iter_tallies = Solve.device_iter_tallies
+    set_iter_tally_buffer = Solve.set_iter_tally_buffer
 
 
 class DualSolve:
     """Wraps a shared-ray solve (``rsk_dual_*``): one traversal per ray feeds the matrix and the sky tallies."""
 
     def __init__(self, ctx: Context, scene: DeviceScene, em: DeviceEmitters, emit_ids, surf_active, cp_table, rot_base,
-                 emit_sid, min_sid, matrix: dict, sky: dict, discrete: bool):
+                 emit_sid, min_sid, matrix: dict, sky: dict, discrete: bool, ray_range=None):
         for side in (matrix, sky):
             if side["tol_mode"] not in ("stderr", "delta"):
                 raise ValueError(f"Unknown tol_mode: {side['tol_mode']}")
@@ -476,13 +481,18 @@ class DualSolve:
             return SolveParams(int(d["max_iters"]), int(d["min_iters"]), int(d["interval"]), 0 if d["tol_mode"] == "stderr" else 1, float(d["tol"]))
 
         pm, pk = pack(matrix), pack(sky)
-        check(ctx.lib.rsk_dual_begin(ctx.handle, scene.handle, em.handle, ptr(ids), C.c_int32(self.n_local), ptr(act), ptr(es), ptr(ms),
-                                     ptr(cpt), C.c_int32(cpt.shape[0]), ptr(rb), C.byref(pm), C.byref(pk),
-                                     C.c_int32(1 if discrete else 0), C.byref(self.handle)), "rsk_dual_begin")
+        rr = None if ray_range is None else np.ascontiguousarray(ray_range, np.int64).reshape(self.n_local, 2)
+        check(ctx.lib.rsk_dual_begin_sliced(ctx.handle, scene.handle, em.handle, ptr(ids), C.c_int32(self.n_local), ptr(act), ptr(es),
+                                            ptr(ms), ptr(cpt), C.c_int32(cpt.shape[0]), ptr(rb), ptr(rr), C.byref(pm), C.byref(pk),
+                                            C.c_int32(1 if discrete else 0), C.byref(self.handle)), "rsk_dual_begin_sliced")
         sky_handle = C.c_void_p()
         check(ctx.lib.rsk_dual_sky_part(self.handle, C.byref(sky_handle)), "rsk_dual_sky_part")
         self.matrix_part = _SolvePart(ctx, scene, self.handle, self.n_local, False, False)
         self.sky_part = _SolvePart(ctx, scene, sky_handle, self.n_local, True, bool(discrete))
+
+    def enqueue_trace(self) -> None:
+        """One traversal per ray for both sides (split-phase stepping; fold each part afterwards)."""
+        check(self.ctx.lib.rsk_solve_enqueue_trace(self.handle), "rsk_solve_enqueue_trace")
 
     def step(self, n_iters: int) -> int:
         n_active = C.c_int32(0)

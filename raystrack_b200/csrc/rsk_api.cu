@@ -704,14 +704,23 @@ extern "C" int rsk_dual_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
                               const float *cp_table, int32_t n_rot, const int32_t *rot_base,
                               const rsk_solve_params *matrix_params, const rsk_solve_params *sky_params, int32_t discrete,
                               rsk_solve **out) {
+    return rsk_dual_begin_sliced(ctx, scene, em, emit_ids, n_local, surf_active, emit_sid, min_sid, cp_table, n_rot, rot_base, nullptr,
+                                 matrix_params, sky_params, discrete, out);
+}
+
+extern "C" int rsk_dual_begin_sliced(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, const int32_t *emit_ids, int32_t n_local,
+                                     const uint8_t *surf_active, const int32_t *emit_sid, const int32_t *min_sid,
+                                     const float *cp_table, int32_t n_rot, const int32_t *rot_base, const int64_t *ray_range,
+                                     const rsk_solve_params *matrix_params, const rsk_solve_params *sky_params, int32_t discrete,
+                                     rsk_solve **out) {
     RSK_REQUIRE(out && matrix_params && sky_params, "rsk_dual_begin: null argument");
     RSK_REQUIRE(n_local == 0 || (emit_sid && min_sid), "rsk_dual_begin: null emit_sid/min_sid");
     *out = nullptr;
     rsk_solve *m = nullptr, *k = nullptr;
     RSK_TRY(rsk_solve_begin(ctx, scene, em, MODE_MATRIX, 0, emit_ids, n_local, surf_active, emit_sid, min_sid, cp_table, n_rot, rot_base,
-                            nullptr, matrix_params, &m));
+                            ray_range, matrix_params, &m));
     int rc = rsk_solve_begin(ctx, scene, em, MODE_SKY, discrete ? 1 : 0, emit_ids, n_local, surf_active, nullptr, nullptr, cp_table, n_rot,
-                             rot_base, nullptr, sky_params, &k);
+                             rot_base, ray_range, sky_params, &k);
     if (rc != RSK_OK) { rsk_solve_destroy(m); return rc; }
     m->twin = k;
     // an emitter without receivers never starts its matrix side (main.py:1285-1287): mark it done up front

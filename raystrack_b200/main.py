@@ -541,31 +541,55 @@ def _shared_ray_solve(meshes, matrix_params: MatrixParams, sky_params: SkyParams
         return dict(max_iters=p["max_iters"], min_iters=p["min_iters"], tol=p["tol"], tol_mode=p["tol_mode"],
                     interval=max(1, int(p["convergence_interval"])) if schedule == "gpu" else 1)
 
-    # Emitters are independent: under torch.distributed every rank solves whole emitters (no ray slices, hence no
-    # per-iteration exchange) and the integer results are summed once at the end.
+    # Emitters are independent: under torch.distributed every rank solves its share (whole emitters, plus a ray slice of
+    # every oversized one, exactly as _solve_sharded does) and the integer results are summed once at the end.
     rank, world = _dist_env()
     n_once = [int(em.n_cells * int(mp["rays"])) for em in emitters]
-    mine = np.asarray([j[0] for j in plan_shards(list(range(n_surf)), n_once, world, allow_split=False)[rank]], np.int32)
+    plan = plan_shards(list(range(n_surf)), n_once, world)[rank]
+    mine = np.asarray([j[0] for j in plan], np.int32)
+    ranges = np.asarray([[j[1], j[2]] for j in plan], np.int64).reshape(-1, 2)
+    n_shared = sum(1 for j in plan if j[3])
+    keep = np.asarray([not (j[3] and rank != 0) for j in plan], bool)          # ray-split jobs are replicated: count once
     n_sky = 145 if sp["discrete"] else 1
     out_m = (np.zeros((n_surf, 2 * n_surf), np.int64), np.zeros(n_surf, np.int64), np.zeros(n_surf, np.int64))
     out_s = (np.zeros((n_surf, n_sky), np.int64), np.zeros(n_surf, np.int64), np.zeros(n_surf, np.int64))
-    if mine.size:
-        solve = _native.DualSolve(ctx, d_scene.native, d_em.native, mine, active[mine], table, mine.copy(), ids[mine], min_sid[mine],
-                                  side(mp), side(sp), bool(sp["discrete"]))
-        try:
-            limit = max(int(mp["max_iters"]), int(sp["max_iters"]))
-            first = max(1, min(limit, max(1, min(int(mp["min_iters"]), int(sp["min_iters"])))))
-            running = solve.step(first) if limit > 0 else 0
+    limit = max(int(mp["max_iters"]), int(sp["max_iters"]))
+    first = max(1, min(limit, max(1, min(int(mp["min_iters"]), int(sp["min_iters"])))))
+    solve = _native.DualSolve(ctx, d_scene.native, d_em.native, mine, active[mine] if mine.size else np.zeros((0, n_surf), np.uint8),
+                              table, mine.copy(), ids[mine], min_sid[mine], side(mp), side(sp), bool(sp["discrete"]),
+                              ray_range=ranges if world > 1 else None)
+    try:
+        if world > 1 and n_shared > 0:
+            # split-phase: trace, sum the iteration tallies of the ray-split jobs (both sides) over the ranks, fold
+            from . import dist as D
+            tm = D.attach_tally_tensor(solve.matrix_part, n_shared, ctx.device)
+            ts = D.attach_tally_tensor(solve.sky_part, n_shared, ctx.device)
+            done, chunk = 0, first
+            while done < limit:
+                for _ in range(chunk):
+                    solve.enqueue_trace()
+                    D.all_reduce_device_(tm, ctx.device)
+                    D.all_reduce_device_(ts, ctx.device)
+                    solve.matrix_part.enqueue_fold()
+                    solve.sky_part.enqueue_fold()
+                done += chunk
+                running = (solve.matrix_part.poll() + solve.sky_part.poll()) if mine.size else 0
+                if D.max_over_ranks(float(running), ctx.device) <= 0:
+                    break
+                chunk = min(4, limit - done)
+        elif mine.size and limit > 0:
+            running = solve.step(first)
             done = first
             while running > 0 and done < limit:
                 chunk = min(4, limit - done)
                 running = solve.step(chunk)
                 done += chunk
+        if mine.size:
             for part, out in ((solve.matrix_part, out_m), (solve.sky_part, out_s)):
                 t, i, r = part.read_block()
-                out[0][mine], out[1][mine], out[2][mine] = t, i.astype(np.int64), r
-        finally:
-            solve.close()
+                out[0][mine[keep]], out[1][mine[keep]], out[2][mine[keep]] = t[keep], i.astype(np.int64)[keep], r[keep]
+    finally:
+        solve.close()
     if world > 1:
         from .dist import allreduce_sum_
         allreduce_sum_([*out_m, *out_s], device=ctx.device)
