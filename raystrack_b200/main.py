@@ -258,6 +258,23 @@ def _context() -> _native.Context:
     return _native.Context.for_device()
 
 
+def _plan_chunks(plan: List[Tuple[int, int, int, bool]], n_hist: int) -> List[List[Tuple[int, int, int, bool]]]:
+    """The device keeps ~40 bytes per (job, bin): iteration tally, total, Welford mean/M2 (+ previous estimate).  Jobs
+    are solved in chunks that fit a memory budget (RSK_SOLVE_MEMORY_MB, default 16384); emitters are independent, so
+    chunking cannot change any result.  Ray-split jobs (first in every rank's list, same order everywhere) stay
+    together in the first chunk."""
+    budget = max(1.0, float(os.environ.get("RSK_SOLVE_MEMORY_MB", "16384")) * (1 << 20))
+    max_jobs = max(1, int(budget // (40 * max(1, n_hist))))
+    n_shared = sum(1 for j in plan if j[3])
+    chunks: List[List[Tuple[int, int, int, bool]]] = []
+    head = plan[:max(n_shared, min(len(plan), max_jobs))] if plan else []
+    if head or not plan:
+        chunks.append(head)
+    for lo in range(len(head), len(plan), max_jobs):
+        chunks.append(plan[lo:lo + max_jobs])
+    return chunks
+
+
 def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_iters, min_iters, interval, tol_mode, tol,
                    emit_sid=None, min_sid=None, sky=False, discrete=False):
     """Run the jobs of ``todo`` (emitter indices) on this rank's shard and return full-size, rank-summed integer
@@ -270,19 +287,7 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
     any_shared = world > 1 and any(j[3] for shard in all_plans for j in shard)
     n_hist = (145 if discrete else 1) if sky else 2 * n_surf
 
-    # The device keeps ~40 bytes per (job, bin): iteration tally, total, Welford mean/M2 (+ previous estimate).  Jobs
-    # are solved in chunks that fit a memory budget; emitters are independent, so chunking cannot change any result.
-    # Ray-split jobs (first in every rank's list, same order everywhere) stay together in the first chunk.
-    budget = max(1.0, float(os.environ.get("RSK_SOLVE_MEMORY_MB", "16384")) * (1 << 20))
-    per_job = 40 * max(1, n_hist)
-    max_jobs = max(1, int(budget // per_job))
-    n_shared = sum(1 for j in plan if j[3])
-    chunks: List[List[Tuple[int, int, int, bool]]] = []
-    head = plan[:max(n_shared, min(len(plan), max_jobs))] if plan else []
-    if head or not plan:
-        chunks.append(head)
-    for lo in range(len(head), len(plan), max_jobs):
-        chunks.append(plan[lo:lo + max_jobs])
+    chunks = _plan_chunks(plan, n_hist)
 
     single = world == 1 and len(chunks) == 1 and len(plan) == n_emit
     # Under NCCL the tally blocks never visit the host before they are summed (dist.DeviceReducer).
@@ -545,51 +550,53 @@ def _shared_ray_solve(meshes, matrix_params: MatrixParams, sky_params: SkyParams
     # every oversized one, exactly as _solve_sharded does) and the integer results are summed once at the end.
     rank, world = _dist_env()
     n_once = [int(em.n_cells * int(mp["rays"])) for em in emitters]
-    plan = plan_shards(list(range(n_surf)), n_once, world)[rank]
-    mine = np.asarray([j[0] for j in plan], np.int32)
-    ranges = np.asarray([[j[1], j[2]] for j in plan], np.int64).reshape(-1, 2)
-    n_shared = sum(1 for j in plan if j[3])
-    keep = np.asarray([not (j[3] and rank != 0) for j in plan], bool)          # ray-split jobs are replicated: count once
     n_sky = 145 if sp["discrete"] else 1
     out_m = (np.zeros((n_surf, 2 * n_surf), np.int64), np.zeros(n_surf, np.int64), np.zeros(n_surf, np.int64))
     out_s = (np.zeros((n_surf, n_sky), np.int64), np.zeros(n_surf, np.int64), np.zeros(n_surf, np.int64))
     limit = max(int(mp["max_iters"]), int(sp["max_iters"]))
     first = max(1, min(limit, max(1, min(int(mp["min_iters"]), int(sp["min_iters"])))))
-    solve = _native.DualSolve(ctx, d_scene.native, d_em.native, mine, active[mine] if mine.size else np.zeros((0, n_surf), np.uint8),
-                              table, mine.copy(), ids[mine], min_sid[mine], side(mp), side(sp), bool(sp["discrete"]),
-                              ray_range=ranges if world > 1 else None)
-    try:
-        if world > 1 and n_shared > 0:
-            # split-phase: trace, sum the iteration tallies of the ray-split jobs (both sides) over the ranks, fold
-            from . import dist as D
-            tm = D.attach_tally_tensor(solve.matrix_part, n_shared, ctx.device)
-            ts = D.attach_tally_tensor(solve.sky_part, n_shared, ctx.device)
-            done, chunk = 0, first
-            while done < limit:
-                for _ in range(chunk):
-                    solve.enqueue_trace()
-                    D.all_reduce_device_(tm, ctx.device)
-                    D.all_reduce_device_(ts, ctx.device)
-                    solve.matrix_part.enqueue_fold()
-                    solve.sky_part.enqueue_fold()
-                done += chunk
-                running = (solve.matrix_part.poll() + solve.sky_part.poll()) if mine.size else 0
-                if D.max_over_ranks(float(running), ctx.device) <= 0:
-                    break
-                chunk = min(4, limit - done)
-        elif mine.size and limit > 0:
-            running = solve.step(first)
-            done = first
-            while running > 0 and done < limit:
-                chunk = min(4, limit - done)
-                running = solve.step(chunk)
-                done += chunk
-        if mine.size:
-            for part, out in ((solve.matrix_part, out_m), (solve.sky_part, out_s)):
-                t, i, r = part.read_block()
-                out[0][mine[keep]], out[1][mine[keep]], out[2][mine[keep]] = t[keep], i.astype(np.int64)[keep], r[keep]
-    finally:
-        solve.close()
+    all_plans = plan_shards(list(range(n_surf)), n_once, world)
+    any_shared = world > 1 and any(j[3] for shard in all_plans for j in shard)
+    for c, plan in enumerate(_plan_chunks(all_plans[rank], 2 * n_surf + n_sky)):
+        mine = np.asarray([j[0] for j in plan], np.int32)
+        ranges = np.asarray([[j[1], j[2]] for j in plan], np.int64).reshape(-1, 2)
+        n_shared = sum(1 for j in plan if j[3])
+        keep = np.asarray([not (j[3] and rank != 0) for j in plan], bool)      # ray-split jobs are replicated: count once
+        solve = _native.DualSolve(ctx, d_scene.native, d_em.native, mine, active[mine] if mine.size else np.zeros((0, n_surf), np.uint8),
+                                  table, mine.copy(), ids[mine], min_sid[mine], side(mp), side(sp), bool(sp["discrete"]),
+                                  ray_range=ranges if world > 1 else None)
+        try:
+            if any_shared and c == 0:
+                # split-phase: trace, sum the iteration tallies of the ray-split jobs (both sides) over the ranks, fold
+                from . import dist as D
+                tm = D.attach_tally_tensor(solve.matrix_part, n_shared, ctx.device)
+                ts = D.attach_tally_tensor(solve.sky_part, n_shared, ctx.device)
+                done, chunk = 0, first
+                while done < limit:
+                    for _ in range(chunk):
+                        solve.enqueue_trace()
+                        D.all_reduce_device_(tm, ctx.device)
+                        D.all_reduce_device_(ts, ctx.device)
+                        solve.matrix_part.enqueue_fold()
+                        solve.sky_part.enqueue_fold()
+                    done += chunk
+                    running = (solve.matrix_part.poll() + solve.sky_part.poll()) if mine.size else 0
+                    if D.max_over_ranks(float(running), ctx.device) <= 0:
+                        break
+                    chunk = min(4, limit - done)
+            elif mine.size and limit > 0:
+                running = solve.step(first)
+                done = first
+                while running > 0 and done < limit:
+                    chunk = min(4, limit - done)
+                    running = solve.step(chunk)
+                    done += chunk
+            if mine.size:
+                for part, out in ((solve.matrix_part, out_m), (solve.sky_part, out_s)):
+                    t, i, r = part.read_block()
+                    out[0][mine[keep]], out[1][mine[keep]], out[2][mine[keep]] = t[keep], i.astype(np.int64)[keep], r[keep]
+        finally:
+            solve.close()
     if world > 1:
         from .dist import allreduce_sum_
         allreduce_sum_([*out_m, *out_s], device=ctx.device)

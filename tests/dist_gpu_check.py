@@ -62,6 +62,9 @@ def main():
     both = M.view_factor_matrix_and_sky(meshes, matrix_params=mp_, sky_params=sp_)
     assert both[0] == rb.view_factor_matrix(meshes, mp_), "dual solve (matrix side) differs from the separate solve"
     assert both[1] == rb.view_factor_to_tregenza_sky(meshes, sp_), "dual solve (sky side) differs from the separate solve"
+    os.environ["RSK_SOLVE_MEMORY_MB"] = "0.02"
+    assert M.view_factor_matrix_and_sky(meshes, matrix_params=mp_, sky_params=sp_) == both, "chunked dual solve differs"
+    del os.environ["RSK_SOLVE_MEMORY_MB"]
     print(f"[rank {rank}/{world}] shared-ray workflow == separate solves", flush=True)
     if rank == 0:
         # single-GPU run of the same solve inside this process group is not possible; compare with a saved file if present

@@ -166,11 +166,14 @@ def test_chunked_solve_equals_single_solve(rb, monkeypatch):
     meshes = synthetic.urban_block(3, 4, 8, 0)
     p = rb.MatrixParams(samples=2, rays=16, seed=3, bvh="builtin", max_iters=20, min_iters=4, tol=2e-3, reciprocity=True)
     sp = rb.SkyParams(samples=2, rays=16, seed=3, bvh="builtin", max_iters=9, min_iters=4, tol=1e-3, discrete=True)
+    import raystrack_b200.main as M
     whole = rb.view_factor_matrix(meshes, p)
     whole_sky = rb.view_factor_to_tregenza_sky(meshes, sp)
+    whole_both = M.view_factor_matrix_and_sky(meshes, matrix_params=p, sky_params=sp)
     monkeypatch.setenv("RSK_SOLVE_MEMORY_MB", "0.02")            # ~5 emitters per chunk
     assert rb.view_factor_matrix(meshes, p) == whole
     assert rb.view_factor_to_tregenza_sky(meshes, sp) == whole_sky
+    assert M.view_factor_matrix_and_sky(meshes, matrix_params=p, sky_params=sp) == whole_both      # dual solve in chunks
 
 
 @pytest.mark.parametrize("offset", [(0.0, 0.0, 0.0), (512345.0, 4112233.0, 250.0)])
