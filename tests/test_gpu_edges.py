@@ -206,3 +206,48 @@ def test_georeferenced_coordinates_per_ray(rb, offset):
             total += hit.shape[0]
         assert agree / total >= 0.9999, (use_bvh, agree, total)
         ps.clear_device_cache()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_triangle_soups_per_ray(rb, seed):
+    """Unstructured geometry: meshes of random, mutually intersecting triangles with very different sizes (incl.
+    slivers and a zero-area triangle).  Device preparation, the LBVH/wide-BVH builder and both traversal modes
+    must still agree with the oracle ray by ray (closest hit and any-hit), through the BVH and by brute force."""
+    from oracle import oracle as O
+    from raystrack_b200 import _native
+    from raystrack_b200.prepared import PreparedSolver
+    rng = np.random.default_rng(1000 + seed)
+    meshes = []
+    for m in range(7):
+        nt = int(rng.integers(1, 90))
+        centre = rng.uniform(-4, 4, 3)
+        size = 10.0 ** rng.uniform(-1.5, 0.8)
+        V = centre + rng.standard_normal((nt * 3, 3)) * size
+        if m == 2 and nt > 1:
+            V[3:6] = V[3]                                                  # zero-area triangle
+        if m == 4 and nt > 2:
+            V[7] = V[6] + 1e-4 * (V[8] - V[6])                             # sliver
+        meshes.append((f"soup{m}", V, np.arange(nt * 3, dtype=np.int64).reshape(nt, 3)))
+    ctx = _native.Context.for_device(0)
+    S = O.OracleSolver(meshes)
+    oem = S.emitters(8, 16, False)
+    centers, extents = S.bounds()
+    agree = total = 0
+    for use_bvh in (True, False):
+        ps = PreparedSolver(meshes)
+        sc = ps.get_device_scene(use_bvh=use_bvh, ctx=ctx).native
+        em = ps.get_device_emitters(samples=8, rays=16, flip_faces=False, ctx=ctx).native
+        for e in (0, 3, 6):
+            cpg, cpd = O.rotation(seed, e, 2)
+            act = O.surface_mask(e, oem[e], centers, extents)
+            ro, rd = O.build_rays(oem[e], cpg, cpd)
+            o, d, hit, front = _native.trace_rays(ctx, sc, em, e, act, e, 0, np.concatenate([cpg, cpd]), mode=0)
+            assert np.array_equal(o, ro) and np.array_equal(d, rd)
+            rh, rf = O.trace_firsthit(S.scene(use_bvh), ro, rd, act, e, 0)
+            agree += int(np.sum((hit == rh) & (front == rf)))
+            _, _, occl, _ = _native.trace_rays(ctx, sc, em, e, act, e, 0, np.concatenate([cpg, cpd]), mode=1, want_rays=False)
+            rmask = O.trace_hitmask(S.scene(use_bvh), ro, rd, act, e, 0)
+            agree += int(np.sum(occl.astype(bool) == np.asarray(rmask).astype(bool)))
+            total += 2 * hit.shape[0]
+        ps.clear_device_cache()
+    assert total > 0 and agree / total >= 0.9999, (agree, total)
