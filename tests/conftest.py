@@ -23,7 +23,9 @@ def stage():
 
 @pytest.fixture(scope="session")
 def solves():
-    return json.loads((GOLDEN / "solves.json").read_text())
+    both = json.loads((GOLDEN / "solves.json").read_text())
+    both.update(json.loads((GOLDEN / "solves_extra.json").read_text()))        # further parameter combinations (X*)
+    return both
 
 
 @pytest.fixture(scope="session")

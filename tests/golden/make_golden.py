@@ -10,6 +10,7 @@ Outputs (committed):
                       hit masks, Tregenza patch ids  (reference functions called directly)
   solves.json         whole-solve results + per-emitter iteration counts for the BASELINE configs C1-C4,
                       two validation cases and the sky variants (reference public API, device="cpu")
+  solves_extra.json   further parameter combinations (row-sum enforcement, delta sky, flipped enclosure with BVH, tilted meshes)
   workflow.json       view_factor_outside_workflow / view_factor_matrix_and_sky results (reference api.py, main.py:1209)
   shipped.json        the result files the reference ships (examples/*.json, validation/results/*), verbatim data
 """
@@ -242,6 +243,38 @@ def solves():
     (HERE / "solves.json").write_text(json.dumps(out, indent=1, sort_keys=True))
 
 
+def solves_extra():
+    """More parameter combinations of the public solves (written to solves_extra.json; same format as solves.json)."""
+    out = {}
+    canyon = synthetic.street_canyon()
+    cube = synthetic.unit_cube_enclosure()
+    urb = synthetic.urban_block(n_side=3, face_grid=4, ground_grid=8, seed=0)
+    tilted = synthetic.tilted_pair()
+
+    def add(name, fn, meshes, params):
+        res, iters = run_logged(fn, meshes, params)
+        out[name] = {"params": params.as_dict(), "result": res, "iters": iters}
+        print(name, "done", iters)
+
+    add("X1_canyon_rowsum", view_factor_matrix, canyon,
+        MatrixParams(samples=8, rays=64, seed=11, bvh="off", device="cpu", max_iters=40, min_iters=6, tol=5e-4, reciprocity=True,
+                     enforce_reciprocity_rowsum=True))
+    add("X2_canyon_sky_delta", view_factor_to_tregenza_sky, canyon,
+        SkyParams(samples=8, rays=64, seed=4, bvh="builtin", device="cpu", max_iters=50, min_iters=4, tol=1e-3, tol_mode="delta",
+                  discrete=True))
+    add("X3_cube_flip_bvh", view_factor_matrix, cube,
+        MatrixParams(samples=16, rays=64, seed=2, bvh="builtin", device="cpu", flip_faces=True, reciprocity=True, max_iters=60,
+                     min_iters=5, tol=2e-3))
+    add("X4_urban_delta_recip", view_factor_matrix, urb,
+        MatrixParams(samples=2, rays=32, seed=5, bvh="builtin", device="cpu", max_iters=20, min_iters=3, tol=2e-3, tol_mode="delta",
+                     reciprocity=True))
+    add("X5_tilted_matrix", view_factor_matrix, tilted,
+        MatrixParams(samples=32, rays=64, seed=8, bvh="builtin", device="cpu", max_iters=30, min_iters=5, tol=1e-3, reciprocity=False))
+    add("X5_tilted_sky", view_factor_to_tregenza_sky, tilted,
+        SkyParams(samples=32, rays=64, seed=8, bvh="off", device="cpu", max_iters=12, min_iters=4, tol=1e-3, discrete=False))
+    (HERE / "solves_extra.json").write_text(json.dumps(out, indent=1, sort_keys=True))
+
+
 def workflow():
     """view_factor_outside_workflow (api.py) and view_factor_matrix_and_sky (main.py:1209) on the canyon."""
     from raystrack import view_factor_outside_workflow
@@ -296,11 +329,13 @@ def shipped():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["stage", "solves", "shipped", "workflow"]
+    what = sys.argv[1:] or ["stage", "solves", "extra", "shipped", "workflow"]
     if "stage" in what:
         stage_vectors()
     if "solves" in what:
         solves()
+    if "extra" in what:
+        solves_extra()
     if "shipped" in what:
         shipped()
     if "workflow" in what:

@@ -6,12 +6,14 @@ def scene_for(case: str):
     tag = case[:2]
     if tag == "C1":
         return synthetic.parallel_unit_squares()
-    if tag in ("C2", "C3", "V0"):
+    if tag in ("C2", "C3", "V0", "X1", "X2"):
         return synthetic.street_canyon()
-    if tag == "C4":
+    if tag in ("C4", "X3"):
         return synthetic.unit_cube_enclosure()
-    if tag == "U3":
+    if tag in ("U3", "X4"):
         return synthetic.urban_block(3, 4, 8, 0)
+    if tag == "X5":
+        return synthetic.tilted_pair()
     raise KeyError(case)
 
 

@@ -177,7 +177,8 @@ def test_bvh_structure(ctx):
 
 SOLVE_CASES = ["C1_readme_squares", "C2_canyon_ex01", "C2b_canyon_delta_norecip", "C3_canyon_sky_discrete",
                "C3b_canyon_sky_merged", "C4_cube_ex04", "V06_canyon_view3d", "U3_urban_matrix_bvh",
-               "U3_urban_matrix_recip", "U3_urban_sky"]
+               "U3_urban_matrix_recip", "U3_urban_sky",
+               "X1_canyon_rowsum", "X2_canyon_sky_delta", "X3_cube_flip_bvh", "X4_urban_delta_recip", "X5_tilted_matrix", "X5_tilted_sky"]
 
 
 @pytest.mark.parametrize("case", SOLVE_CASES)

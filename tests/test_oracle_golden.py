@@ -87,7 +87,8 @@ def test_tregenza_patch_ids_bit_exact(stage):
 # reference is compiled with fastmath, the oracle evaluates in source order)
 @pytest.mark.parametrize("case", ["C1_readme_squares", "C2_canyon_ex01", "C2b_canyon_delta_norecip",
                                   "C3_canyon_sky_discrete", "C3b_canyon_sky_merged", "C4_cube_ex04",
-                                  "U3_urban_matrix_recip", "U3_urban_sky"])
+                                  "U3_urban_matrix_recip", "U3_urban_sky",
+                                  "X2_canyon_sky_delta", "X3_cube_flip_bvh", "X4_urban_delta_recip", "X5_tilted_matrix", "X5_tilted_sky"])
 def test_whole_solve_matches_reference(solves, case):
     g = solves[case]
     S = O.OracleSolver(scene_for(case))
@@ -96,9 +97,10 @@ def test_whole_solve_matches_reference(solves, case):
     res = S.view_factor_to_tregenza_sky(per_emitter=pe, **p) if "discrete" in p else S.view_factor_matrix(per_emitter=pe, **p)
     assert {k: v["iters"] for k, v in pe.items()} == g["iters"]
     for name, row in g["result"].items():
-        assert set(res[name]) == set(row)
-        for key, val in row.items():
-            assert abs(res[name][key] - val) <= 1e-5
+        # a key exists as soon as ONE ray hits that receiver side, so a near-tie ray may add or drop a key whose value
+        # is a single ray's weight; every value (absent = 0) must agree to 1e-5
+        for key in set(res[name]) | set(row):
+            assert abs(res[name].get(key, 0.0) - row.get(key, 0.0)) <= 1e-5, (name, key)
 
 
 def test_shipped_result_files(solves, shipped):
