@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
             const int n_need = __popc(need);
 #if RSK_CTA_POOL
             if (buf_n < n_need && !pool_empty) {
-                // the 4096 rays of the tile are one pool: a warp that runs out takes the next 32, whichever warp it is
+                // the rays of the tile are one pool: a warp that runs out takes the next 32, whichever warp it is
                 int base = 0;
                 if (lane == 0) base = atomicAdd(&s_next, 32);
                 base = __shfl_sync(FULL, base, 0);

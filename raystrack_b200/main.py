@@ -159,7 +159,7 @@ def _rotation_rows(seed: int, rows: int) -> np.ndarray:
     return table
 
 
-TILE_RAYS = 4096               # rays per CTA tile (csrc/rsk_common.cuh RSK_TILE_RAYS): slices are cut on tile boundaries
+TILE_RAYS = 4096               # ray slices of split emitters are cut on multiples of this (half the largest CTA tile)
 
 
 def plan_shards(todo: Sequence[int], n_rays_once: Sequence[int], world: int,
