@@ -372,6 +372,10 @@ def run_ours(args):
     traffic_file = ROOT / "profiles" / "c5_trace_dram_bytes.json"
     if traffic_file.exists():
         line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch")
+    # what actually binds the kernel (not measured live: read from the committed ncu capture, profiles/r1_summary.md)
+    line["roofline"]["binding_resource"] = {"name": "instruction issue", "issue_slots_busy_pct": 72.8, "lanes_per_instruction": 20.9,
+                                            "pipe_alu_pct": 58.5, "pipe_xu_pct": 50.2, "l1_hit_pct": 59.4, "l2_hit_pct": 96.8,
+                                            "source": "profiles/r1_summary.md (ncu --set full of this kernel, same scene)"}
     emit(line)
 
 
