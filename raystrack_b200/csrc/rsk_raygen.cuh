@@ -8,6 +8,17 @@
 #pragma once
 #include "rsk_common.cuh"
 
+// The five Halton values of a ray are read exactly once per iteration: RSK_HALTON_STREAM=1 loads them with the
+// evict-first policy (__ldcs) instead of the read-only path.
+#ifndef RSK_HALTON_STREAM
+#define RSK_HALTON_STREAM 0
+#endif
+#if RSK_HALTON_STREAM
+#define RSK_HLOAD(p) __ldcs(p)
+#else
+#define RSK_HLOAD(p) __ldg(p)
+#endif
+
 struct Ray {
     float ox, oy, oz;
     float dx, dy, dz;
@@ -39,10 +50,10 @@ __device__ __forceinline__ Ray rsk_make_ray(const EmitterView &ev, const Emitter
     const double vg = rsk_mod1((double)__fadd_rn(jit.y, cp[1]));                       // :55
     const float *h = ev.halton + k;
     const int64_t hs = ev.halton_stride;
-    const double q_tri = rsk_mod1((double)__fadd_rn(__ldg(h), cp[2]));                 // :57
+    const double q_tri = rsk_mod1((double)__fadd_rn(RSK_HLOAD(h), cp[2]));                 // :57
     const int tri = rsk_cdf_search(ev.cdf + e.tri_off, e.n_tri, q_tri);                // :58
-    const double ur = rsk_mod1(__dadd_rn((double)__fadd_rn(__ldg(h + hs), cp[3]), ug));     // :60
-    const double vr = rsk_mod1(__dadd_rn((double)__fadd_rn(__ldg(h + 2 * hs), cp[4]), vg)); // :61
+    const double ur = rsk_mod1(__dadd_rn((double)__fadd_rn(RSK_HLOAD(h + hs), cp[3]), ug));     // :60
+    const double vr = rsk_mod1(__dadd_rn((double)__fadd_rn(RSK_HLOAD(h + 2 * hs), cp[4]), vg)); // :61
     const double s = sqrt(ur);                                                         // :63
     const double mix_b = __dmul_rn(s, vr);
     const double mix_c = __dmul_rn(s, __dsub_rn(1.0, vr));
@@ -56,8 +67,8 @@ __device__ __forceinline__ Ray rsk_make_ray(const EmitterView &ev, const Emitter
     const double py = __dadd_rn(__dadd_rn((double)A.y, __dmul_rn(mix_b, (double)E1.y)), __dmul_rn(mix_c, (double)E2.y));
     const double pz = __dadd_rn(__dadd_rn((double)A.z, __dmul_rn(mix_b, (double)E1.z)), __dmul_rn(mix_c, (double)E2.z));
 
-    const double r1 = rsk_mod1((double)__fadd_rn(__ldg(h + 3 * hs), cp[5]));           // :75
-    const double r2 = rsk_mod1((double)__fadd_rn(__ldg(h + 4 * hs), cp[6]));           // :76
+    const double r1 = rsk_mod1((double)__fadd_rn(RSK_HLOAD(h + 3 * hs), cp[5]));           // :75
+    const double r2 = rsk_mod1((double)__fadd_rn(RSK_HLOAD(h + 4 * hs), cp[6]));           // :76
     const double sin_t = sqrt(__dsub_rn(1.0, r1));                                     // :78
     const double phi = __dmul_rn(6.283185307179586, r2);
     double sn, cs;

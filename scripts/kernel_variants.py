@@ -27,6 +27,10 @@ VARIANTS = {      # compile-time knobs of csrc/rsk_trace.cu(h) and csrc/rsk_bvh.
     "tris_at_once": ("RSK_POSTPONE=0",),
     "all_i2f_mask_shifts": ("RSK_PRMT_AXES=0", "RSK_MASK_PIN=0"),
     "prmt_x": ("RSK_PRMT_AXES=1",),
+    "halton_stream": ("RSK_HALTON_STREAM=1",),
+    "stack6": ("RSK_SMEM_STACK_N=6",),
+    "stack4": ("RSK_SMEM_STACK_N=4",),
+    "refill26": ("RSK_REFILL_BELOW=26",),
     "prmt_yz": ("RSK_PRMT_AXES=6",),
     "p6i3": ("RSK_POSTPONE=6", "RSK_POSTPONE_IDLE=3"),
     "p32i6": ("RSK_POSTPONE=32", "RSK_POSTPONE_IDLE=6"),
