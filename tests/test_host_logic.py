@@ -156,3 +156,83 @@ def test_reciprocity_write_back_split():
     R._write_back(res, ["a", "b"], Fp)
     assert res["a"] == {"b_front": 0.4, "b_back": 0.4} and res["b"] == {"a_back": pytest.approx(0.3)}
     assert np.array_equal(R._totals_matrix(res, ["a", "b"]), np.array([[0.0, 0.8], [0.3, 0.0]]))
+
+
+# --------------------------------------------------------------------------- host side of the device-side preparation
+
+def _emulated_summary(meshes, flip):
+    """What rsk_prepare_meshes_kernel returns (float64 statistics against the first triangle), computed with NumPy from
+    the host-prepared arrays; lets the host half of the device path be tested without a GPU."""
+    from raystrack_b200 import _native
+    from raystrack_b200.prepared import prepare_emitters
+    ems = prepare_emitters(meshes, samples=4, rays=4, flip_faces=flip)
+    S = np.zeros(len(meshes), _native.MESH_SUMMARY_DTYPE)
+    for i, e in enumerate(ems):
+        if e.tri_a.shape[0] == 0:
+            continue
+        n = e.tri_n.astype(np.float64)
+        n0, org = n[0], e.tri_a[0]
+        worst = mag = 0.0
+        for p in (e.tri_a, e.tri_a + e.tri_e1, e.tri_a + e.tri_e2):
+            d = (p - org).astype(np.float64) * n0
+            worst = max(worst, float(np.abs(d.sum(1)).max()))
+            mag = max(mag, float(np.abs(d).sum(1).max()))
+        S[i] = (e.total_area, org, e.tri_n[0], e.tri_origin_eps.max(), 0, (n @ n0).min(), worst, mag)
+    return ems, S
+
+
+@pytest.mark.parametrize("flip", [False, True])
+def test_summaries_from_device_reproduce_the_plane_records(flip):
+    from raystrack_b200 import synthetic
+    from raystrack_b200.prepared import device_plane_verdict, summaries_from_device
+    rng = np.random.default_rng(5)
+    meshes = synthetic.urban_block(2, 4, 4, 0) + synthetic.tilted_pair() + synthetic.unit_cube_enclosure()
+    meshes.append(("empty", np.zeros((0, 3)), np.zeros((0, 3), np.int64)))
+    meshes.append(("needle", np.array([[0, 0, 0], [1e-9, 0, 0], [0, 1e-9, 0]], np.float32), np.array([[0, 1, 2]])))
+    for i in range(24):                                     # tilted grids near and far from the origin, some slightly bent
+        scale = 3.0 if i % 2 else 600.0
+        name, V, F = synthetic.quad_grid(f"t{i}", tuple(rng.uniform(-scale, scale, 3)), tuple(rng.uniform(-2, 2, 3)),
+                                         tuple(rng.uniform(-2, 2, 3)), 6)
+        if i % 3 == 0:
+            V = V + (rng.standard_normal(V.shape) * 10.0 ** rng.uniform(-8, -4)).astype(V.dtype)
+        meshes.append((name, V, F))
+    ems, S = _emulated_summary(meshes, flip)
+    got = summaries_from_device(S, np.asarray([e.g for e in ems]), meshes, samples=4, rays=4, flip_faces=flip)
+    assert len(got) == len(ems)
+    for s, e in zip(got, ems):
+        assert s.plane_is_planar == e.plane_is_planar and s.plane_tol == e.plane_tol
+        assert s.total_area == e.total_area and s.g == e.g and s.n_cells == e.n_cells
+        assert np.array_equal(s.plane_origin.view(np.uint32), e.plane_origin.view(np.uint32))
+        assert np.array_equal(s.plane_normal.view(np.uint32), e.plane_normal.view(np.uint32))
+    verdicts = [device_plane_verdict(row, e.plane_tol) for row, e in zip(S, ems) if e.tri_a.shape[0]]
+    decided = [(v, e.plane_is_planar) for v, e in zip(verdicts, [e for e in ems if e.tri_a.shape[0]]) if v is not None]
+    assert decided and all(v == h for v, h in decided)       # the statistics never decide wrongly ...
+    assert any(v is None for v in verdicts)                  # ... and the fallback is exercised
+
+
+def test_flatten_meshes_layout_and_index_range():
+    from raystrack_b200.prepared import flatten_meshes
+    a = ("a", np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], np.float64), np.array([[0, 1, 2], [1, 3, -1]], np.int64))
+    b = ("b", np.zeros((0, 3)), np.zeros((0, 3), np.int64))
+    c = ("c", [[0, 0, 1], [1, 0, 1], [0, 1, 1]], [[0, 1, 2]])                         # plain lists, as load_meshes_json gives
+    verts, vo, faces, to = flatten_meshes([a, b, c])
+    assert verts.dtype == np.float32 and faces.dtype == np.int32 and verts.flags.c_contiguous and faces.flags.c_contiguous
+    assert vo.tolist() == [0, 4, 4, 7] and to.tolist() == [0, 2, 2, 3]
+    assert faces.tolist() == [[0, 1, 2], [1, 3, -1], [0, 1, 2]] and np.array_equal(verts[4:], np.asarray(c[1], np.float32))
+    assert [x.shape for x in flatten_meshes([])] == [(0, 3), (1,), (0, 3), (1,)]
+    with pytest.raises(IndexError):
+        flatten_meshes([("big", np.zeros((3, 3)), np.array([[0, 1, 2 ** 40]]))])
+
+
+def test_prepared_solver_mesh_bounds_match_per_mesh_loop():
+    from raystrack_b200 import synthetic
+    from raystrack_b200.prepared import PreparedSolver
+    for meshes in (synthetic.urban_block(2, 3, 4, 1), [("e", np.zeros((0, 3)), np.zeros((0, 3), np.int64))] + synthetic.tilted_pair()):
+        centers, extents = PreparedSolver(meshes).get_mesh_bounds()
+        for i, (_, V, _) in enumerate(meshes):
+            v = np.asarray(V, np.float32)
+            if v.size == 0:
+                assert not centers[i].any() and not extents[i].any()
+                continue
+            lo, hi = v.min(0), v.max(0)
+            assert np.array_equal(centers[i], (0.5 * (lo + hi)).astype(np.float32)) and np.array_equal(extents[i], (0.5 * (hi - lo)).astype(np.float32))
