@@ -250,6 +250,11 @@ int rsk_dual_sky_part(rsk_solve *solve, rsk_solve **sky);
 int rsk_solve_destroy(rsk_solve *solve);
 /* Rays traced so far by this solve (all emitters, all iterations). */
 int rsk_solve_rays_traced(rsk_solve *solve, int64_t *rays);
+/* Diagnostic work counters of the trace kernels since the last reset: out[0] node visits, [1] triangle tests,
+ * [2] triangles skipped by the surface mask, [3] rays, [4] triangle-flush trips, [5] stack pushes, [6..7] 0.  Counted
+ * only by builds with -DRSK_COUNTERS=1 (scripts/kernel_variants.py); the product build returns zeros.  The reference
+ * has no counterpart; SURVEY.md 8(d) measured the same quantities by instrumenting cpu_trace.py:120-277. */
+int rsk_trace_counters(rsk_ctx *ctx, int64_t *out, int32_t reset);
 
 /* ------------------------------------------------------------------------------------------- reciprocity
  * Replaces the dense core of enforce_reciprocity_and_rowsum (utils/helpers.py:70-96): G = 0.5*(A F + (A F)^T),

@@ -32,7 +32,7 @@ EXPORTS = (
     "rsk_matrix_begin", "rsk_matrix_step", "rsk_matrix_read", "rsk_solve_read_block", "rsk_matrix_device_tallies",
     "rsk_sky_begin", "rsk_sky_step", "rsk_sky_read", "rsk_dual_begin", "rsk_dual_begin_sliced", "rsk_dual_step", "rsk_dual_sky_part",
     "rsk_solve_enqueue_trace", "rsk_solve_enqueue_fold", "rsk_solve_poll", "rsk_solve_device_iter_tallies", "rsk_solve_set_iter_tally_buffer",
-    "rsk_solve_destroy", "rsk_solve_rays_traced", "rsk_reciprocity_rowsum",
+    "rsk_solve_destroy", "rsk_solve_rays_traced", "rsk_trace_counters", "rsk_reciprocity_rowsum",
 )
 
 
@@ -137,6 +137,13 @@ class Context:
         n = C.c_int64(0)
         check(self.lib.rsk_ctx_launch_count(self.handle, C.byref(n)))
         return int(n.value)
+
+    def trace_counters(self, reset: bool = True) -> dict:
+        """Work counters of the trace kernels (all zero unless the library is an RSK_COUNTERS=1 build)."""
+        out = (C.c_int64 * 8)()
+        check(self.lib.rsk_trace_counters(self.handle, out, C.c_int32(1 if reset else 0)))
+        names = ("node_visits", "tri_tests", "tri_masked", "rays", "flush_trips", "stack_pushes")
+        return {k: int(out[i]) for i, k in enumerate(names)}
 
     def device_info(self) -> dict:
         name = C.create_string_buffer(256)

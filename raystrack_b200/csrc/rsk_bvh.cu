@@ -281,7 +281,7 @@ __device__ __forceinline__ int quant_exp(float ext, int min_exp) {
         frexpf(ext / 255.0f, &k);     // ext/255 = m * 2^k, m in [0.5,1)  =>  2^k >= ext/255
         e = max(k, min_exp);
     }
-    return min(max(e, -126), 127);
+    return min(max(e, -126), 112);      // + 14 on RSK_PRMT_AXES axes must stay a finite float
 }
 
 __global__ void k_collapse(const CollapseArgs a) {
@@ -299,7 +299,7 @@ __global__ void k_collapse(const CollapseArgs a) {
     cand[0] = a.left[bnode];
     cand[1] = a.right[bnode];
     const bool bottom = sub_count(a, bnode) <= RSK_BOTTOM_MAX;
-    while (nc < RSK_FANOUT) {
+    while (nc < RSK_WIDE) {
         int best = -1;
         float best_score = -1.f;
         for (int c = 0; c < nc; ++c) {
@@ -335,7 +335,7 @@ __global__ void k_collapse(const CollapseArgs a) {
         for (int c = 0; c < nc; ++c) {
             if (slot_of[c] >= 0) continue;
             const float vx = 0.5f * (clo[c].x + chi[c].x) - ctr.x, vy = 0.5f * (clo[c].y + chi[c].y) - ctr.y, vz = 0.5f * (clo[c].z + chi[c].z) - ctr.z;
-            for (int s = 0; s < RSK_FANOUT; ++s) {
+            for (int s = 0; s < RSK_WIDE; ++s) {
                 if (child_in[s] >= 0) continue;
                 const float v = ((s & 1) ? vx : -vx) + ((s & 2) ? vy : -vy) + ((s & 4) ? vz : -vz);
                 if (v > bestv) { bestv = v; bc = c; bs = s; }
@@ -358,19 +358,20 @@ __global__ void k_collapse(const CollapseArgs a) {
     WideNode node;
     node.sid_min = __float_as_int(a.nlo[bnode].w);
     node.sid_max = __float_as_int(a.nhi[bnode].w);
-    node.reserved[0] = node.reserved[1] = 0u;
+    node.reserved = 0u;
     node.ox = lo.x; node.oy = lo.y; node.oz = lo.z;
     const int ex = quant_exp(hi.x - lo.x, a.min_exp), ey = quant_exp(hi.y - lo.y, a.min_exp), ez = quant_exp(hi.z - lo.z, a.min_exp);
-    node.ex = (uint8_t)(ex + 127); node.ey = (uint8_t)(ey + 127); node.ez = (uint8_t)(ez + 127);
+    node.scale[0] = exp2f((float)(ex + ((RSK_PRMT_AXES & 1) ? 14 : 0)));
+    node.scale[1] = exp2f((float)(ey + ((RSK_PRMT_AXES & 2) ? 14 : 0)));
+    node.scale[2] = exp2f((float)(ez + ((RSK_PRMT_AXES & 4) ? 14 : 0)));
     const float ix = exp2f((float)-ex), iy = exp2f((float)-ey), iz = exp2f((float)-ez);
-    node.imask = 0;
     node.child_base = (uint32_t)child_base;
     node.tri_base = (uint32_t)tri_base;
+    uint32_t imask = 0u, leaf_bits = 0u;
     int inner_rank = 0, tri_off = 0;
     for (int s = 0; s < RSK_WIDE; ++s) {
         const int c = child_in[s];
-        if (c < 0) {
-            node.meta[s] = 0;
+        if (c < 0) {        // empty slot: an inverted box no ray can enter, no bits
             for (int ax = 0; ax < 3; ++ax) { node.qlo[ax][s] = 255; node.qhi[ax][s] = 0; }
             continue;
         }
@@ -386,15 +387,15 @@ __global__ void k_collapse(const CollapseArgs a) {
             int tris[RSK_LEAF_MAX];
             sub_triangles(a, bn, tris);
             for (int t = 0; t < cnt; ++t) a.tri_order[tri_base + tri_off + t] = tris[t];
-            node.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | (unsigned)tri_off);
+            leaf_bits |= ((1u << cnt) - 1u) << (3 * s);
             tri_off += cnt;
         } else {
-            node.imask |= (uint8_t)(1u << s);
-            node.meta[s] = (uint8_t)(0x20u | (24u + s));
+            imask |= 1u << s;
             a.queue_out[out_base + inner_rank] = make_int2(bn, child_base + inner_rank);
             inner_rank++;
         }
     }
+    node.leaf_imask = leaf_bits | (imask << 24);
     a.nodes[widx] = node;
 }
 
@@ -430,11 +431,11 @@ __global__ void k_tiny_root(const float4 *tlo, const float4 *thi, int n, WideNod
     node.sid_max = smax;
     node.ox = lo.x; node.oy = lo.y; node.oz = lo.z;
     const int e[3] = {quant_exp(hi.x - lo.x, min_exp), quant_exp(hi.y - lo.y, min_exp), quant_exp(hi.z - lo.z, min_exp)};
-    node.ex = (uint8_t)(e[0] + 127); node.ey = (uint8_t)(e[1] + 127); node.ez = (uint8_t)(e[2] + 127);
+    for (int ax = 0; ax < 3; ++ax) node.scale[ax] = exp2f((float)(e[ax] + (((RSK_PRMT_AXES >> ax) & 1) ? 14 : 0)));
     for (int s = 0; s < RSK_WIDE; ++s)
         for (int ax = 0; ax < 3; ++ax) { node.qlo[ax][s] = 255; node.qhi[ax][s] = 0; }
     for (int ax = 0; ax < 3; ++ax) { node.qlo[ax][0] = 0; node.qhi[ax][0] = 255; }
-    node.meta[0] = (uint8_t)((((1u << n) - 1u) << 5) | 0u);
+    node.leaf_imask = (1u << n) - 1u;      // slot 0: a leaf with every triangle
     nodes[0] = node;
 }
 

@@ -51,14 +51,21 @@ constexpr int RSK_TILE_RAYS_MAX = 8192;    // rays per CTA tile: chosen per laun
 constexpr int RSK_TREGENZA_BINS = 145;     // utils/cuda_trace.py:12
 constexpr float RSK_INF = 1.0e20f;         // utils/cpu_trace.py:8
 constexpr int RSK_WIDE = 8;                // slots of a wide node
-#ifndef RSK_FANOUT
-#define RSK_FANOUT 8                        // children actually used per node (8, or 4 = slots 0..3 only: experiment)
-#endif
 #ifndef RSK_LEAF_MAX_TRIS
 #define RSK_LEAF_MAX_TRIS 3
 #endif
-constexpr int RSK_LEAF_MAX = RSK_LEAF_MAX_TRIS;   // triangles per leaf child (<= 3: 24 triangle bits per node)
+constexpr int RSK_LEAF_MAX = RSK_LEAF_MAX_TRIS;   // triangles per leaf child (<= 3: three triangle bits per slot)
 constexpr int RSK_MAX_DEPTH_HOST = 32;     // traversal stack entries per ray (wide-tree depth limit)
+
+// How the quantised plane bytes of a node become ray parameters, per axis (bit a set = axis a):
+//   bit clear: t = float(byte) * (cell / d) + (origin - o) / d                 -- one I2F (XU pipe) + FFMA per plane
+//   bit set:   one PRMT drops the byte into mantissa bits 8..15 of the float 2.0, f = 2 + byte * 2^-14 exactly;
+//              t = f * (cell * 2^14 / d) + ((origin - o) / d - 2 * cell * 2^14 / d)  -- PRMT (ALU pipe) + FFMA, no XU
+// The builder stores the matching per-axis scale (cell, or cell * 2^14) in the node, so the kernel and rsk_bvh.cu
+// share this constant.
+#ifndef RSK_PRMT_AXES
+#define RSK_PRMT_AXES 4       // z planes through PRMT, x and y through I2F (balances the XU and ALU pipes)
+#endif
 
 // One emitter mesh.  Triangle rows live in EmitterSet::tri[5][*] starting at tri_off.
 struct EmitterDesc {
@@ -69,19 +76,25 @@ struct EmitterDesc {
     int64_t n_rays_once;     // g*g*rays_per_cell
 };
 
-// 96-byte compressed 8-wide BVH node (six 16-byte words, 32-byte aligned): the 80-byte compressed-wide-BVH record
-// plus the range of mesh ids below the node, which lets a ray drop whole sub-trees of surfaces it must ignore.
-struct __align__(16) WideNode {
+// 96-byte compressed 8-wide BVH node: three 32-byte sectors, fetched with three LDG.256.
+//   sector 0  everything the walk needs besides the boxes: quantisation origin, first inner child, first triangle,
+//             which slots hold inner nodes (imask) / how many triangles each leaf slot holds (leaf_bits), and the
+//             range of mesh ids below the node (lets a ray drop whole sub-trees of surfaces it must ignore)
+//   sector 1  low planes x, y, z and high planes x of the 8 child boxes, one byte per slot
+//   sector 2  high planes y, z; per-axis scale of the byte grid (RSK_PRMT_AXES picks cell or cell * 2^14)
+// Slot s is an inner node when bit s of imask is set (inner children are contiguous from child_base, in slot order);
+// otherwise bits 3s..3s+2 of leaf_bits hold its triangle count in unary (0 = empty slot).  The triangles of a node
+// are contiguous from tri_base in slot order: triangle bit b is triangle tri_base + popc(leaf_bits & ((1 << b) - 1)).
+struct __align__(32) WideNode {
     float ox, oy, oz;        // quantisation origin = node box minimum
-    uint8_t ex, ey, ez;      // biased float exponents: cell size = 2^(e-127) per axis
-    uint8_t imask;           // bit s: slot s holds an inner node
-    uint32_t child_base;     // index of the first inner child (inner children contiguous, slot order)
+    uint32_t child_base;     // index of the first inner child
     uint32_t tri_base;       // index of the first triangle referenced by this node's leaf children
-    uint8_t meta[8];         // inner: 0x20|(24+s); leaf: (unary tri count)<<5 | first tri bit; empty: 0
+    uint32_t leaf_imask;     // leaf_bits (24 bits) | imask << 24
+    int32_t sid_min, sid_max;   // smallest / largest mesh id of the triangles below this node
     uint8_t qlo[3][8];       // quantised child boxes, [axis][slot]
     uint8_t qhi[3][8];
-    int32_t sid_min, sid_max;   // smallest / largest mesh id of the triangles below this node
-    uint32_t reserved[2];
+    float scale[3];          // per axis: cell size 2^e, times 2^14 on RSK_PRMT_AXES axes
+    uint32_t reserved;
 };
 static_assert(sizeof(WideNode) == 96, "WideNode must be 96 bytes");
 constexpr int RSK_NODE_WORDS = sizeof(WideNode) / 16;

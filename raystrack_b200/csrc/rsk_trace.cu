@@ -11,26 +11,34 @@
 
 
 constexpr unsigned FULL = 0xffffffffu;
+// RSK_COUNTERS=1 (diagnostic builds, scripts/kernel_variants.py): per-launch work counters read with rsk_trace_counters --
+// [0] node visits, [1] triangle tests, [2] triangles skipped by the surface mask, [3] rays, [4] triangle-flush trips,
+// [5] stack pushes.  The product build compiles them out.
+#ifndef RSK_COUNTERS
+#define RSK_COUNTERS 0
+#endif
+__device__ unsigned long long rsk_work_counters[8];
+#if RSK_COUNTERS
+#define RSK_COUNT(i) (++cnt[i])
+#else
+#define RSK_COUNT(i) ((void)0)
+#endif
 #ifndef RSK_MIN_CTAS_PER_SM
 #define RSK_MIN_CTAS_PER_SM 4
 #endif
-#ifndef RSK_RAY_BUFFER
-#define RSK_RAY_BUFFER 1
-#endif
-#ifndef RSK_CTA_POOL
-#define RSK_CTA_POOL 1        // needs RSK_RAY_BUFFER
-#endif
 #ifndef RSK_POSTPONE
-#define RSK_POSTPONE 10       // closest-hit walks test their pending triangle groups once this many lanes hold one (0: at once)
+#define RSK_POSTPONE 10       // closest-hit walks test their pending triangle groups once this many lanes hold one
 #endif
 #ifndef RSK_POSTPONE_IDLE
 #define RSK_POSTPONE_IDLE 4   // ... or once this many lanes have nothing else to do
 #endif
 #ifndef RSK_REFILL_BELOW
-#define RSK_REFILL_BELOW 24     // with the warp-wide ray buffer a refill is cheap: 24-27 measured best, 20 without it
+#define RSK_REFILL_BELOW 24   // leave the traversal loop to fetch new rays when fewer lanes are busy (24-27 measured best)
 #endif
 constexpr int RSK_MIN_CTAS = RSK_MIN_CTAS_PER_SM;   // 4 CTAs x 256 threads per SM -> at most 64 registers per thread
-constexpr int REFILL_BELOW = RSK_REFILL_BELOW;     // leave the traversal loop to fetch new rays when fewer lanes are busy
+constexpr int REFILL_BELOW = RSK_REFILL_BELOW;
+constexpr int RAY_SLOTS = 64;                       // per-warp ray buffer: a top-up adds <= 32 rays to < 32 leftovers
+constexpr uint32_t STACK_STRIDE = RSK_TILE_THREADS * sizeof(uint2);      // bytes between two stack levels of a thread
 
 
 // Result bin of a finished ray, -1 = nothing to tally.  Matrix bins: 2*receiver + (front ? 0 : 1) (cpu_trace.py:114);
@@ -64,6 +72,34 @@ __device__ __forceinline__ void rsk_debug_store(const TraceArgs &a, int64_t k, c
     }
 }
 
+// One step of the wide-BVH walk up to the node test: pop a node group when the current one is used up, pick the
+// nearest inner child still to visit, push the rest of the group.  Returns false when the walk has nothing left;
+// otherwise `node` is the node to test.  Stack entries 0..RSK_SMEM_STACK-1 of a thread live in shared memory and are
+// accessed with predicated loads/stores (no branch: the lanes of a warp that pop, push or do neither stay converged);
+// deeper entries spill to local memory on a rarely taken path.
+__device__ __forceinline__ bool rsk_walk_next(Walk &w, uint32_t stack_base, uint2 *spill, uint32_t &node) {
+    const uint32_t smem_end = stack_base + RSK_SMEM_STACK * STACK_STRIDE;
+    const bool used_up = w.ng.y <= 0x00ffffffu;
+    const bool bottom = w.sp == stack_base;
+    const bool pop = used_up && !bottom;
+    if (pop) w.sp -= STACK_STRIDE;
+    rsk_lds64_if(w.sp, pop && w.sp < smem_end, w.ng);
+    if (pop && w.sp >= smem_end) w.ng = spill[(w.sp - smem_end) / STACK_STRIDE];
+    if (used_up && bottom) return false;
+    const int bit = 31 - __clz(w.ng.y);
+    w.ng.y &= ~(1u << bit);
+    const uint32_t slot = (uint32_t)(bit - 24) ^ w.octinv;
+    node = w.ng.x + __popc(w.ng.y & 0xffu & ((1u << slot) - 1u));
+    const bool push = w.ng.y > 0x00ffffffu;
+    rsk_sts64_if(w.sp, push && w.sp < smem_end, w.ng);
+    if (push && w.sp >= smem_end) {
+        const uint32_t level = (w.sp - smem_end) / STACK_STRIDE;
+        if (level < RSK_LOCAL_STACK) spill[level] = w.ng;
+    }
+    if (push && w.sp < stack_base + RSK_MAX_DEPTH * STACK_STRIDE) w.sp += STACK_STRIDE;
+    return true;
+}
+
 // MODE_MATRIX: closest hit among the receivers of the job.  MODE_SKY: any hit among the active non-emitter meshes,
 // misses binned by direction.  MODE_DUAL: both from one traversal (reference trace_cpu_[bvh_]combined,
 // cpu_trace.py:280-522): the closest receiver hit bounds the walk, every hit of an active mesh marks the ray as
@@ -71,9 +107,9 @@ __device__ __forceinline__ void rsk_debug_store(const TraceArgs &a, int64_t k, c
 // reference's shared-ray loop does (main.py:1380-1547).
 template <int MODE, bool BVH>
 __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kernel(const TraceArgs a) {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];
     __shared__ int s_job;
-    __shared__ int s_next;      // next unclaimed ray of the tile (RSK_CTA_POOL)
+    __shared__ int s_next;      // next unclaimed ray of the tile
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {           // job lookup: last k with tile_start[k] <= blockIdx.x
@@ -109,15 +145,15 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
         for (int i = 0; i < 7; ++i) cp[i] = __ldg(row + i);
     }
 
-    // shared memory: [traversal stacks][ray buffers][occluder mask][receiver mask (dual only)][histogram]
+    // shared memory: [traversal stacks][priority table][ray buffers][occluder mask][receiver mask (dual only)][histogram]
     // (the fixed-size parts come first, so the addresses the walk loop uses are compile-time offsets)
     constexpr int STACK_WORDS = BVH ? RSK_SMEM_STACK * RSK_TILE_THREADS * 2 : 0;
-    constexpr int RAY_WORDS = RSK_RAY_BUFFER ? (RSK_TILE_THREADS / 32) * 7 * 64 : 0;
+    constexpr int LUT_WORDS = BVH ? RSK_PERM_LUT_BYTES / 4 : 0;
+    constexpr int RAY_WORDS = (RSK_TILE_THREADS / 32) * 7 * RAY_SLOTS;
     const int mw = a.sc.mask_words;
     const int n_hist_all = a.n_hist + (MODE == MODE_DUAL ? a.n_hist2 : 0);
-    uint2 *s_stack = reinterpret_cast<uint2 *>(smem);
-    uint32_t *s_mask = smem + STACK_WORDS + RAY_WORDS;         // surfaces that stop / receive rays
-    uint32_t *s_recv = MODE == MODE_DUAL ? s_mask + mw : s_mask;   // surfaces the matrix may tally
+    uint32_t *s_mask = smem + STACK_WORDS + LUT_WORDS + RAY_WORDS;     // surfaces that stop / receive rays
+    uint32_t *s_recv = MODE == MODE_DUAL ? s_mask + mw : s_mask;       // surfaces the matrix may tally
     uint32_t *s_hist = s_mask + (MODE == MODE_DUAL ? 2 * mw : mw);
     const int hist_words = a.hist_in_smem ? n_hist_all : 0;
     {
@@ -129,39 +165,51 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
         }
     }
     for (int i = tid; i < hist_words; i += RSK_TILE_THREADS) s_hist[i] = 0;
+    if (BVH) rsk_build_perm_lut(reinterpret_cast<uint8_t *>(smem + STACK_WORDS), tid);
     __syncthreads();
+    const uint32_t stack_base = rsk_smem_addr(smem) + tid * (uint32_t)sizeof(uint2);
+    const uint32_t lut_base = rsk_smem_addr(smem + STACK_WORDS);
+    const uint32_t mask_addr = rsk_smem_addr(s_mask), recv_addr = rsk_smem_addr(s_recv);
 
     const int job_min_sid = (a.min_sid && !(MODE == MODE_DUAL && want_s)) ? a.min_sid[job] : 0;
     unsigned long long *g_tally = a.tally ? a.tally + (int64_t)job * a.n_hist : nullptr;
     unsigned long long *g_tally2 = (MODE == MODE_DUAL && a.tally2) ? a.tally2 + (int64_t)job * a.n_hist2 : nullptr;
     const int sky_base = MODE == MODE_DUAL ? a.n_hist : 0;
     const int n_sky = MODE == MODE_DUAL ? a.n_hist2 : a.n_hist;
+    const bool debug_out = MODE != MODE_DUAL && (a.dbg_hit || a.dbg_orig || a.dbg_dirs || a.dbg_front);
 
     const int tile_n = (int)(end - begin);
-#if !(RSK_RAY_BUFFER && RSK_CTA_POOL)
-    // fixed slices: each warp owns tile_rays/8 consecutive rays of the tile and hands them to its lanes on demand
-    const int WARP_RAYS = a.tile_rays / (RSK_TILE_THREADS / 32);
-    int next = warp * WARP_RAYS;
-    const int wend = min(next + WARP_RAYS, tile_n);
-#endif
-
-#if RSK_RAY_BUFFER
-    constexpr int RAY_SLOTS = 64;        // a top-up adds <= 32 rays to < 32 leftovers
-    float *s_rays = reinterpret_cast<float *>(smem + STACK_WORDS) + warp * (7 * RAY_SLOTS);
+    float *s_rays = reinterpret_cast<float *>(smem + STACK_WORDS + LUT_WORDS) + warp * (7 * RAY_SLOTS);
     int buf_n = 0;
-#if RSK_CTA_POOL
     bool pool_empty = tile_n <= 0;
-#endif
-#endif
     Walk w;
     bool active = false;
     bool any_hit = false;     // the current ray has met an occluder (sky / dual modes); lives as long as the ray
     int key = -1;             // finished-ray result waiting to be tallied
-#if RSK_POSTPONE
-    uint2 ptg = make_uint2(0u, 0u);   // triangle group found but not tested yet (lives as long as the ray)
-#endif
-    int64_t my_k = 0;
+    TriGroup ptg = {0u, 0u, 0u};   // triangle group found but not tested yet (lives as long as the ray)
+    int my_pos = 0;           // the current ray is ray begin + my_pos of the emitter
     uint2 spill[BVH ? RSK_LOCAL_STACK : 1];
+#if RSK_COUNTERS
+    unsigned cnt[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+#endif
+
+    // One triangle of a pending group against the current ray (Moeller-Trumbore, cpu_trace.py:88-114).  Returns true
+    // when the ray is settled by it (sky-only walks stop at the first hit).
+    auto test_triangle = [&](int tri) -> bool {
+        const float4 *tp = a.sc.tri + 3 * (int64_t)tri;
+        const float4 V0 = __ldg(tp), E1 = __ldg(tp + 1), E2 = __ldg(tp + 2);
+        const int sid = __float_as_int(V0.w);
+        if (!rsk_surface_on_s(mask_addr, sid)) { RSK_COUNT(2); return false; }
+        RSK_COUNT(1);
+        float t;
+        if (!rsk_tri_hit(V0, E1, E2, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, t) || !(t > 1e-6f)) return false;
+        if (want_s) {
+            any_hit = true;
+            if (!want_m) return true;
+        }
+        if (want_m && t < w.best && (MODE != MODE_DUAL || rsk_surface_on_s(recv_addr, sid))) { w.best = t; w.best_tri = tri; }
+        return false;
+    };
 
     for (;;) {
         // ---- warp-aggregated tally of the rays finished since the last refill
@@ -175,14 +223,12 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
             }
             key = -1;
         }
-        // ---- refill idle lanes with fresh rays
+        // ---- refill idle lanes with fresh rays.  Rays are generated 32 at a time by the whole warp (the float64
+        // sampler then runs with every lane busy and the Halton rows are read coalesced) into a small per-warp buffer;
+        // idle lanes take their next ray from it.
         const unsigned need = __ballot_sync(FULL, !active);
-#if RSK_RAY_BUFFER
-        // Rays are generated 32 at a time by the whole warp (the float64 sampler then runs with every lane busy and
-        // the Halton rows are read coalesced) into a small per-warp buffer; idle lanes take their next ray from it.
         if (need) {
             const int n_need = __popc(need);
-#if RSK_CTA_POOL
             if (buf_n < n_need && !pool_empty) {
                 // the rays of the tile are one pool: a warp that runs out takes the next 32, whichever warp it is
                 int base = 0;
@@ -191,26 +237,13 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
                 const int made = max(0, min(32, tile_n - base));
                 if (lane < made) {
                     const int pos = base + lane;
-#else
-            if (buf_n < n_need && next < wend) {
-                const int made = min(32, wend - next);
-                {
-                    const int pos = next + lane;
-                    if (pos < wend) {
-#endif
                     const Ray r = rsk_make_ray(a.ev, e, begin + pos, cp);
                     float *slot = s_rays + buf_n + lane;
                     slot[0 * RAY_SLOTS] = r.ox; slot[1 * RAY_SLOTS] = r.oy; slot[2 * RAY_SLOTS] = r.oz;
                     slot[3 * RAY_SLOTS] = r.dx; slot[4 * RAY_SLOTS] = r.dy; slot[5 * RAY_SLOTS] = r.dz;
                     slot[6 * RAY_SLOTS] = __int_as_float(pos);
-#if RSK_CTA_POOL
                 }
                 pool_empty = base + 32 >= tile_n;
-#else
-                    }
-                }
-                next += made;
-#endif
                 buf_n += made;
                 __syncwarp();
             }
@@ -220,102 +253,53 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
                 Ray r;
                 r.ox = slot[0 * RAY_SLOTS]; r.oy = slot[1 * RAY_SLOTS]; r.oz = slot[2 * RAY_SLOTS];
                 r.dx = slot[3 * RAY_SLOTS]; r.dy = slot[4 * RAY_SLOTS]; r.dz = slot[5 * RAY_SLOTS];
-                my_k = begin + __float_as_int(slot[6 * RAY_SLOTS]);
-                rsk_walk_begin(w, r);
+                my_pos = __float_as_int(slot[6 * RAY_SLOTS]);
+                rsk_walk_begin(w, r, stack_base, lut_base);
+                RSK_COUNT(3);
                 active = true;
                 any_hit = false;
-#if RSK_POSTPONE
-                ptg.y = 0u;
-#endif
+                ptg.hits = 0u;
             }
             buf_n -= min(n_need, buf_n);
         }
         if (!__any_sync(FULL, active)) break;
-#if RSK_CTA_POOL
         const bool rays_left = buf_n > 0 || !pool_empty;
-#else
-        const bool rays_left = buf_n > 0 || next < wend;
-#endif
-#else
-        if (need) {
-            const int pos = next + __popc(need & ((1u << lane) - 1u));
-            if (!active && pos < wend) {
-                my_k = begin + pos;
-                const Ray r = rsk_make_ray(a.ev, e, my_k, cp);
-                rsk_walk_begin(w, r);
-                active = true;
-                any_hit = false;
-#if RSK_POSTPONE
-                ptg.y = 0u;
-#endif
-            }
-            next += __popc(need);
-        }
-        if (!__any_sync(FULL, active)) break;
-        const bool rays_left = next < wend;
-#endif
 
-        if (BVH) {
-            // ---- 8-wide BVH walk, one node step per loop trip.
-#if RSK_POSTPONE
-          if (MODE != MODE_SKY) {
-            // Closest hit: the triangles a node step uncovers are kept as one pending group per lane while the lane
-            // goes on stepping nodes (culling with a slightly stale closest hit); the warp tests the pending groups
-            // together once RSK_POSTPONE lanes hold one, a lane holds two, or RSK_POSTPONE_IDLE lanes have nothing
-            // else to do.  Tested at once, the triangle loop runs one or two lanes wide on nearly every trip (25 % of
-            // the issued instructions); batched it is +8 % rays/s.  (Postponing until the whole warp reconverges,
-            // "while-while", is 30 % slower: lanes idle through other lanes' node steps.)
+        if (BVH && MODE != MODE_SKY) {
+            // ---- closest hit: 8-wide BVH walk, one node step per loop trip.  The triangles a node step uncovers are
+            // kept as one pending group per lane while the lane goes on stepping nodes (culling with a slightly stale
+            // closest hit); the warp tests the pending groups together once RSK_POSTPONE lanes hold one, a lane holds
+            // two, or RSK_POSTPONE_IDLE lanes have nothing else to do.  Tested at once, the triangle loop runs one or
+            // two lanes wide on nearly every trip (25 % of the issued instructions); batched it is +8 % rays/s.
+            // (Postponing until the whole warp reconverges, "while-while", is 30 % slower: lanes idle through other
+            // lanes' node steps.)
             bool done = false;
             const int flush_at = want_m ? RSK_POSTPONE : 1;
             while (active) {
-                bool more = true;
-                if (w.ng.y <= 0x00ffffffu) {
-                    if (w.sp == 0) more = false;
-                    else {
-                        --w.sp;
-                        w.ng = w.sp < RSK_SMEM_STACK ? s_stack[w.sp * RSK_TILE_THREADS + tid] : spill[w.sp - RSK_SMEM_STACK];
-                    }
-                }
-                uint2 tg = make_uint2(0u, 0u);
+                uint32_t node;
+                const bool more = rsk_walk_next(w, stack_base, spill, node);
+                TriGroup tg = {0u, 0u, 0u};
                 if (more) {
-                    const int bit = 31 - __clz(w.ng.y);
-                    w.ng.y &= ~(1u << bit);
-                    const uint32_t slot = (uint32_t)(bit - 24) ^ w.octinv;
-                    const uint32_t node = w.ng.x + __popc(w.ng.y & 0xffu & ((1u << slot) - 1u));
-                    if (w.ng.y > 0x00ffffffu) {
-                        if (w.sp < RSK_SMEM_STACK) s_stack[w.sp * RSK_TILE_THREADS + tid] = w.ng;
-                        else if (w.sp < RSK_MAX_DEPTH) spill[w.sp - RSK_SMEM_STACK] = w.ng;
-                        if (w.sp < RSK_MAX_DEPTH) ++w.sp;
-                    }
+                    RSK_COUNT(0);
                     uint2 ng2;
-                    rsk_test_node(a.sc.nodes, node, w, want_m ? w.best : RSK_INF, ng2, tg, s_mask, job_min_sid);
+                    rsk_test_node(a.sc.nodes, node, w, want_m ? w.best : RSK_INF, ng2, tg, mask_addr, job_min_sid);
                     w.ng = ng2;
                 }
-                if (!ptg.y) { ptg = tg; tg.y = 0u; }
+                if (!ptg.hits) { ptg = tg; tg.hits = 0u; }
                 const unsigned in_loop = __activemask();
-                const unsigned pend = __ballot_sync(in_loop, ptg.y != 0u);
-                const unsigned full = __ballot_sync(in_loop, tg.y != 0u);
+                const unsigned pend = __ballot_sync(in_loop, ptg.hits != 0u);
+                const unsigned full = __ballot_sync(in_loop, tg.hits != 0u);
                 const unsigned idle = __ballot_sync(in_loop, !more);
                 if (__popc(pend) >= flush_at || full || __popc(idle) >= RSK_POSTPONE_IDLE || idle == in_loop) {
-                    while (ptg.y) {
-                        const int b = __ffs(ptg.y) - 1;
-                        ptg.y &= ptg.y - 1u;
-                        const int tri = (int)(ptg.x + b);
-                        const float4 *tp = a.sc.tri + 3 * (int64_t)tri;
-                        const float4 V0 = __ldg(tp), E1 = __ldg(tp + 1), E2 = __ldg(tp + 2);
-                        const int sid = __float_as_int(V0.w);
-                        if (!rsk_surface_on(s_mask, sid)) continue;
-                        float t;
-                        if (!rsk_tri_hit(V0, E1, E2, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, t) || !(t > 1e-6f)) continue;
-                        if (want_s) {
-                            any_hit = true;
-                            if (!want_m) { ptg.y = 0u; break; }
-                        }
-                        if (want_m && t < w.best && (MODE != MODE_DUAL || rsk_surface_on(s_recv, sid))) { w.best = t; w.best_tri = tri; }
+                    if (ptg.hits) RSK_COUNT(4);
+                    while (ptg.hits) {
+                        const int b = __ffs(ptg.hits) - 1;
+                        ptg.hits &= ptg.hits - 1u;
+                        if (test_triangle((int)(ptg.base + __popc(ptg.leaf_bits & ((1u << b) - 1u))))) { ptg.hits = 0u; break; }
                     }
-                    if (tg.y) ptg = tg;
+                    if (tg.hits) ptg = tg;
                 }
-                if ((any_hit && !want_m) || (w.ng.y <= 0x00ffffffu && w.sp == 0 && !ptg.y)) {
+                if ((any_hit && !want_m) || (w.ng.y <= 0x00ffffffu && w.sp == stack_base && !ptg.hits)) {
                     done = true;
                     active = false;
                     break;
@@ -324,86 +308,55 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
             }
             if (done) {      // the rays finished during these trips are classified together, after the loop has reconverged
                 key = rsk_result_key(a, w, want_m, want_s, any_hit, sky_base, n_sky);
-                if (MODE != MODE_DUAL && (a.dbg_hit || a.dbg_orig || a.dbg_dirs || a.dbg_front)) rsk_debug_store<MODE>(a, my_k, w, key, any_hit);
+                if (debug_out) rsk_debug_store<MODE>(a, begin + my_pos, w, key, any_hit);
             }
-          } else
-#endif
-          {
-            // Any hit (and the RSK_POSTPONE=0 build): the triangles a step uncovers are tested at once.
+        } else if (BVH) {
+            // ---- any hit: the triangles a step uncovers are tested at once (a ray ends at its first hit, so postponing
+            // only adds node steps: 3.53 vs 3.71 Grays/s)
             while (active) {
-                bool finished = false;
-                if (w.ng.y <= 0x00ffffffu) {
-                    if (w.sp == 0) finished = true;
-                    else {
-                        --w.sp;
-                        w.ng = w.sp < RSK_SMEM_STACK ? s_stack[w.sp * RSK_TILE_THREADS + tid] : spill[w.sp - RSK_SMEM_STACK];
-                    }
-                }
+                uint32_t node;
+                bool finished = !rsk_walk_next(w, stack_base, spill, node);
                 if (!finished) {
-                    const int bit = 31 - __clz(w.ng.y);
-                    w.ng.y &= ~(1u << bit);
-                    const uint32_t slot = (uint32_t)(bit - 24) ^ w.octinv;
-                    const uint32_t node = w.ng.x + __popc(w.ng.y & 0xffu & ((1u << slot) - 1u));
-                    if (w.ng.y > 0x00ffffffu) {
-                        if (w.sp < RSK_SMEM_STACK) s_stack[w.sp * RSK_TILE_THREADS + tid] = w.ng;
-                        else if (w.sp < RSK_MAX_DEPTH) spill[w.sp - RSK_SMEM_STACK] = w.ng;
-                        if (w.sp < RSK_MAX_DEPTH) ++w.sp;
-                    }
-                    uint2 ng2, tg;
-                    rsk_test_node(a.sc.nodes, node, w, want_m ? w.best : RSK_INF, ng2, tg, s_mask, job_min_sid);
-                    while (tg.y) {
-                        const int b = __ffs(tg.y) - 1;
-                        tg.y &= tg.y - 1u;
-                        const int tri = (int)(tg.x + b);
-                        const float4 *tp = a.sc.tri + 3 * (int64_t)tri;
-                        const float4 V0 = __ldg(tp), E1 = __ldg(tp + 1), E2 = __ldg(tp + 2);
-                        const int sid = __float_as_int(V0.w);
-                        if (!rsk_surface_on(s_mask, sid)) continue;
-                        float t;
-                        if (!rsk_tri_hit(V0, E1, E2, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, t) || !(t > 1e-6f)) continue;
-                        if (want_s) {
-                            any_hit = true;
-                            if (!want_m) break;                       // sky only: the first hit settles the ray
-                        }
-                        if (want_m && t < w.best && (MODE != MODE_DUAL || rsk_surface_on(s_recv, sid))) { w.best = t; w.best_tri = tri; }
-                    }
+                    RSK_COUNT(0);
+                    uint2 ng2;
+                    TriGroup tg;
+                    rsk_test_node(a.sc.nodes, node, w, RSK_INF, ng2, tg, mask_addr, job_min_sid);
                     w.ng = ng2;
-                    if (any_hit && !want_m) finished = true;
+                    while (tg.hits) {
+                        const int b = __ffs(tg.hits) - 1;
+                        tg.hits &= tg.hits - 1u;
+                        if (test_triangle((int)(tg.base + __popc(tg.leaf_bits & ((1u << b) - 1u))))) { finished = true; break; }
+                    }
                 }
                 if (finished) {
                     key = rsk_result_key(a, w, want_m, want_s, any_hit, sky_base, n_sky);
-                    if (MODE != MODE_DUAL && (a.dbg_hit || a.dbg_orig || a.dbg_dirs || a.dbg_front)) rsk_debug_store<MODE>(a, my_k, w, key, any_hit);
+                    if (debug_out) rsk_debug_store<MODE>(a, begin + my_pos, w, key, any_hit);
                     active = false;
                     break;
                 }
                 if (rays_left && __popc(__activemask()) < REFILL_BELOW) break;
             }
-          }
         } else {
             // ---- no BVH: every triangle in input order, strict t<best (utils/cpu_trace.py:54-117, 280-352, 540-583)
             if (active) {
-                for (int tri = 0; tri < a.sc.n_tri; ++tri) {
-                    const float4 *tp = a.sc.tri + 3 * (int64_t)tri;
-                    const float4 V0 = __ldg(tp);
-                    const int sid = __float_as_int(V0.w);
-                    if (!rsk_surface_on(s_mask, sid)) continue;
-                    const float4 E1 = __ldg(tp + 1), E2 = __ldg(tp + 2);
-                    float t;
-                    if (!rsk_tri_hit(V0, E1, E2, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, t) || !(t > 1e-6f)) continue;
-                    if (want_s) {
-                        any_hit = true;
-                        if (!want_m) break;
-                    }
-                    if (want_m && t < w.best && (MODE != MODE_DUAL || rsk_surface_on(s_recv, sid))) { w.best = t; w.best_tri = tri; }
-                }
+                for (int tri = 0; tri < a.sc.n_tri; ++tri)
+                    if (test_triangle(tri)) break;
                 key = rsk_result_key(a, w, want_m, want_s, any_hit, sky_base, n_sky);
-                if (MODE != MODE_DUAL && (a.dbg_hit || a.dbg_orig || a.dbg_dirs || a.dbg_front)) rsk_debug_store<MODE>(a, my_k, w, key, any_hit);
+                if (debug_out) rsk_debug_store<MODE>(a, begin + my_pos, w, key, any_hit);
                 active = false;
             }
         }
         __syncwarp();
     }
 
+#if RSK_COUNTERS
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        unsigned v = cnt[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == 0 && v) atomicAdd(&rsk_work_counters[i], (unsigned long long)v);
+    }
+#endif
     // ---- flush the CTA histogram: one global atomic per touched bin
     if (a.hist_in_smem) {
         __syncthreads();
@@ -421,8 +374,8 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
 static size_t rsk_trace_smem(const TraceArgs &a, bool bvh, bool dual) {
     const size_t hist = (size_t)a.n_hist + (dual ? a.n_hist2 : 0);
     const size_t words = (size_t)a.sc.mask_words * (dual ? 2 : 1) + (a.hist_in_smem ? hist : 0);
-    return (bvh ? (size_t)RSK_SMEM_STACK * RSK_TILE_THREADS * sizeof(uint2) : 0)
-           + (RSK_RAY_BUFFER ? (size_t)(RSK_TILE_THREADS / 32) * 7 * 64 * sizeof(float) : 0) + words * 4;
+    return (bvh ? (size_t)RSK_SMEM_STACK * RSK_TILE_THREADS * sizeof(uint2) + RSK_PERM_LUT_BYTES : 0)
+           + (size_t)(RSK_TILE_THREADS / 32) * 7 * RAY_SLOTS * sizeof(float) + words * 4;
 }
 
 template <int MODE, bool BVH>
@@ -445,4 +398,20 @@ int rsk_launch_trace(rsk_ctx *ctx, TraceArgs &a, int mode, int64_t n_tiles) {
     if (mode == MODE_DUAL) return bvh ? rsk_launch_one<MODE_DUAL, true>(ctx, a, n_tiles) : rsk_launch_one<MODE_DUAL, false>(ctx, a, n_tiles);
     if (mode == MODE_MATRIX) return bvh ? rsk_launch_one<MODE_MATRIX, true>(ctx, a, n_tiles) : rsk_launch_one<MODE_MATRIX, false>(ctx, a, n_tiles);
     return bvh ? rsk_launch_one<MODE_SKY, true>(ctx, a, n_tiles) : rsk_launch_one<MODE_SKY, false>(ctx, a, n_tiles);
+}
+
+// Diagnostic work counters of the trace kernels since the last reset (all zero unless the library was built with
+// -DRSK_COUNTERS=1): node visits, triangle tests, mask-skipped triangles, rays, triangle-flush trips, stack pushes.
+extern "C" int rsk_trace_counters(rsk_ctx *ctx, int64_t *out, int32_t reset) {
+    RSK_REQUIRE(ctx && out, "rsk_trace_counters: bad arguments");
+    RskScope scope(ctx);
+    unsigned long long h[8];
+    RSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    RSK_CUDA(cudaMemcpyFromSymbol(h, rsk_work_counters, sizeof(h)));
+    for (int i = 0; i < 8; ++i) out[i] = (int64_t)h[i];
+    if (reset) {
+        memset(h, 0, sizeof(h));
+        RSK_CUDA(cudaMemcpyToSymbol(rsk_work_counters, h, sizeof(h)));
+    }
+    return RSK_OK;
 }

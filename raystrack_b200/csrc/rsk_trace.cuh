@@ -45,16 +45,61 @@ __device__ __forceinline__ bool rsk_surface_on(const uint32_t *mask, int sid) {
     return (mask[sid >> 5] >> (sid & 31)) & 1u;
 }
 
+// ---- shared memory through 32-bit shared-window addresses: the compiler otherwise rebuilds the window base
+// (S2UR SR_CgaCtaId / UMOV / ULEA) in front of every access of the walk loop.
+__device__ __forceinline__ uint32_t rsk_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t rsk_lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t rsk_lds8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// predicated 8-byte stack accesses: no branch, so the lanes of a warp that push / pop / do neither stay converged
+__device__ __forceinline__ void rsk_lds64_if(uint32_t addr, bool pred, uint2 &v) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p ld.shared.v2.u32 {%0, %1}, [%2]; }"
+                 : "+r"(v.x), "+r"(v.y) : "r"(addr), "r"((uint32_t)pred));
+}
+__device__ __forceinline__ void rsk_sts64_if(uint32_t addr, bool pred, const uint2 &v) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.shared.v2.u32 [%2], {%0, %1}; }"
+                 :: "r"(v.x), "r"(v.y), "r"(addr), "r"((uint32_t)pred) : "memory");
+}
+__device__ __forceinline__ bool rsk_surface_on_s(uint32_t mask_addr, int sid) {
+    return (rsk_lds32(mask_addr + ((uint32_t)(sid >> 5) << 2)) >> (sid & 31)) & 1u;
+}
+
+// Inner children are visited front to back: slot s has priority s ^ octinv (octinv bit a set: direction component a
+// is >= 0).  The 8 hit bits of a node test come out in slot order; this 8 x 256 byte table (built once per CTA) maps
+// them to priority order: lut[o][m] = OR over the set bits s of m of 1 << (s ^ o).
+constexpr int RSK_PERM_LUT_BYTES = 8 * 256;
+__device__ __forceinline__ void rsk_build_perm_lut(uint8_t *lut, int tid) {
+    for (int i = tid; i < RSK_PERM_LUT_BYTES; i += RSK_TILE_THREADS) {
+        const uint32_t o = (uint32_t)i >> 8, m = (uint32_t)i & 255u;
+        uint32_t r = 0;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) r |= ((m >> s) & 1u) << (s ^ o);
+        lut[i] = (uint8_t)r;
+    }
+}
+
 // Per-ray traversal state of the 8-wide BVH walk.
 struct Walk {
     float ox, oy, oz, dx, dy, dz;
     float ix, iy, iz;        // 1/d (clamped)
     float best;              // closest accepted t so far (RSK_INF = none)
     int best_tri;            // slot of the closest triangle, -1 = none
-    uint2 ng;                // current node group: x = first inner child, y = hit bits<<24 | imask
-    int sp;
+    uint2 ng;                // current node group: x = first inner child, y = hit bits (priority order) << 24 | imask
+    uint32_t sp;             // stack pointer: shared-window address of this thread's next free stack entry
     uint32_t octinv;         // bit a set: direction component a >= 0
-    uint32_t octinv4;        // octinv replicated into four bytes
+    uint32_t lut_row;        // shared-window address of perm_lut[octinv]
+};
+
+// Triangles a node test uncovered: tri bit b (set in `hits`) is triangle base + popc(leaf_bits & ((1 << b) - 1)).
+struct TriGroup {
+    uint32_t base, hits, leaf_bits;
 };
 
 __device__ __forceinline__ float rsk_safe_inv(float d) {
@@ -62,121 +107,94 @@ __device__ __forceinline__ float rsk_safe_inv(float d) {
     return 1.0f / (fabsf(d) > lim ? d : copysignf(lim, d));
 }
 
-__device__ __forceinline__ void rsk_walk_begin(Walk &w, const Ray &r) {
+__device__ __forceinline__ void rsk_walk_begin(Walk &w, const Ray &r, uint32_t stack_base, uint32_t lut_base) {
     w.ox = r.ox; w.oy = r.oy; w.oz = r.oz; w.dx = r.dx; w.dy = r.dy; w.dz = r.dz;
     w.ix = rsk_safe_inv(r.dx); w.iy = rsk_safe_inv(r.dy); w.iz = rsk_safe_inv(r.dz);
     w.best = RSK_INF; w.best_tri = -1;
     w.octinv = (r.dx >= 0.0f ? 1u : 0u) | (r.dy >= 0.0f ? 2u : 0u) | (r.dz >= 0.0f ? 4u : 0u);
-    w.octinv4 = w.octinv * 0x01010101u;
+    w.lut_row = lut_base + (w.octinv << 8);
     w.ng = make_uint2(0u, 0x80000000u);     // pseudo group whose only child is the root
-    w.sp = 0;
+    w.sp = stack_base;
 }
 
-// How the quantised plane bytes become ray parameters, chosen per axis by the bits of RSK_PRMT_AXES:
-//   bit clear: t = float(byte) * (cell * 1/d) + (origin - o) * 1/d           -- one I2F (XU pipe) + one FFMA per plane
-//   bit set:   one PRMT drops the byte into mantissa bits 8..15 of the float 2.0, i.e. f = 2 + byte * 2^-14 exactly;
-//              t = f * A + B with A = cell * 2^14 / d and B = (origin - o)/d - 2A            -- PRMT (ALU) + FFMA, no XU.
-//              B carries a rounding error of <= 2^-9 cell, so the near/far biases are moved outwards by 2^-8 cell.
-// All 48 conversions through I2F keep the XU pipe 67 % busy, all through PRMT load the ALU pipe instead (same speed);
-// one axis through PRMT balances the two pipes: +1.4 % rays/s, identical tallies (profiles/kernel_variants_r1.md).
-#ifndef RSK_PRMT_AXES
-#if defined(RSK_BYTE_MODE) && RSK_BYTE_MODE == 3
-#define RSK_PRMT_AXES 7
-#else
-#define RSK_PRMT_AXES 4       // z planes through PRMT, x and y through I2F
-#endif
-#endif
-
-#ifndef RSK_MASK_PIN
-#define RSK_MASK_PIN 2      // 2: hit-mask bytes extracted with PRMT from two pinned words (-14 instructions per node test)
-#endif
-#ifndef RSK_SUBTREE_SKIP
-#define RSK_SUBTREE_SKIP 2      // 0 = off, 2 = range word loaded together with the node (shipped)
-#endif
-// True when no triangle below node `idx` can matter to this ray: every mesh id there is below the job's `min_sid`
-// (reciprocity: receivers j <= i are ignored, main.py:1181-1182), or the sub-tree belongs to a single mesh that is
-// switched off for this emitter (its own mesh, or a mesh behind its plane, main.py:167-204).  One 8-byte load.
-__device__ __forceinline__ bool rsk_node_ignorable(const uint4 *__restrict__ nodes, uint32_t idx, const uint32_t *mask, int min_sid) {
-    const int2 r = __ldg(reinterpret_cast<const int2 *>(nodes + RSK_NODE_WORDS * (size_t)idx + 5));
-    return r.y < min_sid || (r.x == r.y && !rsk_surface_on(mask, r.x));
+// 32 bytes (one sector) per instruction and lane: sm_100 LDG.256 through the read-only path.  A node is three of
+// them; six LDG.128 cost twice the L1 wavefronts (the data stage moves one sector per lane and instruction).
+__device__ __forceinline__ void rsk_ldg256(const void *p, uint4 &a, uint4 &b) {
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
 }
 
 // Slab test of the 8 quantised child boxes of node `idx` against the ray over [0, tmax].
-// Returns the new node group (inner children hit, priority-permuted) and the 24-bit triangle mask.
+// Returns the new node group (inner children hit, in priority order) and the triangles of the leaf children hit.
+// A sub-tree that holds nothing this ray may hit -- every mesh id below min_sid (reciprocity: receivers j <= i are
+// ignored, main.py:1181-1182), or a single mesh that is switched off for this emitter (its own mesh, or a mesh
+// behind its plane, main.py:167-204) -- reports no hits.
 __device__ __forceinline__ void rsk_test_node(const uint4 *__restrict__ nodes, uint32_t idx, const Walk &w, float tmax,
-                                              uint2 &ng, uint2 &tg, const uint32_t *mask, int min_sid) {
+                                              uint2 &ng, TriGroup &tg, uint32_t mask_addr, int min_sid) {
     const uint4 *p = nodes + RSK_NODE_WORDS * (size_t)idx;
-    const uint4 n0 = __ldg(p), n1 = __ldg(p + 1), n2 = __ldg(p + 2), n3 = __ldg(p + 3), n4 = __ldg(p + 4);
-#if RSK_SUBTREE_SKIP == 2
-    {   // all six words are requested together; an ignorable sub-tree costs the loads but no test and no descent
-        const int2 r = __ldg(reinterpret_cast<const int2 *>(p + 5));
-        if (r.y < min_sid || (r.x == r.y && !rsk_surface_on(mask, r.x))) {
-            ng = make_uint2(0u, 0u);
-            tg = make_uint2(0u, 0u);
-            return;
-        }
-    }
-#endif
-    const uint32_t imask = n0.w >> 24;
-    // Per axis (bit a of RSK_PRMT_AXES): planes through I2F (t = float(byte) * A + B) or dropped into the mantissa of
-    // 2.0 with PRMT (f = 2 + byte * 2^-14; t = f * A' + B', near/far biases moved outwards by 2^-8 cell for B's rounding).
-#define RSK_AXIS_SETUP(AXIS, shift, org, o, inv, A, BN, BF)                                                   \
-    float A, BN, BF;                                                                                           \
+    uint4 a0, a1, b0, b1, c0, c1;
+    rsk_ldg256(p, a0, a1);
+    rsk_ldg256(p + 2, b0, b1);
+    rsk_ldg256(p + 4, c0, c1);
+    const int sid_lo = (int)a1.z, sid_hi = (int)a1.w;
+    const bool ignore = sid_hi < min_sid || (sid_lo == sid_hi && !rsk_surface_on_s(mask_addr, sid_lo));
+
+    // per axis: t = plane * A + B (near / far biases differ on PRMT axes, whose B carries a rounding error of <= 2^-9 cell)
+#define RSK_AXIS_SETUP(AXIS, org, scale, o, inv, A, BN, BF)                                                   \
+    const float A = __uint_as_float(scale) * inv;                                                              \
+    float BN, BF;                                                                                              \
     if ((RSK_PRMT_AXES >> AXIS) & 1) {                                                                         \
-        A = __uint_as_float((((n0.w >> shift) & 0xffu) + 14u) << 23) * inv;                                    \
         const float c = fmaf(-2.0f, A, (__uint_as_float(org) - o) * inv);                                      \
         const float e = fabsf(A) * 0x1p-22f;                                                                   \
         BN = c - e; BF = c + e;                                                                                \
     } else {                                                                                                   \
-        A = __uint_as_float(((n0.w >> shift) & 0xffu) << 23) * inv;                                            \
         BN = (__uint_as_float(org) - o) * inv; BF = BN;                                                        \
     }
-    RSK_AXIS_SETUP(0, 0, n0.x, w.ox, w.ix, ax, bnx, bfx)
-    RSK_AXIS_SETUP(1, 8, n0.y, w.oy, w.iy, ay, bny, bfy)
-    RSK_AXIS_SETUP(2, 16, n0.z, w.oz, w.iz, az, bnz, bfz)
+    RSK_AXIS_SETUP(0, a0.x, c1.x, w.ox, w.ix, ax, bnx, bfx)
+    RSK_AXIS_SETUP(1, a0.y, c1.y, w.oy, w.iy, ay, bny, bfy)
+    RSK_AXIS_SETUP(2, a0.z, c1.z, w.oz, w.iz, az, bnz, bfz)
 #undef RSK_AXIS_SETUP
 #define RSK_PLANE_I2F(word, j) ((float)(((word) >> (8 * (j))) & 0xffu))
 #define RSK_PLANE_PRMT(word, j) __uint_as_float(__byte_perm(word, 0x40000000u, 0x7404u | ((unsigned)(j) << 4)))
 #define RSK_PLANE(AXIS, word, j) (((RSK_PRMT_AXES >> AXIS) & 1) ? RSK_PLANE_PRMT(word, j) : RSK_PLANE_I2F(word, j))
-    // byte planes: n2 = qlo.x[0..7] qlo.y[0..7]; n3 = qlo.z[0..7] qhi.x[0..7]; n4 = qhi.y[0..7] qhi.z[0..7]
     const bool px = w.octinv & 1u, py = w.octinv & 2u, pz = w.octinv & 4u;
-    uint32_t hits = 0;
+    uint32_t hit8 = 0;
 #pragma unroll
-    for (int half = 0; half < RSK_FANOUT / 4; ++half) {
-        const uint32_t meta = half ? n1.w : n1.z;
-        const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
-        const uint32_t hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t lox = half ? b0.y : b0.x, loy = half ? b0.w : b0.z, loz = half ? b1.y : b1.x;
+        const uint32_t hix = half ? b1.w : b1.z, hiy = half ? c0.y : c0.x, hiz = half ? c0.w : c0.z;
         const uint32_t nxw = px ? lox : hix, fxw = px ? hix : lox;
         const uint32_t nyw = py ? loy : hiy, fyw = py ? hiy : loy;
         const uint32_t nzw = pz ? loz : hiz, fzw = pz ? hiz : loz;
-        // four meta bytes at once: inner children (meta = 0b001_11sss) get their slot XOR-ed with the octant
-        // permutation, leaf children keep their first-triangle bit; empty slots have no bits to contribute
-        const uint32_t inner4 = (((meta & (meta << 1)) & 0x10101010u) >> 4) * 0xffu;
-        uint32_t index4 = (meta ^ (w.octinv4 & inner4)) & 0x1f1f1f1fu;
-        uint32_t bits4 = (meta >> 5) & 0x07070707u;
-#if RSK_MASK_PIN
-        asm volatile("" : "+r"(index4), "+r"(bits4));       // keep the two words: ptxas otherwise re-derives them per child
-#endif
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float tnx = fmaf(RSK_PLANE(0, nxw, j), ax, bnx), tfx = fmaf(RSK_PLANE(0, fxw, j), ax, bfx);
-            const float tny = fmaf(RSK_PLANE(1, nyw, j), ay, bny), tfy = fmaf(RSK_PLANE(1, fyw, j), ay, bfy);
-            const float tnz = fmaf(RSK_PLANE(2, nzw, j), az, bnz), tfz = fmaf(RSK_PLANE(2, fzw, j), az, bfz);
-            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
-            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-#if RSK_MASK_PIN >= 2
-            const uint32_t contrib = __byte_perm(bits4, 0u, 0x4440u | j) << __byte_perm(index4, 0u, 0x4440u | j);
-            hits |= (tn <= tf) ? contrib : 0u;
-#else
-            if (tn <= tf) hits |= ((bits4 >> (8 * j)) & 0xffu) << ((index4 >> (8 * j)) & 0xffu);
-#endif
+        for (int j = 0; j < 4; j += 2) {
+            // packed FP32 (Blackwell FFMA2): the plane parameters of two children per instruction
+#define RSK_PAIR(AXIS, word, A, B) __ffma2_rn(make_float2(RSK_PLANE(AXIS, word, j), RSK_PLANE(AXIS, word, j + 1)), \
+                                              make_float2(A, A), make_float2(B, B))
+            const float2 tnx = RSK_PAIR(0, nxw, ax, bnx), tfx = RSK_PAIR(0, fxw, ax, bfx);
+            const float2 tny = RSK_PAIR(1, nyw, ay, bny), tfy = RSK_PAIR(1, fyw, ay, bfy);
+            const float2 tnz = RSK_PAIR(2, nzw, az, bnz), tfz = RSK_PAIR(2, fzw, az, bfz);
+#undef RSK_PAIR
+            const float tn0 = fmaxf(fmaxf(tnx.x, tny.x), fmaxf(tnz.x, 0.0f)), tf0 = fminf(fminf(tfx.x, tfy.x), fminf(tfz.x, tmax));
+            const float tn1 = fmaxf(fmaxf(tnx.y, tny.y), fmaxf(tnz.y, 0.0f)), tf1 = fminf(fminf(tfx.y, tfy.y), fminf(tfz.y, tmax));
+            hit8 |= (tn0 <= tf0) ? (1u << (4 * half + j)) : 0u;
+            hit8 |= (tn1 <= tf1) ? (2u << (4 * half + j)) : 0u;
         }
     }
 #undef RSK_PLANE
 #undef RSK_PLANE_I2F
 #undef RSK_PLANE_PRMT
-    ng = make_uint2(n1.x, (hits & 0xff000000u) | imask);
-    tg = make_uint2(n1.y, hits & 0x00ffffffu);
+    if (ignore) hit8 = 0u;
+    const uint32_t imask = a1.y >> 24;
+    ng = make_uint2(a0.w, (rsk_lds8(w.lut_row + (hit8 & imask)) << 24) | imask);
+    // every hit bit -> the three triangle bits of its slot (the node's leaf_bits keep those that exist)
+    uint32_t x = hit8;
+    x = (x | (x << 8)) & 0x00f00fu;
+    x = (x | (x << 4)) & 0x0c30c3u;
+    x = (x | (x << 2)) & 0x249249u;
+    tg.base = a1.x;
+    tg.hits = (x * 7u) & a1.y & 0x00ffffffu;
+    tg.leaf_bits = a1.y;
 }
 
 // Tregenza patch of an upward direction (utils/cpu_trace.py:735-777, float32 arguments).  atan2 is evaluated

@@ -12,28 +12,12 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 VARIANTS = {      # compile-time knobs of csrc/rsk_trace.cu(h) and csrc/rsk_bvh.cu; the product is built with the defaults
     "shipped": (),
-    "warp_slices": ("RSK_CTA_POOL=0",),
-    "per_lane_raygen": ("RSK_RAY_BUFFER=0", "RSK_REFILL_BELOW=20"),
-    "no_subtree_skip": ("RSK_SUBTREE_SKIP=0",),
-    "byte_prmt_mantissa": ("RSK_PRMT_AXES=7",),
-    "morton_per_axis": ("RSK_MORTON_UNIFORM=0",),
-    "ploc_r16": ("RSK_PLOC=1", "RSK_PLOC_RADIUS=16"),
-    "bottom8": ("RSK_BOTTOM_MAX=8",),
-    "bottom12": ("RSK_BOTTOM_MAX=12",),
-    "bottom16": ("RSK_BOTTOM_MAX=16",),
-    "bottom24": ("RSK_BOTTOM_MAX=24",),
-    "regs80": ("RSK_MIN_CTAS_PER_SM=3",),
-    "fanout4": ("RSK_FANOUT=4",),
-    "tris_at_once": ("RSK_POSTPONE=0",),
-    "all_i2f_mask_shifts": ("RSK_PRMT_AXES=0", "RSK_MASK_PIN=0"),
-    "prmt_x": ("RSK_PRMT_AXES=1",),
-    "halton_stream": ("RSK_HALTON_STREAM=1",),
-    "stack6": ("RSK_SMEM_STACK_N=6",),
-    "stack4": ("RSK_SMEM_STACK_N=4",),
-    "refill26": ("RSK_REFILL_BELOW=26",),
-    "prmt_yz": ("RSK_PRMT_AXES=6",),
-    "p6i3": ("RSK_POSTPONE=6", "RSK_POSTPONE_IDLE=3"),
-    "p32i6": ("RSK_POSTPONE=32", "RSK_POSTPONE_IDLE=6"),
+    "counters": ("RSK_COUNTERS=1",),
+    "prmt7": ("RSK_PRMT_AXES=7",),
+    "prmt0": ("RSK_PRMT_AXES=0",),
+    "prmt6": ("RSK_PRMT_AXES=6",),
+    "refill20": ("RSK_REFILL_BELOW=20",),
+    "refill28": ("RSK_REFILL_BELOW=28",),
 }
 OUT = ROOT / "raystrack_b200" / "_lib" / "variants"
 

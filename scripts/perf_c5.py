@@ -50,6 +50,7 @@ solve = _native.Solve(ctx, sc, em, ids, active[ids], table, ids.copy(), max_iter
                       sky=args.sky, discrete=True, ray_range=ranges)
 solve.step(1)
 r0 = solve.rays_traced()
+ctx.trace_counters(reset=True)
 ctx.timer_start()
 solve.step(args.iters)
 ms = ctx.timer_stop()
@@ -59,6 +60,8 @@ if not args.sky:
     import zlib
     hf, hb, it, tot, _, _ = solve.read_matrix()
     crc = f"  tallies crc32 {zlib.crc32(hf.tobytes() + hb.tobytes()):08x}"
-print(f"{rays} rays in {ms:.1f} ms -> {rays/ms/1e6:.4f} Grays/s{crc}", flush=True)
+cnt = ctx.trace_counters()
+per_ray = "".join(f" {k}/ray {v / cnt['rays']:.2f}" for k, v in cnt.items() if k != "rays") if cnt["rays"] else ""
+print(f"{rays} rays in {ms:.1f} ms -> {rays/ms/1e6:.4f} Grays/s{crc}{per_ray}", flush=True)
 if not args.sky:
     print("hit fraction", (hf.sum() + hb.sum()) / tot.sum(), "iters", it[:3], "launches", ctx.launch_count())

@@ -136,32 +136,35 @@ def test_bvh_structure(ctx):
     sid_sorted = hs.sid[order]
     node_sids = [set() for _ in range(nodes.shape[0])]
     children = [[] for _ in range(nodes.shape[0])]
+    prmt_axes = 4                                           # RSK_PRMT_AXES of the product build (rsk_common.cuh)
     for ni in range(nodes.shape[0]):
         raw = nodes[ni]
         o = raw[:12].view(np.float32)
-        ex = raw[12:15].astype(np.int32) - 127
-        imask = int(raw[15])
-        child_base, tri_base = raw[16:24].view(np.uint32)
-        meta = raw[24:32]
+        child_base, tri_base, leaf_imask = (int(x) for x in raw[12:24].view(np.uint32))
+        imask, leaf_bits = leaf_imask >> 24, leaf_imask & 0xffffff
         q = raw[32:80].reshape(6, 8).astype(np.float64)      # qlo x,y,z ; qhi x,y,z
-        scale = np.exp2(ex.astype(np.float64))
+        scale = raw[80:92].view(np.float32).astype(np.float64)
+        scale = scale / np.array([2.0 ** 14 if (prmt_axes >> ax) & 1 else 1.0 for ax in range(3)])
+        assert np.all(np.log2(scale) == np.round(np.log2(scale)))          # power-of-two cells
         rank = 0
         for s in range(8):
-            m = int(meta[s])
-            if m == 0:
+            cnt = bin((leaf_bits >> (3 * s)) & 7).count("1")
+            inner = (imask >> s) & 1
+            if not inner and cnt == 0:
+                assert np.all(q[0:3, s] == 255) and np.all(q[3:6, s] == 0)      # empty slot: inverted box
                 continue
+            assert not (inner and cnt)
+            assert ((leaf_bits >> (3 * s)) & 7) in (0, 1, 3, 7)              # unary triangle count
             lo = o + q[0:3, s] * scale
             hi = o + q[3:6, s] * scale
-            if (imask >> s) & 1:
-                assert m == (0x20 | (24 + s))
-                reach[int(child_base) + rank] += 1
-                children[ni].append(int(child_base) + rank)
+            if inner:
+                reach[child_base + rank] += 1
+                children[ni].append(child_base + rank)
                 rank += 1
             else:
-                cnt = bin(m >> 5).count("1")
-                off = m & 31
+                off = bin(leaf_bits & ((1 << (3 * s)) - 1)).count("1")
                 for t in range(cnt):
-                    ti = int(tri_base) + off + t
+                    ti = tri_base + off + t
                     seen[ti] += 1
                     node_sids[ni].add(int(sid_sorted[ti]))
                     assert np.all(lo_t[ti] >= lo - 1e-6) and np.all(hi_t[ti] <= hi + 1e-6), (ni, s, ti)
@@ -171,7 +174,7 @@ def test_bvh_structure(ctx):
     for ni in range(nodes.shape[0] - 1, -1, -1):
         for c in children[ni]:
             node_sids[ni] |= node_sids[c]
-        smin, smax = nodes[ni][80:88].view(np.int32)
+        smin, smax = nodes[ni][24:32].view(np.int32)
         assert (int(smin), int(smax)) == (min(node_sids[ni]), max(node_sids[ni])), ni
 
 
