@@ -15,8 +15,13 @@ followed by the on-device statistics/convergence pass.  Prints ONE JSON line (ra
             BVH built on the GPU, 40 iterations, tally download and result assembly
   roofline  memory roofline of the dominant kernel (rsk_trace_kernel<matrix,bvh>): algorithmic bytes per ray
             (reference data layout, counted by the oracle's instrumented replay) x rays / kernel time
-  cpu_baseline / --impl reference: the CPU oracle port of the reference's Numba kernels (oracle/), all host threads,
-            on a bounded sample of the same workload
+  parity    results independent of the GPU count: crc32 of the rank-summed C5 tally block after 2 fixed iterations,
+            equal to the block of an unsharded solve (N > 1) and to the committed single-GPU crc; reference goldens
+            through the sharded public API; per-ray agreement with the oracle on the CPU sample (N = 1)
+  cpu_baseline      the CPU oracle port (oracle/, C + OpenMP, all host threads) on a bounded sample of the workload
+  reference_baselines   (N = 1) the UNMODIFIED reference from baseline/_ref on the same box: its Numba CPU kernels and its
+            Numba-CUDA path (baseline/numba_baselines.py, separate process)
+  --impl reference  times the reference's own Numba CPU kernels (baseline/_ref) on the bounded sample, all host threads
 """
 from __future__ import annotations
 
@@ -39,6 +44,7 @@ UNIT = "Grays/s"
 WORKLOAD = "C5 synthetic urban block: 2001 meshes, 1,026,048 triangles, samples=4 rays=64 (239,026,176 rays/iteration)"
 SAMPLE_STRIDE = 16          # CPU sample: every 16th emitter (126 emitters incl. the ground) ...
 SAMPLE_RAYS = 16384         # ... first 16384 rays of each  (= 2,064,384 rays per CPU step)
+PARITY_ITERS = 2            # fixed iterations of the sharded-parity solve (crc of the rank-summed tally block)
 FALLBACK_BYTES_PER_RAY = 5400.0   # SURVEY.md 8d, used only if the live replay is not run (N>1) and no file exists
 
 
@@ -143,16 +149,39 @@ class CpuSample:
                 f"{self.rays_per_step} rays/step, reference BVH (median split, leaf 8), closest hit")
 
 
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path on the box's host cores: its Numba kernels build_rays +
+    trace_cpu_bvh_firsthit with its own preparation, imported unmodified from baseline/_ref (kind "reference"); the C
+    port under oracle/ only if the reference cannot be imported there (kind "port").  All host threads in either case
+    -- torchrun exports OMP_NUM_THREADS=1, which is overridden here."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as O
+    sys.path.insert(0, str(ROOT / "baseline"))
+    import numba_baselines as NB
+    threads = NB.prepare_environment(host_threads())          # before numba / OpenMP start
     meshes = build_scene(args.side)
-    cpu = CpuSample(meshes, args.samples, args.rays, args.seed)
-    cores = O.num_threads()
-    log(f"[reference] oracle prep {cpu.prep_s:.1f}s, {cores} threads, {cpu.rays_per_step} rays/step")
-    for w in range(args.warmup):
+    why = NB.reference_available()
+    if why is None:
+        try:
+            cpu = NB.NumbaCpuSample(meshes, args.samples, args.rays, args.seed)
+            kind, cores = "reference", cpu.threads
+        except Exception as e:      # noqa: BLE001
+            why = f"{type(e).__name__}: {e}"[:200]
+    if why is not None:
+        from oracle import oracle as O
+        O.set_num_threads(threads)
+        cpu = CpuSample(meshes, args.samples, args.rays, args.seed)
+        kind, cores = "port", O.num_threads()
+    log(f"[reference] kind={kind} prep {cpu.prep_s:.1f}s, {cores} threads, {cpu.rays_per_step} rays/step" + (f" (reference unavailable: {why})" if why else ""))
+    for w in range(max(args.warmup, 1)):                       # the first step also JIT-compiles the Numba kernels
         cpu.step(w)
     t = time.perf_counter()
     for k in range(args.steps):
@@ -163,12 +192,123 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 (f64 ray generation)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": cpu.describe()},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu.describe()},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": cpu.describe()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if why:
+        line["cpu_baseline"]["reference_unavailable"] = why
     emit(line)
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+
+def _time_steps(ctx, fn, steps, flush, torch):
+    """CUDA-event time (ms per call) of ``fn`` on the context's stream, L2 flushed before every call."""
+    out = []
+    for _ in range(steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ctx.timer_start()
+        fn()
+        out.append(ctx.timer_stop())
+    return float(np.mean(out))
+
+
+def _max_abs_diff(res, gold):
+    err = 0.0
+    for name, row in gold.items():
+        for key in set(row) | set(res[name]):
+            err = max(err, abs(res[name].get(key, 0.0) - row.get(key, 0.0)))
+    return err
+
+
+def parity_block(ctx, rank, world, sc, em, active, n_once, table, args):
+    """Results independent of the GPU count, checked inside the driver-run bench at every N:
+    the rank-summed C5 tally block after PARITY_ITERS fixed iterations through the sharded solve driver -- its crc32,
+    whether it equals the block an unsharded solve of the same process produces (N > 1), and whether the crc equals the
+    committed single-GPU value; golden solves of the reference through the sharded public API; a ray-split scene."""
+    import zlib
+    from raystrack_b200 import MatrixParams, main as M, synthetic, view_factor_matrix
+    sys.path.insert(0, str(ROOT / "tests"))
+    from scenes import scene_for
+    K = PARITY_ITERS
+    n = active.shape[0]
+    ids = np.arange(n, dtype=np.int32)
+    kw = dict(max_iters=K, min_iters=K, interval=1, tol_mode="stderr", tol=0.0, emit_sid=ids, min_sid=np.zeros(n, np.int32))
+    tallies, iters, totals = M._solve_sharded(ctx, sc, em, list(range(n)), n_once, active, table, **kw)
+    tallies = np.array(tallies, copy=True)                     # the result may be a view of the pinned staging area
+    out = {"iters": K, "tally_crc32": f"{zlib.crc32(tallies.tobytes()) & 0xffffffff:08x}", "tally_sum": int(tallies.sum()),
+           "rays": int(totals.sum())}
+    ref_file = ROOT / "profiles" / "c5_tally_crc_r2.json"
+    if ref_file.exists() and args.side == 20 and args.samples == 4 and args.rays == 64 and args.seed == 1:
+        want = json.loads(ref_file.read_text())
+        if int(want.get("iters", -1)) == K:
+            out["crc_equals_committed_n1"] = out["tally_crc32"] == want["tally_crc32"]
+    if world > 1:
+        M._DIST_OVERRIDE = (0, 1)                              # the same solve, unsharded, on this rank's GPU
+        try:
+            t1, i1, r1 = M._solve_sharded(ctx, sc, em, list(range(n)), n_once, active, table, **kw)
+            same = bool(np.array_equal(t1, tallies) and np.array_equal(i1, iters) and np.array_equal(r1, totals))
+        finally:
+            M._DIST_OVERRIDE = None
+        flags = np.array([1 if same else 0], np.int64)
+        from raystrack_b200 import dist as D
+        D.allreduce_sum_([flags])
+        out["equals_n1"] = bool(int(flags[0]) == world)
+    # the reference's own results through the sharded public API
+    gold = json.loads((ROOT / "tests" / "golden" / "solves.json").read_text())
+    worst = 0.0
+    cases = ("C2_canyon_ex01", "U3_urban_matrix_bvh")
+    for case in cases:
+        worst = max(worst, _max_abs_diff(view_factor_matrix(scene_for(case), MatrixParams(**gold[case]["params"])), gold[case]["result"]))
+    out["golden_max_abs_err"] = worst
+    out["golden_cases"] = list(cases)
+    # one oversized emitter (the ground) -> ray-split path with its per-iteration all-reduce
+    meshes = synthetic.urban_block(4, 4, 8, 0)
+    prm = MatrixParams(samples=4, rays=32, seed=2, bvh="builtin", reciprocity=False, max_iters=12, min_iters=3, tol=5e-4)
+    res = view_factor_matrix(meshes, prm)
+    if world > 1:
+        from raystrack_b200.prepared import PreparedSolver
+        n4 = [int(e.n_cells * 32) for e in PreparedSolver(meshes).get_emitters(samples=4, rays=32, flip_faces=False)]
+        out["ray_split_jobs_per_rank"] = sum(1 for j in M.plan_shards(list(range(len(meshes))), n4, world)[rank] if j[3])
+        M._DIST_OVERRIDE = (0, 1)
+        try:
+            same = view_factor_matrix(meshes, prm) == res
+        finally:
+            M._DIST_OVERRIDE = None
+        flags = np.array([1 if same else 0], np.int64)
+        D.allreduce_sum_([flags])
+        out["ray_split_equals_n1"] = bool(int(flags[0]) == world)
+    return out
+
+
+def secondary_block(ctx, sc, em, active, n_once, table, rays_per_step, flush, torch):
+    """The other kernels of the path on the same scene and step definition (one iteration of every emitter), CUDA-event
+    timed, L2 flushed: discrete-sky any-hit, dual (closest hit + any-hit flag from one walk), and the API-default
+    reciprocity=True schedule (emitter i ignores meshes j <= i; the last emitter has no receivers)."""
+    from raystrack_b200 import _native
+    n = active.shape[0]
+    ids = np.arange(n, dtype=np.int32)
+    zeros = np.zeros(n, np.int32)
+    out = {}
+    common = dict(max_iters=64, min_iters=64, interval=1, tol_mode="stderr", tol=0.0)
+
+    def run(name, solve, rays):
+        solve.step(2)
+        ms = _time_steps(ctx, lambda: solve.step(1), 3, flush, torch)
+        out[name] = {"value": rays / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms}
+        solve.close()
+
+    run("sky_discrete_any_hit", _native.Solve(ctx, sc.native, em.native, ids, active, table, ids.copy(), sky=True, discrete=True, **common),
+        rays_per_step)
+    side = dict(max_iters=64, min_iters=64, tol=0.0, tol_mode="stderr", interval=1)
+    run("dual_matrix_and_sky", _native.DualSolve(ctx, sc.native, em.native, ids, active, table, ids.copy(), ids, zeros, side, side, True),
+        rays_per_step)
+    has_recv = np.asarray([bool(active[i, i + 1:].any()) for i in range(n)], bool)
+    rid = ids[has_recv]
+    run("matrix_reciprocity_schedule", _native.Solve(ctx, sc.native, em.native, rid, active[rid], table, rid.copy(), emit_sid=rid,
+                                                     min_sid=rid + 1, **common), int(sum(n_once[i] for i in rid)))
+    return out
+
 
 def run_ours(args):
     import torch
@@ -176,12 +316,15 @@ def run_ours(args):
     from raystrack_b200.prepared import PreparedSolver
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank, world = D.init_from_env("nccl") if world > 1 else (0, 1)
+    rank, world = D.init_from_env("nccl") if world > 1 else (0, 1)     # torchrun's group: rendezvous + the driver's NCCL check
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if _native.device_count() <= 0:
         raise RuntimeError("bench.py needs a B200: no CUDA device visible")
-    ctx = M._context() if world > 1 else _native.Context.for_device(local, _native.torch_stream_handle(local))
+    # N > 1: the context that owns the library's own NCCL communicator (rsk_comm_init; id handed over through the group)
+    ctx = M._context() if world > 1 else _native.Context.for_device(local)
+    if world > 1 and not D.native_comm_active():
+        raise RuntimeError(f"library communicator unavailable: {D._NATIVE_FAILED}")
 
     meshes = build_scene(args.side)
     ps = PreparedSolver(meshes)
@@ -198,8 +341,8 @@ def run_ours(args):
     active = M._surface_masks(ems, centers, extents)
     n_once = [int(e.n_cells * args.rays) for e in ems]
     rays_per_step = int(sum(n_once))
-    total_iters = args.warmup + 2 * args.steps + 2
-    table = M._rotation_table(args.seed, n, total_iters)
+    total_iters = max(args.warmup, 3) + 2 * args.steps + 2
+    table = M._rotation_table(args.seed, n, max(total_iters, 64))
     plans = M.plan_shards(list(range(n)), n_once, world)
     plan = plans[rank]
     ids = np.asarray([j[0] for j in plan], np.int32)
@@ -208,7 +351,6 @@ def run_ours(args):
     solve = _native.Solve(ctx, sc.native, em.native, ids, active[ids], table, ids.copy(), max_iters=total_iters,
                           min_iters=total_iters, interval=1, tol_mode="stderr", tol=0.0,
                           emit_sid=ids, min_sid=np.zeros(len(ids), np.int32), ray_range=ranges)
-    tally = D.attach_tally_tensor(solve, n_shared, local) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local}")     # > 126 MB L2
 
     def one_step(trace_only_timer=None):
@@ -217,11 +359,11 @@ def run_ours(args):
         solve.enqueue_trace()
         if trace_only_timer is not None:
             trace_only_timer.append(ctx.timer_stop())
-        if tally is not None:
-            D.all_reduce_device_(tally, local)
+        if world > 1 and n_shared:
+            solve.allreduce_iter_tallies(n_shared)              # NCCL on the context's stream, between trace and fold
         solve.enqueue_fold()
 
-    for _ in range(max(args.warmup, 3) if args.warmup else 0):
+    for _ in range(max(args.warmup, 3)):
         one_step()
     ctx.synchronize()
     if world > 1:
@@ -242,7 +384,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         D.barrier()
-    total_ms = D.max_over_ranks(float(sum(step_ms)), local)
+    total_ms = D.max_over_ranks(float(sum(step_ms)))
     value = rays_per_step * args.steps / (total_ms * 1e-3) / 1e9
 
     # dominant kernel alone (same stream, CUDA events around the trace launch only)
@@ -274,25 +416,32 @@ def run_ours(args):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         phases.append({k: round(1e3 * v, 1) for k, v in M.LAST_TIMING.items()})
-        return D.max_over_ranks(dt, local)
+        return D.max_over_ranks(dt)
 
     e2e_times, e2e_single, phases = [], [], []
+    parity = secondary = None
     try:
         if args.e2e_steps > 0:
             timed_call(1)                                       # warm-up of the public path
             e2e_times = [timed_call(args.e2e_iters) for _ in range(args.e2e_steps)]
             e2e_single = [timed_call(1) for _ in range(3)]
+        if not args.no_parity:
+            parity = parity_block(ctx, rank, world, sc, em, active, n_once, table, args)
+        if world == 1 and not args.no_secondary:
+            secondary = secondary_block(ctx, sc, em, active, n_once, table, rays_per_step, flush, torch)
     finally:
         M._log = old_log
     e2e_value = rays_per_step * args.e2e_iters / float(np.mean(e2e_times)) / 1e9 if e2e_times else None
     e2e_single_value = rays_per_step / float(np.mean(e2e_single)) / 1e9 if e2e_single else None
-    n_tri = ps.total_faces
     h2d = geometry_bytes + n * n + table.nbytes                # vertices + faces + offsets, surf_active, rotations
-    d2h = len(ids) * 2 * n * 8 + len(ids) * 12                 # int64 tally block + iteration/ray counters
+    d2h = n * 2 * n * 8 + n * 12                               # rank-summed int64 tally block + iteration/ray counters
+    comm = ctx.comm_info() if world > 1 else None
 
     if world > 1:
         D.barrier()
+        D.shutdown_native()
         import torch.distributed as dist
+        dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
@@ -302,6 +451,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "step": "one Monte-Carlo iteration of all 2001 emitters", "rays_per_step": rays_per_step,
                        "bvh": f"GPU LBVH -> 8-wide quantised, {info['n_nodes']} nodes, depth {info['depth']}, built in {info['build_us']/1e3:.1f} ms",
                        "l2": "flushed between timed steps (256 MB write)", "sharding": f"emitters over {world} GPU(s), {n_shared} ray-split",
+                       "collectives": None if comm is None else f"librsk_b200 rsk_comm (NCCL {comm['nccl_version']}, {comm['nranks']} ranks) on the kernel stream",
                        "upload_prepare_build_s": round(prep_s, 3)},
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -312,15 +462,20 @@ def run_ours(args):
                     "phases_ms_last_call": phases[args.e2e_steps] if len(phases) > args.e2e_steps else None,
                     "single_iteration_call": {"value": e2e_single_value, "unit": UNIT,
                                               "ms": 1e3 * float(np.mean(e2e_single)) if e2e_single else None}}}
+    if parity is not None:
+        line["parity"] = parity
+    if secondary is not None:
+        line["secondary"] = secondary
 
-    # ---- CPU oracle: baseline + algorithmic bytes per ray + per-ray parity on the sample (N=1 only)
+    # ---- CPU oracle (C port, all host threads): baseline + algorithmic bytes per ray; per-ray parity on the sample (N=1)
     bpr_file = ROOT / "profiles" / "c5_bytes_per_ray.json"
     bytes_per_ray, bpr_src = FALLBACK_BYTES_PER_RAY, "SURVEY.md 8d"
     if bpr_file.exists():
         bytes_per_ray = float(json.loads(bpr_file.read_text())["bytes_per_ray"])
         bpr_src = "profiles/c5_bytes_per_ray.json"
-    if world == 1 and not args.no_cpu:
+    if not args.no_cpu:
         from oracle import oracle as O
+        O.set_num_threads(host_threads())                        # torchrun exports OMP_NUM_THREADS=1
         cpu = CpuSample(meshes, args.samples, args.rays, args.seed)
         cpu.step(0)                                              # warm-up
         stats = np.zeros(4, np.int64)
@@ -337,46 +492,83 @@ def run_ours(args):
         bpr_src = "oracle replay on the CPU sample (this run)"
         line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "sample": cpu.describe(),
                                 "visits_per_ray": {"inner": n_in, "leaf": n_leaf, "tri": n_tri_t, "skipped": n_skip}}
-        # per-ray parity of the GPU path on the same sample (iteration 1), through the C-ABI per-ray hook
-        agree = tot = 0
-        for i, cnt in zip(cpu.emit, cpu.counts):
-            cpg, cpd = O.rotation(args.seed, i, 1)
-            _, _, hit, front = _native.trace_rays(ctx, sc.native, em.native, i, active[i], i, 0, np.concatenate([cpg, cpd]),
-                                                  mode=0, n_rays=cnt, want_rays=False)
-            hs, fr = keep[i]
-            agree += int(np.sum((hit == hs) & (front == fr)))
-            tot += cnt
-        line["parity"] = {"per_ray_agreement": agree / tot, "rays_compared": tot}
+        if world == 1:
+            # per-ray parity of the GPU path on the same sample (iteration 1), through the C-ABI per-ray hook
+            agree = tot = 0
+            for i, cnt in zip(cpu.emit, cpu.counts):
+                cpg, cpd = O.rotation(args.seed, i, 1)
+                _, _, hit, front = _native.trace_rays(ctx, sc.native, em.native, i, active[i], i, 0, np.concatenate([cpg, cpd]),
+                                                      mode=0, n_rays=cnt, want_rays=False)
+                hs, fr = keep[i]
+                agree += int(np.sum((hit == hs) & (front == fr)))
+                tot += cnt
+            line.setdefault("parity", {}).update({"per_ray_agreement": agree / tot, "rays_compared": tot})
     # ---- the metric's second half: VF max abs error vs the reference, on the reference's own example config (C2:
     # examples/ex01 street canyon, golden result generated by the reference itself: tests/golden/solves.json)
-    try:
-        from raystrack_b200 import synthetic
-        gold = json.loads((ROOT / "tests" / "golden" / "solves.json").read_text())["C2_canyon_ex01"]
-        M._log = lambda msg: None
-        res = view_factor_matrix(synthetic.street_canyon(), MatrixParams(**gold["params"]))
-        M._log = old_log
-        err = 0.0
-        for name, row in gold["result"].items():
-            for key in set(row) | set(res[name]):
-                err = max(err, abs(res[name].get(key, 0.0) - row.get(key, 0.0)))
-        line["vf_max_abs_err"] = {"value": err, "config": "C2 street canyon, ex01 params (11 meshes, reciprocity, stderr tol 1e-4)",
-                                  "against": "reference CPU result (tests/golden/solves.json), tolerance 1e-4"}
-    except Exception as e:      # noqa: BLE001
-        line["vf_max_abs_err"] = {"value": None, "error": str(e)[:200]}
+    if world == 1:
+        try:
+            from raystrack_b200 import synthetic
+            gold = json.loads((ROOT / "tests" / "golden" / "solves.json").read_text())["C2_canyon_ex01"]
+            M._log = lambda msg: None
+            res = view_factor_matrix(synthetic.street_canyon(), MatrixParams(**gold["params"]))
+            M._log = old_log
+            line["vf_max_abs_err"] = {"value": _max_abs_diff(res, gold["result"]),
+                                      "config": "C2 street canyon, ex01 params (11 meshes, reciprocity, stderr tol 1e-4)",
+                                      "against": "reference CPU result (tests/golden/solves.json), tolerance 1e-4"}
+        except Exception as e:      # noqa: BLE001
+            line["vf_max_abs_err"] = {"value": None, "error": str(e)[:200]}
+    elif parity is not None:
+        line["vf_max_abs_err"] = {"value": parity.get("golden_max_abs_err"), "config": "sharded: " + ", ".join(parity.get("golden_cases", [])),
+                                  "against": "reference CPU results (tests/golden/solves.json), tolerance 1e-4"}
     peak, peak_src = measured_peaks()
     achieved = my_rays * bytes_per_ray / (trace_avg_ms * 1e-3) / 1e9
     line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                         "kernel": "rsk_trace_kernel<matrix,bvh>", "kernel_ms": trace_avg_ms, "bytes_per_ray": bytes_per_ray,
                         "bytes_per_ray_source": bpr_src, "peak_source": peak_src,
-                        "note": "algorithmic bytes of the reference layout; the 80 MB scene is L2-resident, so frac > 1 of HBM is expected"}
-    traffic_file = ROOT / "profiles" / "c5_trace_dram_bytes.json"
-    if traffic_file.exists():
-        line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch")
-    # what actually binds the kernel (not measured live: read from the committed ncu capture, profiles/r1_summary.md)
-    line["roofline"]["binding_resource"] = {"name": "instruction issue", "issue_slots_busy_pct": 72.8, "lanes_per_instruction": 20.9,
-                                            "pipe_alu_pct": 58.5, "pipe_xu_pct": 50.2, "l1_hit_pct": 59.4, "l2_hit_pct": 96.8,
-                                            "source": "profiles/r1_summary.md (ncu --set full of this kernel, same scene)"}
+                        "note": "SURVEY 8(d) yardstick: algorithmic bytes of the REFERENCE's 2-wide layout over the HBM peak; the 80 MB scene is "
+                                "L2-resident, so frac > 1 is expected and says nothing about saturation -- what bounds the kernel is in "
+                                "issue / l1 / l2 below (ncu capture of the same kernel and scene)"}
+    ncu_csv = ROOT / "profiles" / "trace_r2_ncu_raw.csv"
+    if ncu_csv.exists():
+        try:
+            sys.path.insert(0, str(ROOT / "scripts"))
+            import ncu_extract
+            prof = ncu_extract.summary(ncu_csv, "rsk_trace_kernel", rays_per_step)
+            line["roofline"].update({"traffic": prof["dram"]["bytes"], "issue": prof["issue"], "l1": prof["l1"], "l2": prof["l2"],
+                                     "ncu_kernel_ms": prof["kernel_ms"], "registers_per_thread": prof["registers_per_thread"],
+                                     "warps_active_pct": prof["warps_active_pct"],
+                                     "source": "profiles/trace_r2_ncu_raw.csv via scripts/ncu_extract.py (ncu --set full, one launch over the "
+                                               "whole C5 iteration: compare ncu_kernel_ms with kernel_ms at N=1)"})
+        except Exception as e:      # noqa: BLE001
+            line["roofline"]["ncu_error"] = str(e)[:200]
+    # ---- the unmodified reference on this box, next to the numbers above (N=1): Numba CPU kernels and Numba-CUDA path
+    if world == 1 and not args.no_numba:
+        line["reference_baselines"] = run_numba_baselines(args)
+        nb = line["reference_baselines"]
+        for key in ("numba_cpu", "numba_cuda"):
+            v = (nb.get(key) or {}).get("Grays_per_s")
+            if v:
+                nb[key]["speedup_of_value"] = value / v
     emit(line)
+
+
+def run_numba_baselines(args) -> dict:
+    """baseline/numba_baselines.py in a process of its own (Numba-CUDA brings its own CUDA context and JIT): the
+    reference's Numba CPU kernels on the CPU sample and its view_factor_matrix(device='gpu') over the whole scene."""
+    cmd = [sys.executable, str(ROOT / "baseline" / "numba_baselines.py"), "--side", str(args.side), "--iters", "1", "--cpu-seconds", "6"]
+    env = dict(os.environ)
+    env.pop("OMP_NUM_THREADS", None)
+    t = time.time()
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=args.numba_timeout, env=env)
+        last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        out = json.loads(last[-1]) if last else {"unavailable": f"no output (rc {r.returncode}): {r.stderr[-300:]}"}
+    except subprocess.TimeoutExpired:
+        out = {"unavailable": f"timed out after {args.numba_timeout} s"}
+    except Exception as e:      # noqa: BLE001
+        out = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    out["wall_s"] = round(time.time() - t, 1)
+    return out
 
 
 def main():
@@ -392,6 +584,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2, help="timed public-API calls (0 = skip the e2e leg)")
     ap.add_argument("--e2e-iters", type=int, default=40, help="iterations per public-API call (C5: min_iters=max_iters=40)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle legs (profiling runs)")
+    ap.add_argument("--no-numba", action="store_true", help="skip the reference's Numba CPU / Numba-CUDA legs (N=1)")
+    ap.add_argument("--numba-timeout", type=int, default=420)
+    ap.add_argument("--no-parity", action="store_true", help="skip the sharded-parity block")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the sky / dual / reciprocity kernel timings (N=1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RSK_ABI_VERSION 1
+#define RSK_ABI_VERSION 2
 
 typedef enum rsk_status {
     RSK_OK = 0,
@@ -41,11 +41,14 @@ typedef struct rsk_scene rsk_scene;
 typedef struct rsk_emitters rsk_emitters;
 typedef struct rsk_solve rsk_solve;
 typedef struct rsk_geometry rsk_geometry;
+typedef struct rsk_tally_block rsk_tally_block;
 
 /* ------------------------------------------------------------------------------------------- library */
 
 const char *rsk_last_error(void);
 int rsk_abi_version(void);
+/* Hash of the sources this binary was built from (the Python loader rebuilds a library that does not match its tree). */
+const char *rsk_source_hash(void);
 /* Number of visible CUDA devices (0 without a driver); replaces numba.cuda.is_available() (main.py:136-147). */
 int rsk_device_count(int *count);
 
@@ -194,6 +197,9 @@ int rsk_matrix_read(rsk_solve *solve, int64_t *hits_front, int64_t *hits_back, i
 /* The whole tally block in one contiguous copy: matrix solves int64[n_local][n_surf][2] ((front, back) pair per
  * receiver), sky solves int64[n_local][145 or 1]; what the host driver uses. */
 int rsk_solve_read_block(rsk_solve *solve, int64_t *tallies, int32_t *iters, int64_t *total_rays);
+/* rsk_solve_read_block without the second host copy: *tallies_view points into the context's pinned staging area
+ * (valid until the next staged download of this context). */
+int rsk_solve_read_block_view(rsk_solve *solve, int64_t **tallies_view, int32_t *iters, int64_t *total_rays);
 /* Device pointer + element count of the int64 tally block [n_local][n_surf][2] ((front, back) per receiver) for collectives issued by the caller (torch.distributed / NCCL). */
 int rsk_matrix_device_tallies(rsk_solve *solve, void **device_ptr, int64_t *n_elements);
 
@@ -255,6 +261,42 @@ int rsk_solve_rays_traced(rsk_solve *solve, int64_t *rays);
  * only by builds with -DRSK_COUNTERS=1 (scripts/kernel_variants.py); the product build returns zeros.  The reference
  * has no counterpart; SURVEY.md 8(d) measured the same quantities by instrumenting cpu_trace.py:120-277. */
 int rsk_trace_counters(rsk_ctx *ctx, int64_t *out, int32_t reset);
+
+/* ------------------------------------------------------------------------------------------- multi-GPU
+ * The reference is single-device; this is the exchange step of the B200 design:
+ * one process per GPU, each with its own context; emitters (matrix rows, independent units -- main.py:1758-1939)
+ * are sharded over the ranks, the BVH is replicated, and the int64 tallies are summed over NVLink/NVSwitch.  NCCL is
+ * bound at run time (libnccl.so.2 already in the process, else $RSK_NCCL_LIBRARY, else the system library).
+ *
+ * rsk_comm_unique_id: rank 0 creates the 128-byte NCCL id and hands it to the other ranks out of band (file, socket,
+ * MPI, torch.distributed store ...).  rsk_comm_init joins the communicator (collective: every rank calls it); all
+ * later collectives run on the context's stream, ordered with its kernels -- no host synchronisation in between. */
+#define RSK_COMM_ID_BYTES 128
+int rsk_comm_unique_id(uint8_t *id);
+int rsk_comm_init(rsk_ctx *ctx, const uint8_t *id, int32_t rank, int32_t nranks);
+int rsk_comm_destroy(rsk_ctx *ctx);
+/* rank / nranks of the context's communicator (0 / 1 without one); nccl_version e.g. 22809 (0 if NCCL is not loaded). */
+int rsk_comm_info(rsk_ctx *ctx, int32_t *rank, int32_t *nranks, int32_t *nccl_version);
+/* In-place all-reduce of n int64 values in DEVICE memory on the context's stream; op 0 = sum, 1 = max.  A context
+ * without communicator (or with one rank) returns at once. */
+int rsk_allreduce_i64(rsk_ctx *ctx, void *device_ptr, int64_t n, int32_t op);
+/* The same for n <= 4096 HOST values (iteration counters, "is any rank still running"); synchronises the stream. */
+int rsk_allreduce_host_i64(rsk_ctx *ctx, int64_t *values, int64_t n, int32_t op);
+/* Split-phase stepping (see rsk_solve_enqueue_trace): sum the per-iteration tallies of the first n_jobs jobs of
+ * `solve` (the ray-split emitters, first in emit_ids on every rank) over the communicator, on the context's stream. */
+int rsk_solve_allreduce_iter_tallies(rsk_solve *solve, int32_t n_jobs);
+/* Device-resident int64 [n_rows][n_cols] block, zero-initialised, in which the ranks assemble the result of a
+ * sharded solve: add_solve copies the totals of the solve's jobs into the rows named by their emitter ids
+ * (keep: uint8[n_local] or NULL; jobs with keep == 0 are skipped -- a ray-split job is replicated on every rank and
+ * must be counted once), allreduce sums the blocks of all ranks, download brings the result to the host through
+ * pinned memory.  download: dst (caller memory, may be NULL) and/or *view (pointer into the context's pinned staging
+ * area, valid until the next staged download of this context; may be NULL). */
+int rsk_tally_block_create(rsk_ctx *ctx, int64_t n_rows, int64_t n_cols, rsk_tally_block **out);
+int rsk_tally_block_add_solve(rsk_tally_block *block, rsk_solve *solve, const uint8_t *keep);
+int rsk_tally_block_allreduce(rsk_tally_block *block);
+int rsk_tally_block_device(rsk_tally_block *block, void **device_ptr, int64_t *n_elements);
+int rsk_tally_block_download(rsk_tally_block *block, int64_t *dst, int64_t **view);
+int rsk_tally_block_destroy(rsk_tally_block *block);
 
 /* ------------------------------------------------------------------------------------------- reciprocity
  * Replaces the dense core of enforce_reciprocity_and_rowsum (utils/helpers.py:70-96): G = 0.5*(A F + (A F)^T),

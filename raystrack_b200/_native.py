@@ -33,7 +33,13 @@ EXPORTS = (
     "rsk_sky_begin", "rsk_sky_step", "rsk_sky_read", "rsk_dual_begin", "rsk_dual_begin_sliced", "rsk_dual_step", "rsk_dual_sky_part",
     "rsk_solve_enqueue_trace", "rsk_solve_enqueue_fold", "rsk_solve_poll", "rsk_solve_device_iter_tallies", "rsk_solve_set_iter_tally_buffer",
     "rsk_solve_destroy", "rsk_solve_rays_traced", "rsk_trace_counters", "rsk_reciprocity_rowsum",
+    "rsk_solve_read_block_view", "rsk_source_hash",
+    "rsk_comm_unique_id", "rsk_comm_init", "rsk_comm_destroy", "rsk_comm_info", "rsk_allreduce_i64", "rsk_allreduce_host_i64",
+    "rsk_solve_allreduce_iter_tallies",
+    "rsk_tally_block_create", "rsk_tally_block_add_solve", "rsk_tally_block_allreduce", "rsk_tally_block_device",
+    "rsk_tally_block_download", "rsk_tally_block_destroy",
 )
+COMM_ID_BYTES = 128
 
 
 class MeshSummary(C.Structure):
@@ -56,15 +62,24 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists() or os.environ.get("RSK_REBUILD"):
-        from . import _build
-        _build.build(force=bool(os.environ.get("RSK_REBUILD")))
+    from . import _build
+    # The library is rebuilt whenever it is missing or was compiled from other sources than the ones in the tree (a
+    # hash of csrc/ + include/ is embedded at build time and kept next to the .so): a stale binary never runs
+    # against newer Python.  Without nvcc a stale library is an error, not a silent mismatch.
+    if os.environ.get("RSK_REBUILD") or _build.stale():
+        _build.build(force=True)
     # RSK_LIB: load an experimental build of the same library (kernel tuning, scripts/kernel_variants.py)
-    lib = C.CDLL(os.environ.get("RSK_LIB") or str(LIB_PATH))
+    variant = os.environ.get("RSK_LIB")
+    lib = C.CDLL(variant or str(LIB_PATH))
     lib.rsk_last_error.restype = C.c_char_p
+    lib.rsk_source_hash.restype = C.c_char_p
     for name in EXPORTS:
-        if name != "rsk_last_error":
+        if name not in ("rsk_last_error", "rsk_source_hash"):
             getattr(lib, name).restype = C.c_int
+    if not variant:
+        built_from = lib.rsk_source_hash().decode()
+        if built_from != _build.source_hash():
+            raise NativeError(f"{LIB_PATH} was built from other sources ({built_from}) than this tree ({_build.source_hash()})")
     _lib = lib
     return lib
 
@@ -162,6 +177,38 @@ class Context:
         check(self.lib.rsk_surface_masks(self.handle, C.c_int32(ne), C.c_int32(ns), ptr(planar), ptr(po), ptr(pn), ptr(tol),
                                          ptr(c), ptr(x), ptr(out)), "rsk_surface_masks")
         return out
+
+    # ---- multi-GPU (rsk_comm.cu)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        check(load().rsk_comm_unique_id(buf), "rsk_comm_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int) -> None:
+        if len(unique_id) != COMM_ID_BYTES:
+            raise ValueError(f"NCCL unique id must be {COMM_ID_BYTES} bytes")
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        check(self.lib.rsk_comm_init(self.handle, buf, C.c_int32(rank), C.c_int32(nranks)), "rsk_comm_init")
+
+    def comm_destroy(self) -> None:
+        check(self.lib.rsk_comm_destroy(self.handle), "rsk_comm_destroy")
+
+    def comm_info(self) -> dict:
+        r, n, v = C.c_int32(0), C.c_int32(1), C.c_int32(0)
+        check(self.lib.rsk_comm_info(self.handle, C.byref(r), C.byref(n), C.byref(v)), "rsk_comm_info")
+        return {"rank": int(r.value), "nranks": int(n.value), "nccl_version": int(v.value)}
+
+    def allreduce_device(self, device_ptr: int, n: int, op: str = "sum") -> None:
+        check(self.lib.rsk_allreduce_i64(self.handle, C.c_void_p(device_ptr), C.c_int64(n), C.c_int32(0 if op == "sum" else 1)),
+              "rsk_allreduce_i64")
+
+    def allreduce_host(self, values: np.ndarray, op: str = "sum") -> np.ndarray:
+        """In-place all-reduce of a small int64 host array over the context's communicator (synchronises)."""
+        assert values.dtype == np.int64 and values.flags.c_contiguous
+        check(self.lib.rsk_allreduce_host_i64(self.handle, ptr(values), C.c_int64(values.size), C.c_int32(0 if op == "sum" else 1)),
+              "rsk_allreduce_host_i64")
+        return values
 
     def reciprocity_rowsum(self, area: np.ndarray, F: np.ndarray, target: Optional[np.ndarray] = None,
                            tol: float = 1e-10, max_iter: int = 500) -> int:
@@ -414,6 +461,22 @@ class Solve:
         check(self.ctx.lib.rsk_solve_read_block(self.handle, ptr(tallies), ptr(iters), ptr(total)), "rsk_solve_read_block")
         return tallies, iters, total
 
+    def read_block_view(self):
+        """``read_block`` without the second host copy: the tallies are a NumPy view of the context's pinned staging
+        area, valid until the next staged download on this context."""
+        nh = (145 if self.discrete else 1) if self.sky else 2 * self.scene.n_surf
+        iters = np.zeros(self.n_local, np.int32)
+        total = np.zeros(self.n_local, np.int64)
+        view = C.POINTER(C.c_int64)()
+        check(self.ctx.lib.rsk_solve_read_block_view(self.handle, C.byref(view), ptr(iters), ptr(total)), "rsk_solve_read_block_view")
+        if self.n_local * nh == 0:
+            return np.zeros((self.n_local, nh), np.int64), iters, total
+        return np.ctypeslib.as_array(view, shape=(self.n_local, nh)), iters, total
+
+    def allreduce_iter_tallies(self, n_jobs: int) -> None:
+        """Sum the iteration tallies of the first ``n_jobs`` (ray-split) jobs over the context's communicator."""
+        check(self.ctx.lib.rsk_solve_allreduce_iter_tallies(self.handle, C.c_int32(n_jobs)), "rsk_solve_allreduce_iter_tallies")
+
     def read_counters(self):
         """(iterations int32 [n_local], total rays int64 [n_local]) without the tally block."""
         iters = np.zeros(self.n_local, np.int32)
@@ -452,6 +515,52 @@ class Solve:
             pass
 
 
+class TallyBlock:
+    """Wraps ``rsk_tally_block``: the device-resident [n_rows, n_cols] int64 block in which the ranks of a sharded solve
+    assemble and sum their results (scatter kernel + NCCL all-reduce + pinned download, all inside the library)."""
+
+    def __init__(self, ctx: Context, n_rows: int, n_cols: int):
+        self.ctx, self.shape = ctx, (int(n_rows), int(n_cols))
+        self.handle = C.c_void_p()
+        check(ctx.lib.rsk_tally_block_create(ctx.handle, C.c_int64(n_rows), C.c_int64(n_cols), C.byref(self.handle)), "rsk_tally_block_create")
+
+    def add_solve(self, solve, keep: Optional[np.ndarray] = None) -> None:
+        k = None if keep is None else np.ascontiguousarray(keep, np.uint8)
+        check(self.ctx.lib.rsk_tally_block_add_solve(self.handle, solve.handle, ptr(k)), "rsk_tally_block_add_solve")
+
+    def allreduce(self) -> None:
+        check(self.ctx.lib.rsk_tally_block_allreduce(self.handle), "rsk_tally_block_allreduce")
+
+    def device_pointer(self):
+        p, n = C.c_void_p(), C.c_int64(0)
+        check(self.ctx.lib.rsk_tally_block_device(self.handle, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def download(self, copy: bool = False) -> np.ndarray:
+        """The block on the host: a view of the context's pinned staging area (valid until the next staged download on
+        this context) or, with ``copy``, an array of its own."""
+        if self.shape[0] * self.shape[1] == 0:
+            return np.zeros(self.shape, np.int64)
+        if copy:
+            out = np.empty(self.shape, np.int64)
+            check(self.ctx.lib.rsk_tally_block_download(self.handle, ptr(out), None), "rsk_tally_block_download")
+            return out
+        view = C.POINTER(C.c_int64)()
+        check(self.ctx.lib.rsk_tally_block_download(self.handle, None, C.byref(view)), "rsk_tally_block_download")
+        return np.ctypeslib.as_array(view, shape=self.shape)
+
+    def close(self) -> None:
+        if self.handle:
+            self.ctx.lib.rsk_tally_block_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class _SolvePart:
     """Read-only view of one side of a dual solve (shares Solve.read_block)."""
 
@@ -459,7 +568,9 @@ class _SolvePart:
         self.ctx, self.scene, self.handle, self.n_local, self.sky, self.discrete = ctx, scene, handle, n_local, sky, discrete
 
     read_block = Solve.read_block
+    read_block_view = Solve.read_block_view
     read_counters = Solve.read_counters
+    allreduce_iter_tallies = Solve.allreduce_iter_tallies
     enqueue_fold = Solve.enqueue_fold
     poll = Solve.poll
     device_iter_tallies = Solve.device_iter_tallies

@@ -1,7 +1,7 @@
 // rsk_api.cu -- the extern "C" boundary of librsk_b200 (include/raystrack_b200.h).
 #include <cstdarg>
 
-#include "rsk_stats.cuh"
+#include "rsk_solve.cuh"
 
 static thread_local char g_error[1024] = "";
 thread_local cudaStream_t rsk_tl_stream = nullptr;
@@ -15,6 +15,10 @@ void rsk_set_error(const char *fmt, ...) {
 
 extern "C" const char *rsk_last_error(void) { return g_error; }
 extern "C" int rsk_abi_version(void) { return RSK_ABI_VERSION; }
+#ifndef RSK_SOURCE_HASH
+#define RSK_SOURCE_HASH "unknown"
+#endif
+extern "C" const char *rsk_source_hash(void) { return RSK_SOURCE_HASH; }
 
 extern "C" int rsk_device_count(int *count) {
     RSK_REQUIRE(count, "rsk_device_count: null output");
@@ -53,9 +57,16 @@ extern "C" int rsk_ctx_create(int device, void *stream, rsk_ctx **out) {
         if (e != cudaSuccess) { delete ctx; rsk_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return RSK_ERR_CUDA; }
         ctx->own_stream = true;
     }
-    cudaEventCreate(&ctx->ev0);
-    cudaEventCreate(&ctx->ev1);
-    cudaMallocHost((void **)&ctx->h_pinned, 16 * sizeof(int32_t));
+    {
+        cudaError_t e = cudaEventCreate(&ctx->ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+        if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_pinned, 16 * sizeof(int32_t));
+        if (e != cudaSuccess) {
+            rsk_set_error("rsk_ctx_create: %s", cudaGetErrorString(e));
+            rsk_ctx_destroy(ctx);
+            return e == cudaErrorMemoryAllocation ? RSK_ERR_OOM : RSK_ERR_CUDA;
+        }
+    }
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -70,13 +81,15 @@ extern "C" int rsk_ctx_create(int device, void *stream, rsk_ctx **out) {
 
 extern "C" int rsk_ctx_destroy(rsk_ctx *ctx) {
     if (!ctx) return RSK_OK;
+    if (ctx->comm) rsk_comm_destroy(ctx);
     RskScope scope(ctx);
     rsk_dev_free(ctx->halton);
     rsk_dev_free(ctx->grid);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    cudaEventDestroy(ctx->ev0);
-    cudaEventDestroy(ctx->ev1);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RSK_OK;
@@ -406,31 +419,6 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
 
 // ----------------------------------------------------------------------------- solves
 
-struct rsk_solve {
-    rsk_ctx *ctx = nullptr;
-    rsk_scene *scene = nullptr;
-    rsk_emitters *em = nullptr;
-    int mode = MODE_MATRIX;
-    int32_t n_local = 0, n_hist = 0, discrete = 0;
-    rsk_solve_params p{};
-    int64_t n_tiles = 0;
-    int32_t tile_rays = RSK_TILE_RAYS_MAX;
-    // device state
-    int32_t *min_sid = nullptr;
-    int32_t *emit_ids = nullptr, *rot_base = nullptr, *iters_done = nullptr, *done = nullptr, *not_conv = nullptr, *have_prev = nullptr;
-    int64_t *tile_start = nullptr, *n_rays_once = nullptr, *total_rays = nullptr, *ray_begin = nullptr, *ray_end = nullptr;
-    uint32_t *mask = nullptr;
-    float *cp_table = nullptr;
-    unsigned long long *iter_tally = nullptr, *rays_traced = nullptr;
-    long long *total = nullptr;
-    double *mean = nullptr, *m2 = nullptr, *prev = nullptr;
-    int32_t *n_active = nullptr;
-    int32_t *h_pinned = nullptr;     // [0] n_active
-    int32_t last_active = 0;
-    bool stepped = false;
-    bool external_tally = false;     // iter_tally belongs to the caller (rsk_solve_set_iter_tally_buffer)
-    rsk_solve *twin = nullptr;       // dual solves: the sky side (this object is the matrix side)
-};
 
 static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int mode, int discrete,
                            const int32_t *emit_ids, int32_t n_local, const uint8_t *surf_active,
@@ -687,6 +675,24 @@ extern "C" int rsk_solve_read_block(rsk_solve *s, int64_t *tallies, int32_t *ite
     RSK_TRY(rsk_read_common(s, iters, total_rays));
     const size_t nh = (size_t)s->n_local * s->n_hist;
     if (tallies && nh) RSK_CUDA(cudaMemcpyAsync(tallies, s->total, nh * 8, cudaMemcpyDeviceToHost, s->ctx->stream));
+    RSK_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    return RSK_OK;
+}
+
+// The same through the context's pinned staging area, without a second host copy: *tallies_view points INTO that
+// area (valid until the next staged download on this context).
+extern "C" int rsk_solve_read_block_view(rsk_solve *s, int64_t **tallies_view, int32_t *iters, int64_t *total_rays) {
+    RSK_REQUIRE(s && tallies_view, "rsk_solve_read_block_view: null argument");
+    RskScope scope(s->ctx);
+    *tallies_view = nullptr;
+    RSK_TRY(rsk_read_common(s, iters, total_rays));
+    const size_t nh = (size_t)s->n_local * s->n_hist;
+    if (nh) {
+        void *stage = nullptr;
+        RSK_TRY(rsk_ctx_stage(s->ctx, nh * 8, &stage));
+        RSK_CUDA(cudaMemcpyAsync(stage, s->total, nh * 8, cudaMemcpyDeviceToHost, s->ctx->stream));
+        *tallies_view = (int64_t *)stage;
+    }
     RSK_CUDA(cudaStreamSynchronize(s->ctx->stream));
     return RSK_OK;
 }

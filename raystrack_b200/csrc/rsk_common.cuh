@@ -137,7 +137,16 @@ struct rsk_ctx {
     std::map<int, std::pair<int64_t, int64_t>> grid_index;   // g -> (offset, cells) inside grid
     float2 *grid = nullptr;
     int64_t grid_cap = 0, grid_used = 0;
+    // multi-GPU (rsk_comm.cu): NCCL communicator of this context, small device scratch for host-value all-reduces
+    void *comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    long long *comm_scratch = nullptr;
+    // pinned staging area for large downloads (grow-only)
+    void *stage = nullptr;
+    size_t stage_cap = 0;
 };
+constexpr int RSK_COMM_SCRATCH = 4096;     // int64 elements of rsk_ctx::comm_scratch
+int rsk_ctx_stage(rsk_ctx *ctx, size_t bytes, void **stage);
 
 struct rsk_scene {
     rsk_ctx *ctx = nullptr;

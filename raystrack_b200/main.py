@@ -213,49 +213,68 @@ def _run_solve(solve: _native.Solve, min_iters: int, max_iters: int) -> None:
         done += chunk
 
 
-def _run_solve_shared(solve: _native.Solve, n_shared: int, min_iters: int, max_iters: int, device: int) -> None:
+def _run_solve_shared(solve, n_shared: int, min_iters: int, max_iters: int, exchange: str) -> None:
     """Multi-GPU variant when some emitters are ray-split over the ranks: per iteration trace -> all-reduce of the
-    shared jobs' iteration tallies (NCCL, on the solve's stream) -> statistics.  Every rank issues the same
-    sequence of collectives; the loop ends when no rank has a running job."""
+    shared jobs' iteration tallies -> statistics.  ``exchange`` "native": the library's NCCL communicator, on the
+    solve's stream (rsk_solve_allreduce_iter_tallies); "host": torch.distributed on host tensors (CPU stand-ins of
+    the tests).  Every rank issues the same sequence of collectives; the loop ends when no rank has a running job."""
     from . import dist as D
     if max_iters <= 0:
         return
-    tally = D.attach_tally_tensor(solve, n_shared, device)
+    tally = D.attach_tally_tensor(solve, n_shared) if exchange == "host" else None
     done = 0
     chunk = max(1, min(int(max_iters), max(int(min_iters), 1)))
     while done < max_iters:
         for _ in range(chunk):
             solve.enqueue_trace()
-            D.all_reduce_device_(tally, device)
+            if exchange == "host":
+                D.all_reduce_tensor_(tally)
+            elif n_shared and solve.n_local:
+                solve.allreduce_iter_tallies(n_shared)
             solve.enqueue_fold()
         done += chunk
         active = solve.poll() if solve.n_local else 0
-        if D.max_over_ranks(float(active), device) <= 0:
+        if D.max_over_ranks(float(active)) <= 0:
             break
         chunk = min(4, max_iters - done)
 
 
+_DIST_OVERRIDE: Optional[Tuple[int, int]] = None     # tests / bench.py: (0, 1) solves unsharded inside a process group
+
+
 def _dist_env() -> Tuple[int, int]:
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            return dist.get_rank(), dist.get_world_size()
-    except Exception:
-        pass
-    return 0, 1
+    """(rank, world) of this process: the library's own communicator if there is one, else the torch process group."""
+    if _DIST_OVERRIDE is not None:
+        return _DIST_OVERRIDE
+    from . import dist as D
+    if D.native_comm_active():
+        return D.native_comm_env()
+    return D._torch_group()
 
 
 def _context() -> _native.Context:
-    """The CUDA context of this process.  Under torch.distributed/NCCL the library shares torch's current stream
-    so that collectives and kernels are ordered without host synchronisation."""
-    rank, world = _dist_env()
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        if dist.get_backend() == "nccl":
-            dev = torch.cuda.current_device()
-            return _native.Context.for_device(dev, _native.torch_stream_handle(dev))
+    """The CUDA context of this process.  With more than one rank it is the context that owns the library's NCCL
+    communicator (joined on first use when a torch process group exists), so that collectives and kernels are ordered
+    on one stream without host synchronisation."""
+    if _DIST_OVERRIDE is None:
+        from . import dist as D
+        ctx = D.native_comm_context(create=True)
+        if ctx is not None:
+            return ctx
     return _native.Context.for_device()
+
+
+def _exchange_kind(ctx, world: int) -> Optional[str]:
+    """How the ranks exchange tallies DURING a solve (needed to ray-split an emitter): "native" = the library's NCCL
+    communicator on the context's stream; "host" = torch.distributed on host tensors, only for the CPU stand-ins of
+    the tests; None = no ordered exchange available (e.g. a gloo group on a GPU box without NCCL) -- emitters are then
+    assigned whole and the results summed once at the end."""
+    if world <= 1:
+        return None
+    if isinstance(ctx, _native.Context):
+        from . import dist as D
+        return "native" if D.native_comm_active() and D.native_comm_context() is ctx else None
+    return "host"
 
 
 def _plan_chunks(plan: List[Tuple[int, int, int, bool]], n_hist: int) -> List[List[Tuple[int, int, int, bool]]]:
@@ -282,7 +301,8 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
     n_emit = active.shape[0]
     n_surf = active.shape[1]
     rank, world = _dist_env()
-    all_plans = plan_shards(todo, n_rays_once, world)
+    exchange = _exchange_kind(ctx, world)
+    all_plans = plan_shards(todo, n_rays_once, world, allow_split=exchange is not None)
     plan = all_plans[rank]
     any_shared = world > 1 and any(j[3] for shard in all_plans for j in shard)
     n_hist = (145 if discrete else 1) if sky else 2 * n_surf
@@ -290,60 +310,67 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
     chunks = _plan_chunks(plan, n_hist)
 
     single = world == 1 and len(chunks) == 1 and len(plan) == n_emit
-    # Under NCCL the tally blocks never visit the host before they are summed (dist.DeviceReducer).
-    reducer = None
-    if world > 1 and hasattr(_native.Solve, "device_tallies"):
-        from . import dist as D
-        if D.nccl_active():
-            reducer = D.DeviceReducer(n_emit, n_hist, ctx.device)
+    # With the library communicator the tally blocks never visit the host before they are summed: every rank scatters
+    # the rows of its solves into a zeroed device block, one NCCL all-reduce adds the blocks up over NVLink, and the
+    # result comes back in a single copy through pinned memory.
+    block = _native.TallyBlock(ctx, n_emit, n_hist) if exchange == "native" else None
     tallies = iters = totals = None
     if not single:
-        tallies = None if reducer is not None else np.zeros((n_emit, n_hist), np.int64)
+        tallies = None if block is not None else np.zeros((n_emit, n_hist), np.int64)
         iters = np.zeros(n_emit, np.int64)
         totals = np.zeros(n_emit, np.int64)
-    for c, chunk in enumerate(chunks):
-        ids = np.asarray([j[0] for j in chunk], np.int32)
-        ranges = np.asarray([[j[1], j[2]] for j in chunk], np.int64).reshape(-1, 2)
-        kw = {}
-        if not sky:
-            kw = dict(emit_sid=np.asarray(emit_sid)[ids], min_sid=np.asarray(min_sid)[ids])
-        with _Phase("solve_begin"):
-            solve = _native.Solve(ctx, d_scene.native, d_em.native, ids,
-                                  active[ids] if len(chunk) else np.zeros((0, n_surf), np.uint8),
-                                  table, ids.copy(), max_iters=max_iters, min_iters=min_iters, interval=interval,
-                                  tol_mode=tol_mode, tol=tol, sky=sky, discrete=discrete, ray_range=ranges, **kw)
-        try:
-            with _Phase("iterate"):
-                if any_shared and c == 0:
-                    _run_solve_shared(solve, sum(1 for j in chunk if j[3]), min_iters, max_iters, ctx.device)
+    try:
+        for c, chunk in enumerate(chunks):
+            ids = np.asarray([j[0] for j in chunk], np.int32)
+            ranges = np.asarray([[j[1], j[2]] for j in chunk], np.int64).reshape(-1, 2)
+            kw = {}
+            if not sky:
+                kw = dict(emit_sid=np.asarray(emit_sid)[ids], min_sid=np.asarray(min_sid)[ids])
+            with _Phase("solve_begin"):
+                solve = _native.Solve(ctx, d_scene.native, d_em.native, ids,
+                                      active[ids] if len(chunk) else np.zeros((0, n_surf), np.uint8),
+                                      table, ids.copy(), max_iters=max_iters, min_iters=min_iters, interval=interval,
+                                      tol_mode=tol_mode, tol=tol, sky=sky, discrete=discrete, ray_range=ranges, **kw)
+            try:
+                with _Phase("iterate"):
+                    if any_shared and c == 0:
+                        _run_solve_shared(solve, sum(1 for j in chunk if j[3]), min_iters, max_iters, exchange)
+                    else:
+                        _run_solve(solve, min_iters, max_iters)
+                keep = np.asarray([not (j[3] and rank != 0) for j in chunk], bool)     # replicated (ray-split) jobs count once
+                with _Phase("download"):
+                    if block is not None:
+                        it_loc, tot_loc = solve.read_counters()
+                        block.add_solve(solve, keep)
+                        loc = None
+                    elif single and hasattr(solve, "read_block_view"):
+                        loc, it_loc, tot_loc = solve.read_block_view()
+                    else:
+                        loc, it_loc, tot_loc = solve.read_block()
+            finally:
+                with _Phase("solve_end"):
+                    solve.close()
+            if single:
+                return loc, it_loc.astype(np.int64), tot_loc      # every emitter, in order: no scatter needed
+            if keep.any():
+                if loc is not None:
+                    tallies[ids[keep]] = loc[keep]
+                iters[ids[keep]] = it_loc[keep]
+                totals[ids[keep]] = tot_loc[keep]
+        if world > 1:
+            from .dist import allreduce_sum_
+            with _Phase("all_reduce"):
+                if block is not None:
+                    block.allreduce()
+                    tallies = block.download()
+                    allreduce_sum_([iters, totals])
                 else:
-                    _run_solve(solve, min_iters, max_iters)
-            keep = np.asarray([not (j[3] and rank != 0) for j in chunk], bool)     # replicated (ray-split) jobs count once
-            with _Phase("download"):
-                if reducer is not None:
-                    it_loc, tot_loc = solve.read_counters()
-                    reducer.add_rows(ids, solve.device_tallies()[0], len(chunk), keep)
-                    loc = None
-                else:
-                    loc, it_loc, tot_loc = solve.read_block()
-        finally:
-            with _Phase("solve_end"):
-                solve.close()
-        if single:
-            return loc, it_loc.astype(np.int64), tot_loc      # every emitter, in order: no scatter needed
-        if keep.any():
-            if loc is not None:
-                tallies[ids[keep]] = loc[keep]
-            iters[ids[keep]] = it_loc[keep]
-            totals[ids[keep]] = tot_loc[keep]
-    if world > 1:
-        from .dist import allreduce_sum_
-        with _Phase("all_reduce"):
-            if reducer is not None:
-                tallies = reducer.finish()
-                allreduce_sum_([iters, totals], device=ctx.device)
-            else:
-                allreduce_sum_([tallies, iters, totals], device=ctx.device)
+                    allreduce_sum_([tallies, iters, totals], device=getattr(ctx, "device", 0))
+        elif block is not None:
+            tallies = block.download()
+    finally:
+        if block is not None:
+            block.close()
     return tallies, iters, totals
 
 
@@ -546,61 +573,78 @@ def _shared_ray_solve(meshes, matrix_params: MatrixParams, sky_params: SkyParams
         return dict(max_iters=p["max_iters"], min_iters=p["min_iters"], tol=p["tol"], tol_mode=p["tol_mode"],
                     interval=max(1, int(p["convergence_interval"])) if schedule == "gpu" else 1)
 
-    # Emitters are independent: under torch.distributed every rank solves its share (whole emitters, plus a ray slice of
+    # Emitters are independent: with several ranks every rank solves its share (whole emitters, plus a ray slice of
     # every oversized one, exactly as _solve_sharded does) and the integer results are summed once at the end.
     rank, world = _dist_env()
+    exchange = _exchange_kind(ctx, world)
     n_once = [int(em.n_cells * int(mp["rays"])) for em in emitters]
     n_sky = 145 if sp["discrete"] else 1
-    out_m = (np.zeros((n_surf, 2 * n_surf), np.int64), np.zeros(n_surf, np.int64), np.zeros(n_surf, np.int64))
-    out_s = (np.zeros((n_surf, n_sky), np.int64), np.zeros(n_surf, np.int64), np.zeros(n_surf, np.int64))
+    blocks = (_native.TallyBlock(ctx, n_surf, 2 * n_surf), _native.TallyBlock(ctx, n_surf, n_sky)) if exchange == "native" else None
+    out_m = [None if blocks else np.zeros((n_surf, 2 * n_surf), np.int64), np.zeros(n_surf, np.int64), np.zeros(n_surf, np.int64)]
+    out_s = [None if blocks else np.zeros((n_surf, n_sky), np.int64), np.zeros(n_surf, np.int64), np.zeros(n_surf, np.int64)]
     limit = max(int(mp["max_iters"]), int(sp["max_iters"]))
     first = max(1, min(limit, max(1, min(int(mp["min_iters"]), int(sp["min_iters"])))))
-    all_plans = plan_shards(list(range(n_surf)), n_once, world)
+    all_plans = plan_shards(list(range(n_surf)), n_once, world, allow_split=exchange == "native")
     any_shared = world > 1 and any(j[3] for shard in all_plans for j in shard)
-    for c, plan in enumerate(_plan_chunks(all_plans[rank], 2 * n_surf + n_sky)):
-        mine = np.asarray([j[0] for j in plan], np.int32)
-        ranges = np.asarray([[j[1], j[2]] for j in plan], np.int64).reshape(-1, 2)
-        n_shared = sum(1 for j in plan if j[3])
-        keep = np.asarray([not (j[3] and rank != 0) for j in plan], bool)      # ray-split jobs are replicated: count once
-        solve = _native.DualSolve(ctx, d_scene.native, d_em.native, mine, active[mine] if mine.size else np.zeros((0, n_surf), np.uint8),
-                                  table, mine.copy(), ids[mine], min_sid[mine], side(mp), side(sp), bool(sp["discrete"]),
-                                  ray_range=ranges if world > 1 else None)
-        try:
-            if any_shared and c == 0:
-                # split-phase: trace, sum the iteration tallies of the ray-split jobs (both sides) over the ranks, fold
-                from . import dist as D
-                tm = D.attach_tally_tensor(solve.matrix_part, n_shared, ctx.device)
-                ts = D.attach_tally_tensor(solve.sky_part, n_shared, ctx.device)
-                done, chunk = 0, first
-                while done < limit:
-                    for _ in range(chunk):
-                        solve.enqueue_trace()
-                        D.all_reduce_device_(tm, ctx.device)
-                        D.all_reduce_device_(ts, ctx.device)
-                        solve.matrix_part.enqueue_fold()
-                        solve.sky_part.enqueue_fold()
-                    done += chunk
-                    running = (solve.matrix_part.poll() + solve.sky_part.poll()) if mine.size else 0
-                    if D.max_over_ranks(float(running), ctx.device) <= 0:
-                        break
-                    chunk = min(4, limit - done)
-            elif mine.size and limit > 0:
-                running = solve.step(first)
-                done = first
-                while running > 0 and done < limit:
-                    chunk = min(4, limit - done)
-                    running = solve.step(chunk)
-                    done += chunk
-            if mine.size:
-                for part, out in ((solve.matrix_part, out_m), (solve.sky_part, out_s)):
-                    t, i, r = part.read_block()
-                    out[0][mine[keep]], out[1][mine[keep]], out[2][mine[keep]] = t[keep], i.astype(np.int64)[keep], r[keep]
-        finally:
-            solve.close()
-    if world > 1:
-        from .dist import allreduce_sum_
-        allreduce_sum_([*out_m, *out_s], device=ctx.device)
-    return out_m, out_s
+    try:
+        for c, plan in enumerate(_plan_chunks(all_plans[rank], 2 * n_surf + n_sky)):
+            mine = np.asarray([j[0] for j in plan], np.int32)
+            ranges = np.asarray([[j[1], j[2]] for j in plan], np.int64).reshape(-1, 2)
+            n_shared = sum(1 for j in plan if j[3])
+            keep = np.asarray([not (j[3] and rank != 0) for j in plan], bool)      # ray-split jobs are replicated: count once
+            solve = _native.DualSolve(ctx, d_scene.native, d_em.native, mine, active[mine] if mine.size else np.zeros((0, n_surf), np.uint8),
+                                      table, mine.copy(), ids[mine], min_sid[mine], side(mp), side(sp), bool(sp["discrete"]),
+                                      ray_range=ranges if world > 1 else None)
+            try:
+                if any_shared and c == 0:
+                    # split-phase: trace, sum the iteration tallies of the ray-split jobs (both sides) over the ranks, fold
+                    from . import dist as D
+                    done, chunk = 0, first
+                    while done < limit:
+                        for _ in range(chunk):
+                            solve.enqueue_trace()
+                            if n_shared and mine.size:
+                                solve.matrix_part.allreduce_iter_tallies(n_shared)
+                                solve.sky_part.allreduce_iter_tallies(n_shared)
+                            solve.matrix_part.enqueue_fold()
+                            solve.sky_part.enqueue_fold()
+                        done += chunk
+                        running = (solve.matrix_part.poll() + solve.sky_part.poll()) if mine.size else 0
+                        if D.max_over_ranks(float(running)) <= 0:
+                            break
+                        chunk = min(4, limit - done)
+                elif mine.size and limit > 0:
+                    running = solve.step(first)
+                    done = first
+                    while running > 0 and done < limit:
+                        chunk = min(4, limit - done)
+                        running = solve.step(chunk)
+                        done += chunk
+                if mine.size:
+                    for k, (part, out) in enumerate(((solve.matrix_part, out_m), (solve.sky_part, out_s))):
+                        if blocks:
+                            i, r = part.read_counters()
+                            blocks[k].add_solve(part, keep)
+                        else:
+                            t, i, r = part.read_block()
+                            out[0][mine[keep]] = t[keep]
+                        out[1][mine[keep]], out[2][mine[keep]] = i.astype(np.int64)[keep], r[keep]
+            finally:
+                solve.close()
+        if blocks:
+            for k, out in enumerate((out_m, out_s)):
+                blocks[k].allreduce()
+                out[0] = blocks[k].download(copy=True)          # two blocks share the context's staging area: copy
+        if world > 1:
+            from .dist import allreduce_sum_
+            if blocks:
+                allreduce_sum_([out_m[1], out_m[2], out_s[1], out_s[2]])
+            else:
+                allreduce_sum_([*out_m, *out_s], device=getattr(ctx, "device", 0))
+    finally:
+        for blk in blocks or ():
+            blk.close()
+    return tuple(out_m), tuple(out_s)
 
 
 def view_factor_matrix_and_sky(meshes: List[Mesh], *, matrix_params: MatrixParams, sky_params: SkyParams,

@@ -66,16 +66,16 @@ def main():
     assert M.view_factor_matrix_and_sky(meshes, matrix_params=mp_, sky_params=sp_) == both, "chunked dual solve differs"
     del os.environ["RSK_SOLVE_MEMORY_MB"]
     print(f"[rank {rank}/{world}] shared-ray workflow == separate solves", flush=True)
+    # the same ray-split solve unsharded on this rank's GPU: bit-identical
+    M._DIST_OVERRIDE = (0, 1)
+    try:
+        assert json.dumps(rb.view_factor_matrix(meshes, prm), sort_keys=True, default=float) == blob, "multi-GPU result differs from the single-GPU result"
+    finally:
+        M._DIST_OVERRIDE = None
     if rank == 0:
-        # single-GPU run of the same solve inside this process group is not possible; compare with a saved file if present
-        ref_file = ROOT / "gpurun_out" / "dist_ref_single.json"
-        if world == 1:
-            ref_file.parent.mkdir(exist_ok=True)
-            ref_file.write_text(blob)
-        elif ref_file.exists():
-            assert ref_file.read_text() == blob, "multi-GPU result differs from the single-GPU result"
-            print(f"[rank 0] ray-split solve ({n_shared} shared emitters per rank) == single-GPU result, bit for bit", flush=True)
+        print(f"[rank 0] ray-split solve ({n_shared} shared emitters per rank) == single-GPU result, bit for bit", flush=True)
         print(f"DIST_CHECK_OK world={world} shared={n_shared} worst={worst_all:.2e}", flush=True)
+    D.shutdown_native()
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, missing
     assert set(_native.EXPORTS) == set(declared_symbols())
-    assert lib.rsk_abi_version() == 1
+    assert lib.rsk_abi_version() == 2
 
 
 def test_sm100a_code_is_embedded():
