@@ -194,6 +194,7 @@ struct TraceArgs {
     const int64_t *tile_start;      // [n_local+1] exclusive prefix of tiles per job
     int32_t n_local;
     int32_t tile_rays;              // rays per CTA tile of this launch
+    int32_t class_mod;              // hand-out units are residue classes of the ray index modulo this (1 = consecutive rays)
     const uint32_t *surf_mask;      // [n_local][mask_words], bit set = surface is a receiver/occluder
     const float *cp_table;          // [n_rot][7]
     const int32_t *rot_base;        // [n_local]
@@ -238,6 +239,21 @@ static inline int rsk_pick_tile_rays(int64_t total_rays, int sm_count) {
     if (t > 4096 && total_rays / t < 8 * wave) t = 4096;
     while (t > 512 && total_rays / t < 2 * wave) t >>= 1;
     return t;
+}
+// Rays are handed to warps in residue classes of the ray index k modulo M.  The per-ray Halton values are radical
+// inverses of k + 1: rays with equal (k + 1) mod 5^a share the leading a base-5 digits of the triangle-pick value (they
+// start from the same 1/5^a slice of the emitter's area CDF), rays with equal (k + 1) mod 11 share the leading digit of
+// the azimuth value, mod 7 the elevation band.  M = 275 = 25 * 11: 1/25 of the emitter x one azimuth sector of 33
+// degrees -- ~30 rays per class in an 8192-ray tile, one warp's worth.  RSK_CLASS_MOD overrides (1 = consecutive rays).
+static inline int rsk_pick_class_mod(int tile_rays) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("RSK_CLASS_MOD");
+        forced = e ? atoi(e) : 0;
+        if (forced < 0 || forced > 4096) forced = 0;
+    }
+    if (forced) return forced;
+    return 1;
 }
 int rsk_qmc_ensure_halton(rsk_ctx *ctx, int64_t n);
 int rsk_qmc_ensure_grid(rsk_ctx *ctx, int g, int64_t *offset);

@@ -179,6 +179,10 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
     const bool debug_out = MODE != MODE_DUAL && (a.dbg_hit || a.dbg_orig || a.dbg_dirs || a.dbg_front);
 
     const int tile_n = (int)(end - begin);
+    // hand-out units of the tile's rays (see the refill below)
+    const int class_mod = (a.class_mod > 1 && tile_n >= 24 * a.class_mod) ? a.class_mod : 1;
+    const int class_phase = (int)((begin + 1) % class_mod);
+    const int n_units = class_mod * (((tile_n + class_mod - 1) / class_mod + 31) / 32);
     float *s_rays = reinterpret_cast<float *>(smem + STACK_WORDS + LUT_WORDS) + warp * (7 * RAY_SLOTS);
     int buf_n = 0;
     bool pool_empty = tile_n <= 0;
@@ -230,20 +234,27 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
         if (need) {
             const int n_need = __popc(need);
             if (buf_n < n_need && !pool_empty) {
-                // the rays of the tile are one pool: a warp that runs out takes the next 32, whichever warp it is
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_next, 32);
-                base = __shfl_sync(FULL, base, 0);
-                const int made = max(0, min(32, tile_n - base));
-                if (lane < made) {
-                    const int pos = base + lane;
+                // the rays of the tile are one pool: a warp that runs out takes the next hand-out unit, whichever warp
+                // it is.  A unit is up to 32 rays of one residue class of the ray index modulo class_mod (see
+                // rsk_pick_class_mod): rays whose Halton digits agree start from the same strip of the emitter and
+                // leave into the same azimuth sector, so the lanes of a warp walk neighbouring nodes.
+                int unit = 0;
+                if (lane == 0) unit = atomicAdd(&s_next, 1);
+                unit = __shfl_sync(FULL, unit, 0);
+                const int cls = unit % class_mod, sub = unit / class_mod;
+                int first = cls - class_phase;          // smallest pos >= 0 with (begin + pos + 1) % class_mod == cls
+                if (first < 0) first += class_mod;
+                const int pos = first + (sub * 32 + lane) * class_mod;
+                const bool valid = unit < n_units && pos < tile_n;
+                const int made = __popc(__ballot_sync(FULL, valid));       // valid lanes are a prefix (pos grows with lane)
+                if (valid) {
                     const Ray r = rsk_make_ray(a.ev, e, begin + pos, cp);
                     float *slot = s_rays + buf_n + lane;
                     slot[0 * RAY_SLOTS] = r.ox; slot[1 * RAY_SLOTS] = r.oy; slot[2 * RAY_SLOTS] = r.oz;
                     slot[3 * RAY_SLOTS] = r.dx; slot[4 * RAY_SLOTS] = r.dy; slot[5 * RAY_SLOTS] = r.dz;
                     slot[6 * RAY_SLOTS] = __int_as_float(pos);
                 }
-                pool_empty = base + 32 >= tile_n;
+                pool_empty = unit + 1 >= n_units;
                 buf_n += made;
                 __syncwarp();
             }
@@ -395,6 +406,7 @@ int rsk_launch_trace(rsk_ctx *ctx, TraceArgs &a, int mode, int64_t n_tiles) {
     // shared-memory histogram when it leaves room for >= 2 CTAs per SM, else warp-aggregated global atomics
     a.hist_in_smem = (((size_t)a.n_hist + (mode == MODE_DUAL ? a.n_hist2 : 0)) * 4 <= 96 * 1024) ? 1 : 0;
     const bool bvh = a.sc.use_bvh != 0;
+    a.class_mod = rsk_pick_class_mod(a.tile_rays);
     if (mode == MODE_DUAL) return bvh ? rsk_launch_one<MODE_DUAL, true>(ctx, a, n_tiles) : rsk_launch_one<MODE_DUAL, false>(ctx, a, n_tiles);
     if (mode == MODE_MATRIX) return bvh ? rsk_launch_one<MODE_MATRIX, true>(ctx, a, n_tiles) : rsk_launch_one<MODE_MATRIX, false>(ctx, a, n_tiles);
     return bvh ? rsk_launch_one<MODE_SKY, true>(ctx, a, n_tiles) : rsk_launch_one<MODE_SKY, false>(ctx, a, n_tiles);
