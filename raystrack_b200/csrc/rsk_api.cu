@@ -369,14 +369,15 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
     const int nw = (scene->n_surf + 31) / 32;
     std::vector<uint32_t> mask(std::max(nw, 1));
     rsk_pack_mask(surf_active, scene->n_surf, emit_sid, min_sid, mask.data());
-    const int tile_rays = rsk_pick_tile_rays(n_rays, ctx->sm_count);
-    const int64_t n_tiles = (n_rays + tile_rays - 1) / tile_rays;
-    const int64_t tiles[2] = {0, n_tiles};
     const int32_t zero = 0;
     const int64_t range[2] = {first_ray, first_ray + n_rays};
+    std::vector<TileDesc> tiles;
+    int tile_rays = 0;
+    rsk_build_tiles(range, range + 1, 1, ctx->sm_count, tiles, &tile_rays);
+    const int64_t n_tiles = (int64_t)tiles.size();
     const int32_t msid1 = mode == MODE_MATRIX ? min_sid : 0;
 
-    uint32_t *d_mask = nullptr; float *d_cp = nullptr; int32_t *d_ids = nullptr, *d_zero = nullptr; int64_t *d_tiles = nullptr, *d_range = nullptr; int32_t *d_msid = nullptr;
+    uint32_t *d_mask = nullptr; float *d_cp = nullptr; int32_t *d_ids = nullptr, *d_zero = nullptr; TileDesc *d_tiles = nullptr; int64_t *d_range = nullptr; int32_t *d_msid = nullptr;
     float *d_orig = nullptr, *d_dirs = nullptr; int32_t *d_hit = nullptr; uint8_t *d_front = nullptr;
     auto cleanup = [&]() { rsk_dev_free(d_mask); rsk_dev_free(d_cp); rsk_dev_free(d_ids); rsk_dev_free(d_zero); rsk_dev_free(d_tiles); rsk_dev_free(d_range); rsk_dev_free(d_msid);
                            rsk_dev_free(d_orig); rsk_dev_free(d_dirs); rsk_dev_free(d_hit); rsk_dev_free(d_front); };
@@ -387,7 +388,7 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
     T_TRY(rsk_upload(ctx, &d_cp, cp, 7));
     T_TRY(rsk_upload(ctx, &d_ids, &emitter, 1));
     T_TRY(rsk_upload(ctx, &d_zero, &zero, 1));
-    T_TRY(rsk_upload(ctx, &d_tiles, tiles, 2));
+    T_TRY(rsk_upload(ctx, &d_tiles, tiles.data(), tiles.size()));
     T_TRY(rsk_upload(ctx, &d_range, range, 2));
     T_TRY(rsk_upload(ctx, &d_msid, &msid1, 1));
     if (orig) T_TRY(rsk_dev_alloc(&d_orig, (size_t)n_rays * 3));
@@ -399,7 +400,7 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
     memset(&a, 0, sizeof(a));
     a.sc = scene->view();
     a.ev = em->view();
-    a.emit_ids = d_ids; a.tile_start = d_tiles; a.n_local = 1; a.tile_rays = tile_rays; a.surf_mask = d_mask;
+    a.emit_ids = d_ids; a.tiles = d_tiles; a.n_local = 1; a.tile_rays = tile_rays; a.surf_mask = d_mask;
     a.cp_table = d_cp; a.rot_base = d_zero; a.iters_done = d_zero; a.done = nullptr; a.tally = nullptr;
     a.n_hist = mode == MODE_MATRIX ? 2 * scene->n_surf : RSK_TREGENZA_BINS;
     a.ray_begin = d_range; a.ray_end = d_range + 1; a.dbg_base = first_ray; a.min_sid = d_msid;
@@ -437,7 +438,8 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
     s->n_hist = mode == MODE_MATRIX ? 2 * scene->n_surf : (discrete ? RSK_TREGENZA_BINS : 1);
     const int nw = std::max((scene->n_surf + 31) / 32, 1);
     std::vector<uint32_t> mask((size_t)n_local * nw);
-    std::vector<int64_t> tiles(n_local + 1, 0), once(n_local), rbeg(n_local), rend(n_local);
+    std::vector<int64_t> once(n_local), rbeg(n_local), rend(n_local);
+    std::vector<TileDesc> tiles;
     std::vector<int32_t> msid(n_local, 0);
     int rc = RSK_OK;
     for (int k = 0; k < n_local; ++k) {
@@ -451,13 +453,8 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
         rend[k] = ray_range ? ray_range[2 * k + 1] : once[k];
         if (rbeg[k] < 0 || rend[k] < rbeg[k] || rend[k] > once[k]) { rsk_set_error("solve begin: ray range out of bounds"); rc = RSK_ERR_INVALID; break; }
     }
-    if (rc == RSK_OK) {
-        int64_t total = 0;
-        for (int k = 0; k < n_local; ++k) total += rend[k] - rbeg[k];
-        s->tile_rays = rsk_pick_tile_rays(total, ctx->sm_count);
-        for (int k = 0; k < n_local; ++k) tiles[k + 1] = tiles[k] + (rend[k] - rbeg[k] + s->tile_rays - 1) / s->tile_rays;
-    }
-    s->n_tiles = tiles[n_local];
+    if (rc == RSK_OK) rsk_build_tiles(rbeg.data(), rend.data(), n_local, ctx->sm_count, tiles, &s->tile_rays);
+    s->n_tiles = (int64_t)tiles.size();
     const size_t nh = (size_t)n_local * s->n_hist;
     auto fail = [&](int code) { rsk_solve_destroy(s); return code; };
     if (rc != RSK_OK) return fail(rc);
@@ -466,7 +463,7 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
     S_TRY(rsk_upload(ctx, &s->emit_ids, emit_ids, n_local));
     S_TRY(rsk_upload(ctx, &s->rot_base, rot_base, n_local));
     S_TRY(rsk_upload(ctx, &s->min_sid, msid.data(), msid.size()));
-    S_TRY(rsk_upload(ctx, &s->tile_start, tiles.data(), tiles.size()));
+    S_TRY(rsk_upload(ctx, &s->tiles, tiles.data(), tiles.size()));
     S_TRY(rsk_upload(ctx, &s->n_rays_once, once.data(), once.size()));
     S_TRY(rsk_upload(ctx, &s->ray_begin, rbeg.data(), rbeg.size()));
     S_TRY(rsk_upload(ctx, &s->ray_end, rend.data(), rend.size()));
@@ -513,7 +510,7 @@ static int rsk_solve_enqueue_trace_impl(rsk_solve *s) {
     memset(&a, 0, sizeof(a));
     a.sc = s->scene->view();
     a.ev = s->em->view();
-    a.emit_ids = s->emit_ids; a.tile_start = s->tile_start; a.n_local = s->n_local; a.tile_rays = s->tile_rays; a.surf_mask = s->mask;
+    a.emit_ids = s->emit_ids; a.tiles = s->tiles; a.n_local = s->n_local; a.tile_rays = s->tile_rays; a.surf_mask = s->mask;
     a.cp_table = s->cp_table; a.rot_base = s->rot_base; a.iters_done = s->iters_done; a.done = s->done;
     a.tally = s->iter_tally; a.n_hist = s->n_hist; a.ray_begin = s->ray_begin; a.ray_end = s->ray_end; a.min_sid = s->min_sid;
     if (s->twin) {
@@ -813,7 +810,7 @@ extern "C" int rsk_solve_destroy(rsk_solve *s) {
     if (s->twin) { rsk_solve_destroy(s->twin); s->twin = nullptr; }
     RskScope scope(s->ctx);
     rsk_dev_free(s->emit_ids); rsk_dev_free(s->min_sid); rsk_dev_free(s->rot_base); rsk_dev_free(s->iters_done); rsk_dev_free(s->done); rsk_dev_free(s->not_conv);
-    rsk_dev_free(s->have_prev); rsk_dev_free(s->tile_start); rsk_dev_free(s->n_rays_once); rsk_dev_free(s->total_rays); rsk_dev_free(s->ray_begin); rsk_dev_free(s->ray_end); rsk_dev_free(s->mask);
+    rsk_dev_free(s->have_prev); rsk_dev_free(s->tiles); rsk_dev_free(s->n_rays_once); rsk_dev_free(s->total_rays); rsk_dev_free(s->ray_begin); rsk_dev_free(s->ray_end); rsk_dev_free(s->mask);
     rsk_dev_free(s->cp_table); if (!s->external_tally) rsk_dev_free(s->iter_tally); rsk_dev_free(s->rays_traced); rsk_dev_free(s->total); rsk_dev_free(s->mean);
     rsk_dev_free(s->m2); rsk_dev_free(s->prev); rsk_dev_free(s->n_active);
     delete s;

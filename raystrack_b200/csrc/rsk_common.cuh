@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -186,14 +187,21 @@ struct rsk_emitters {
     }
 };
 
+// One CTA's share of a launch: rays [begin, begin + count) of the emitter of local job `job`.
+struct TileDesc {
+    int32_t job;
+    int32_t count;
+    int64_t begin;
+};
+
 // Arguments of the fused trace kernels (rsk_trace.cu).
 struct TraceArgs {
     SceneView sc;
     EmitterView ev;
     const int32_t *emit_ids;        // [n_local]
-    const int64_t *tile_start;      // [n_local+1] exclusive prefix of tiles per job
+    const TileDesc *tiles;          // [n_tiles] one CTA each (rsk_build_tiles)
     int32_t n_local;
-    int32_t tile_rays;              // rays per CTA tile of this launch
+    int32_t tile_rays;              // rays of the launch's regular tiles (the tail of the launch uses smaller ones)
     int32_t class_mod;              // hand-out units are residue classes of the ray index modulo this (1 = consecutive rays)
     const uint32_t *surf_mask;      // [n_local][mask_words], bit set = surface is a receiver/occluder
     const float *cp_table;          // [n_rot][7]
@@ -254,6 +262,37 @@ static inline int rsk_pick_class_mod(int tile_rays) {
     }
     if (forced) return forced;
     return 1;
+}
+// Cut the ray ranges [rbeg[k], rend[k]) of n_local jobs into the CTA tiles of one launch: regular tiles of
+// rsk_pick_tile_rays() rays in job order, followed by a tail of small tiles (taken from the ends of the last jobs, about
+// two waves of CTAs) -- the SMs then idle for half a SMALL tile at the end of the launch instead of half a regular one.
+// RSK_TAIL_TILE_RAYS overrides the small size (0 = no tail tiles).
+static inline void rsk_build_tiles(const int64_t *rbeg, const int64_t *rend, int n_local, int sm_count, std::vector<TileDesc> &out,
+                                   int *tile_rays_out) {
+    static int tail_size = -1;
+    if (tail_size < 0) {
+        const char *e = getenv("RSK_TAIL_TILE_RAYS");
+        tail_size = e ? atoi(e) : 1024;
+        if (tail_size != 0 && (tail_size < 256 || tail_size > RSK_TILE_RAYS_MAX)) tail_size = 1024;
+    }
+    int64_t total = 0;
+    for (int k = 0; k < n_local; ++k) total += rend[k] - rbeg[k];
+    const int T = rsk_pick_tile_rays(total, sm_count);
+    if (tile_rays_out) *tile_rays_out = T;
+    const int64_t wave = 4 * (int64_t)(sm_count > 0 ? sm_count : 148);
+    int64_t tail = (tail_size > 0 && tail_size < T) ? std::min<int64_t>(total / 4, 2 * wave * tail_size) : 0;
+    std::vector<int64_t> take(n_local, 0);
+    for (int k = n_local - 1; k >= 0 && tail > 0; --k) {
+        take[k] = std::min<int64_t>(rend[k] - rbeg[k], tail);
+        tail -= take[k];
+    }
+    out.clear();
+    for (int k = 0; k < n_local; ++k)
+        for (int64_t b = rbeg[k]; b < rend[k] - take[k]; b += T)
+            out.push_back(TileDesc{k, (int32_t)std::min<int64_t>(T, rend[k] - take[k] - b), b});
+    for (int k = 0; k < n_local; ++k)
+        for (int64_t b = rend[k] - take[k]; b < rend[k]; b += tail_size)
+            out.push_back(TileDesc{k, (int32_t)std::min<int64_t>(tail_size, rend[k] - b), b});
 }
 int rsk_qmc_ensure_halton(rsk_ctx *ctx, int64_t n);
 int rsk_qmc_ensure_grid(rsk_ctx *ctx, int g, int64_t *offset);

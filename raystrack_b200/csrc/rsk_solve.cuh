@@ -14,7 +14,8 @@ struct rsk_solve {
     // device state
     int32_t *min_sid = nullptr;
     int32_t *emit_ids = nullptr, *rot_base = nullptr, *iters_done = nullptr, *done = nullptr, *not_conv = nullptr, *have_prev = nullptr;
-    int64_t *tile_start = nullptr, *n_rays_once = nullptr, *total_rays = nullptr, *ray_begin = nullptr, *ray_end = nullptr;
+    TileDesc *tiles = nullptr;
+    int64_t *n_rays_once = nullptr, *total_rays = nullptr, *ray_begin = nullptr, *ray_end = nullptr;
     uint32_t *mask = nullptr;
     float *cp_table = nullptr;
     unsigned long long *iter_tally = nullptr, *rays_traced = nullptr;

@@ -108,33 +108,21 @@ __device__ __forceinline__ bool rsk_walk_next(Walk &w, uint32_t stack_base, uint
 template <int MODE, bool BVH>
 __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kernel(const TraceArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ int s_job;
     __shared__ int s_next;      // next unclaimed ray of the tile
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    if (tid == 0) {           // job lookup: last k with tile_start[k] <= blockIdx.x
-        int lo = 0, hi = a.n_local - 1;
-        const int64_t b = blockIdx.x;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (a.tile_start[mid] <= b) lo = mid; else hi = mid - 1;
-        }
-        s_job = lo;
-        s_next = 0;
-    }
+    if (tid == 0) s_next = 0;
+    const TileDesc td = a.tiles[blockIdx.x];
     __syncthreads();
-    const int job = s_job;
+    const int job = td.job;
     const bool side1_done = a.done && a.done[job];
     const bool want_m = MODE == MODE_MATRIX ? true : (MODE == MODE_DUAL ? !side1_done : false);
     const bool want_s = MODE == MODE_SKY ? true : (MODE == MODE_DUAL ? !a.done2[job] : false);
     if (MODE == MODE_DUAL ? (!want_m && !want_s) : side1_done) return;
 
     const EmitterDesc e = a.ev.desc[a.emit_ids[job]];
-    const int64_t tile = (int64_t)blockIdx.x - a.tile_start[job];
-    const int64_t range_begin = a.ray_begin ? a.ray_begin[job] : 0;
-    const int64_t range_end = a.ray_end ? a.ray_end[job] : e.n_rays_once;
-    const int64_t begin = range_begin + tile * a.tile_rays;
-    const int64_t end = min(begin + (int64_t)a.tile_rays, range_end);
+    const int64_t begin = td.begin;
+    const int64_t end = begin + td.count;
 
     float cp[7];
     {
