@@ -281,6 +281,55 @@ def parity_block(ctx, rank, world, sc, em, active, n_once, table, args):
     return out
 
 
+def terrain_block(ctx, flush, torch, with_cpu: bool):
+    """A second workload for tree quality: terrain + small objects (synthetic.terrain_with_objects, 1 053 352 triangles of
+    0.03 ... 50 m, non-planar emitters), closest-hit throughput of one iteration of all 748 emitters and -- against the
+    oracle (median-split reference tree) on a CPU sample -- per-ray agreement."""
+    from raystrack_b200 import _native, main as M, synthetic
+    from raystrack_b200.prepared import PreparedSolver
+    meshes = synthetic.terrain_with_objects()
+    samples, rays, seed = 1, 16, 1
+    ps = PreparedSolver(meshes)
+    sc = ps.get_device_scene(use_bvh=True, ctx=ctx)
+    em = ps.get_device_emitters(samples=samples, rays=rays, flip_faces=False, ctx=ctx)
+    ems = ps.get_emitter_summaries(samples=samples, rays=rays, flip_faces=False, ctx=ctx)
+    n = len(meshes)
+    active = M._surface_masks(ems, *ps.get_mesh_bounds())
+    n_once = [int(e.n_cells * rays) for e in ems]
+    ids = np.arange(n, dtype=np.int32)
+    solve = _native.Solve(ctx, sc.native, em.native, ids, active, M._rotation_table(seed, n, 64), ids.copy(), max_iters=64, min_iters=64,
+                          interval=1, tol_mode="stderr", tol=0.0, emit_sid=ids, min_sid=np.zeros(n, np.int32))
+    solve.step(2)
+    ms = _time_steps(ctx, lambda: solve.step(1), 3, flush, torch)
+    solve.close()
+    info = sc.info()
+    out = {"workload": f"terrain + small objects: {n} meshes, {ps.total_faces} triangles, samples={samples} rays={rays} "
+                       f"({int(sum(n_once))} rays/iteration)", "value": sum(n_once) / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms,
+           "bvh": f"{info['n_nodes']} wide nodes, depth {info['depth']}, built in {info['build_us']/1e3:.1f} ms"}
+    if with_cpu:
+        from oracle import oracle as O
+        t = time.time()
+        S = O.OracleSolver(meshes)
+        scene = S.scene(True)
+        centers, extents = S.bounds()
+        agree = tot = 0
+        emit = list(range(0, 36, 7)) + list(range(36, n, 53))      # terrain tiles, boxes, spheres, slabs
+        for i in emit:
+            oe = O.prepare_emitters([meshes[i]], samples, rays, False)[0]
+            cnt = min(oe.n_rays_once, 16384)
+            cpg, cpd = O.rotation(seed, i, 1)
+            act = O.surface_mask(i, oe, centers, extents)
+            ro, rd = O.build_rays(oe, cpg, cpd, count=cnt)
+            rh, rf = O.trace_firsthit(scene, ro, rd, act, i, 0)
+            _, _, hit, front = _native.trace_rays(ctx, sc.native, em.native, i, act, i, 0, np.concatenate([cpg, cpd]), mode=0, n_rays=cnt,
+                                                  want_rays=False)
+            agree += int(np.sum((hit == rh) & (front == rf)))
+            tot += cnt
+        out["parity"] = {"per_ray_agreement": agree / tot, "rays_compared": tot, "emitters": len(emit),
+                         "against": "oracle (reference median-split BVH, C port)", "oracle_s": round(time.time() - t, 1)}
+    return out
+
+
 def secondary_block(ctx, sc, em, active, n_once, table, rays_per_step, flush, torch):
     """The other kernels of the path on the same scene and step definition (one iteration of every emitter), CUDA-event
     timed, L2 flushed: discrete-sky any-hit, dual (closest hit + any-hit flag from one walk), and the API-default
@@ -429,6 +478,7 @@ def run_ours(args):
             parity = parity_block(ctx, rank, world, sc, em, active, n_once, table, args)
         if world == 1 and not args.no_secondary:
             secondary = secondary_block(ctx, sc, em, active, n_once, table, rays_per_step, flush, torch)
+            secondary["terrain_scene"] = terrain_block(ctx, flush, torch, with_cpu=not args.no_cpu)
     finally:
         M._log = old_log
     e2e_value = rays_per_step * args.e2e_iters / float(np.mean(e2e_times)) / 1e9 if e2e_times else None

@@ -200,6 +200,15 @@ int rsk_solve_read_block(rsk_solve *solve, int64_t *tallies, int32_t *iters, int
 /* rsk_solve_read_block without the second host copy: *tallies_view points into the context's pinned staging area
  * (valid until the next staged download of this context). */
 int rsk_solve_read_block_view(rsk_solve *solve, int64_t **tallies_view, int32_t *iters, int64_t *total_rays);
+/* Result rows in compressed form.  Replaces the dense read-back plus the host loop of main.py:1918-1934 (`F = hits /
+ * total_rays`, keys only for F > 0) for large matrices: per job (row) the column indices (ascending: the reference's
+ * key order "<r0>_front, <r0>_back, <r1>_front, ...") and float64 values F of the non-zero bins.  rsk_solve_csr /
+ * rsk_tally_block_csr build the rows on the device and return row_ptr (int64[n_rows + 1]; nnz = row_ptr[n_rows]);
+ * rsk_csr_fetch then copies cols int32[nnz] and vals float64[nnz] and releases the device copy.  total_rays:
+ * int64[n_rows], the denominator of each row (a solve uses its own counters). */
+int rsk_solve_csr(rsk_solve *solve, int64_t *row_ptr);
+int rsk_tally_block_csr(rsk_tally_block *block, const int64_t *total_rays, int64_t *row_ptr);
+int rsk_csr_fetch(rsk_ctx *ctx, int32_t *cols, double *vals);
 /* Device pointer + element count of the int64 tally block [n_local][n_surf][2] ((front, back) per receiver) for collectives issued by the caller (torch.distributed / NCCL). */
 int rsk_matrix_device_tallies(rsk_solve *solve, void **device_ptr, int64_t *n_elements);
 

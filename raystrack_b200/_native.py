@@ -38,6 +38,7 @@ EXPORTS = (
     "rsk_solve_allreduce_iter_tallies",
     "rsk_tally_block_create", "rsk_tally_block_add_solve", "rsk_tally_block_allreduce", "rsk_tally_block_device",
     "rsk_tally_block_download", "rsk_tally_block_destroy",
+    "rsk_solve_csr", "rsk_tally_block_csr", "rsk_csr_fetch",
 )
 COMM_ID_BYTES = 128
 
@@ -473,6 +474,13 @@ class Solve:
             return np.zeros((self.n_local, nh), np.int64), iters, total
         return np.ctypeslib.as_array(view, shape=(self.n_local, nh)), iters, total
 
+    def read_csr(self):
+        """The result rows in compressed form, built on the device: (row_ptr int64 [n_local + 1], cols int32 [nnz],
+        vals float64 [nnz]) with vals = tally / total rays of the job, non-zero bins only, columns ascending."""
+        row_ptr = np.zeros(self.n_local + 1, np.int64)
+        check(self.ctx.lib.rsk_solve_csr(self.handle, ptr(row_ptr)), "rsk_solve_csr")
+        return _fetch_csr(self.ctx, row_ptr)
+
     def allreduce_iter_tallies(self, n_jobs: int) -> None:
         """Sum the iteration tallies of the first ``n_jobs`` (ray-split) jobs over the context's communicator."""
         check(self.ctx.lib.rsk_solve_allreduce_iter_tallies(self.handle, C.c_int32(n_jobs)), "rsk_solve_allreduce_iter_tallies")
@@ -515,6 +523,14 @@ class Solve:
             pass
 
 
+def _fetch_csr(ctx: "Context", row_ptr: np.ndarray):
+    nnz = int(row_ptr[-1])
+    cols = np.empty(nnz, np.int32)
+    vals = np.empty(nnz, np.float64)
+    check(ctx.lib.rsk_csr_fetch(ctx.handle, ptr(cols), ptr(vals)), "rsk_csr_fetch")
+    return row_ptr, cols, vals
+
+
 class TallyBlock:
     """Wraps ``rsk_tally_block``: the device-resident [n_rows, n_cols] int64 block in which the ranks of a sharded solve
     assemble and sum their results (scatter kernel + NCCL all-reduce + pinned download, all inside the library)."""
@@ -535,6 +551,14 @@ class TallyBlock:
         p, n = C.c_void_p(), C.c_int64(0)
         check(self.ctx.lib.rsk_tally_block_device(self.handle, C.byref(p), C.byref(n)))
         return int(p.value or 0), int(n.value)
+
+    def read_csr(self, total_rays: np.ndarray):
+        """Rows of the (rank-summed) block in compressed form: vals = tally / total_rays[row]."""
+        tot = np.ascontiguousarray(total_rays, np.int64)
+        assert tot.shape[0] == self.shape[0]
+        row_ptr = np.zeros(self.shape[0] + 1, np.int64)
+        check(self.ctx.lib.rsk_tally_block_csr(self.handle, ptr(tot), ptr(row_ptr)), "rsk_tally_block_csr")
+        return _fetch_csr(self.ctx, row_ptr)
 
     def download(self, copy: bool = False) -> np.ndarray:
         """The block on the host: a view of the context's pinned staging area (valid until the next staged download on
@@ -570,6 +594,7 @@ class _SolvePart:
     read_block = Solve.read_block
     read_block_view = Solve.read_block_view
     read_counters = Solve.read_counters
+    read_csr = Solve.read_csr
     allreduce_iter_tallies = Solve.allreduce_iter_tallies
     enqueue_fold = Solve.enqueue_fold
     poll = Solve.poll

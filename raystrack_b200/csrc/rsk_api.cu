@@ -85,6 +85,8 @@ extern "C" int rsk_ctx_destroy(rsk_ctx *ctx) {
     RskScope scope(ctx);
     rsk_dev_free(ctx->halton);
     rsk_dev_free(ctx->grid);
+    rsk_dev_free(ctx->csr_cols);
+    rsk_dev_free(ctx->csr_vals);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->stage) cudaFreeHost(ctx->stage);

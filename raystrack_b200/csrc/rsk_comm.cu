@@ -157,11 +157,6 @@ extern "C" int rsk_solve_allreduce_iter_tallies(rsk_solve *s, int32_t n_jobs) {
 
 // ----------------------------------------------------------------------------- tally block
 
-struct rsk_tally_block {
-    rsk_ctx *ctx = nullptr;
-    int64_t n_rows = 0, n_cols = 0;
-    long long *d = nullptr;
-};
 
 // full[rows[k]][:] = part[k][:] for the kept jobs k (rows < 0 = skip): one CTA column-strides over one row
 __global__ void rsk_scatter_rows_kernel(const long long *__restrict__ part, const int32_t *__restrict__ rows, long long *__restrict__ full,

@@ -142,6 +142,10 @@ struct rsk_ctx {
     void *comm = nullptr;
     int comm_rank = 0, comm_size = 1;
     long long *comm_scratch = nullptr;
+    // result rows in compressed form (rsk_csr_build): column index and F = tally / total rays of every non-zero bin
+    int32_t *csr_cols = nullptr;
+    double *csr_vals = nullptr;
+    int64_t csr_nnz = 0;
     // pinned staging area for large downloads (grow-only)
     void *stage = nullptr;
     size_t stage_cap = 0;

@@ -28,3 +28,10 @@ struct rsk_solve {
     bool external_tally = false;     // iter_tally belongs to the caller (rsk_solve_set_iter_tally_buffer)
     rsk_solve *twin = nullptr;       // dual solves: the sky side (this object is the matrix side)
 };
+
+// Device-resident int64 [n_rows][n_cols] block in which the ranks of a sharded solve assemble their results (rsk_comm.cu).
+struct rsk_tally_block {
+    rsk_ctx *ctx = nullptr;
+    int64_t n_rows = 0, n_cols = 0;
+    long long *d = nullptr;
+};

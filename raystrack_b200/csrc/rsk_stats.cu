@@ -6,7 +6,7 @@
 // (utils/cuda_trace.py:581-616).  All float64 arithmetic uses explicit round-to-nearest intrinsics in the
 // reference's NumPy operation order (no FMA contraction), so decisions are bit-identical to the CPU reference
 // whenever the integer tallies are.
-#include "rsk_stats.cuh"
+#include "rsk_solve.cuh"
 
 
 // main.py:217-228 `_convergence_checkpoint`.
@@ -190,5 +190,152 @@ extern "C" int rsk_reciprocity_rowsum(rsk_ctx *ctx, int32_t n, const double *are
     cleanup();
 #undef RSK_R
 #undef RSK_RC
+    return RSK_OK;
+}
+
+
+// ----------------------------------------------------------------------------- result rows in compressed form
+// Replaces, for city-sized matrices, the dense read-back of the tallies followed by the host loop of main.py:1918-1934
+// (`F = hits / total_rays`, keys only for F > 0): nine bins in ten are zero, so the device emits per row the column
+// indices and values of the non-zero bins (CSR, columns ascending = the reference's key order) and only those cross
+// PCIe.  The division is the reference's: int64 -> float64 conversions (exact below 2^53), one IEEE division.
+
+__global__ void rsk_csr_count_kernel(const long long *__restrict__ block, int64_t n_cols, int32_t *__restrict__ row_count) {
+    const long long *row = block + (int64_t)blockIdx.x * n_cols;
+    int c = 0;
+    for (int64_t j = threadIdx.x; j < n_cols; j += blockDim.x) c += row[j] != 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    __shared__ int s_part[32];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[w];
+        row_count[blockIdx.x] = t;
+    }
+}
+
+// exclusive prefix sum of n counts into row_ptr[0..n] (one CTA; n is the number of meshes)
+__global__ void rsk_csr_scan_kernel(const int32_t *__restrict__ row_count, int64_t n, long long *__restrict__ row_ptr) {
+    __shared__ long long s_carry;
+    __shared__ long long s_warp[32];
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int64_t base = 0; base < n; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const long long v = i < n ? row_count[i] : 0;
+        long long x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        long long before = s_carry;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (i < n) row_ptr[i] = before + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long t = s_carry;
+            for (int w = 0; w < nw; ++w) t += s_warp[w];
+            s_carry = t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) row_ptr[n] = s_carry;
+}
+
+__global__ void rsk_csr_fill_kernel(const long long *__restrict__ block, int64_t n_cols, const long long *__restrict__ total_rays,
+                                    const long long *__restrict__ row_ptr, int32_t *__restrict__ cols, double *__restrict__ vals) {
+    const long long *row = block + (int64_t)blockIdx.x * n_cols;
+    const double denom = (double)total_rays[blockIdx.x];
+    __shared__ int s_warp[32];
+    __shared__ long long s_base;
+    if (threadIdx.x == 0) s_base = row_ptr[blockIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int64_t base = 0; base < n_cols; base += blockDim.x) {
+        const int64_t j = base + threadIdx.x;
+        const long long t = j < n_cols ? row[j] : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, t != 0);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, all = 0;
+        for (int w = 0; w < nw; ++w) { const int c = s_warp[w]; if (w < warp) before += c; all += c; }
+        if (t != 0) {
+            const long long dst = s_base + before + __popc(m & ((1u << lane) - 1u));
+            cols[dst] = (int32_t)j;
+            vals[dst] = __ddiv_rn((double)t, denom);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += all;
+        __syncthreads();
+    }
+}
+
+static int rsk_csr_build_impl(rsk_ctx *ctx, const long long *block, int64_t n_rows, int64_t n_cols, const long long *d_total_rays,
+                              const int64_t *h_total_rays, int64_t *row_ptr) {
+    RSK_REQUIRE(n_rows >= 0 && n_cols >= 0 && n_cols < (1ll << 31) && n_rows < (1ll << 31), "rsk_csr_build: bad shape");
+    cudaStream_t st = ctx->stream;
+    rsk_dev_free(ctx->csr_cols); rsk_dev_free(ctx->csr_vals);
+    ctx->csr_cols = nullptr; ctx->csr_vals = nullptr; ctx->csr_nnz = 0;
+    if (n_rows == 0) { row_ptr[0] = 0; return RSK_OK; }
+    int32_t *d_count = nullptr;
+    long long *d_ptr = nullptr, *d_tot = nullptr;
+    int rc = RSK_OK;
+    auto cleanup = [&]() { rsk_dev_free(d_count); rsk_dev_free(d_ptr); rsk_dev_free(d_tot); };
+#define C_TRY(expr) do { rc = (expr); if (rc != RSK_OK) { cleanup(); return rc; } } while (0)
+#define C_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rsk_set_error("%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); return RSK_ERR_CUDA; } } while (0)
+    C_TRY(rsk_dev_alloc(&d_count, (size_t)n_rows));
+    C_TRY(rsk_dev_alloc(&d_ptr, (size_t)n_rows + 1));
+    if (!d_total_rays) {
+        C_TRY(rsk_dev_alloc(&d_tot, (size_t)n_rows));
+        C_CUDA(cudaMemcpyAsync(d_tot, h_total_rays, (size_t)n_rows * 8, cudaMemcpyHostToDevice, st));
+        d_total_rays = d_tot;
+    }
+    rsk_csr_count_kernel<<<(unsigned)n_rows, 256, 0, st>>>(block, n_cols, d_count);
+    rsk_csr_scan_kernel<<<1, 1024, 0, st>>>(d_count, n_rows, d_ptr);
+    ctx->launches += 2;
+    C_CUDA(cudaMemcpyAsync(row_ptr, d_ptr, ((size_t)n_rows + 1) * 8, cudaMemcpyDeviceToHost, st));
+    C_CUDA(cudaStreamSynchronize(st));
+    const int64_t nnz = row_ptr[n_rows];
+    if (nnz > 0) {
+        C_TRY(rsk_dev_alloc(&ctx->csr_cols, (size_t)nnz));
+        C_TRY(rsk_dev_alloc(&ctx->csr_vals, (size_t)nnz));
+        rsk_csr_fill_kernel<<<(unsigned)n_rows, 256, 0, st>>>(block, n_cols, d_total_rays, d_ptr, ctx->csr_cols, ctx->csr_vals);
+        ctx->launches++;
+        C_CUDA(cudaGetLastError());
+    }
+    ctx->csr_nnz = nnz;
+    cleanup();
+#undef C_TRY
+#undef C_CUDA
+    return RSK_OK;
+}
+
+extern "C" int rsk_solve_csr(rsk_solve *s, int64_t *row_ptr) {
+    RSK_REQUIRE(s && row_ptr, "rsk_solve_csr: null argument");
+    RskScope scope(s->ctx);
+    return rsk_csr_build_impl(s->ctx, s->total, s->n_local, s->n_hist, (const long long *)s->total_rays, nullptr, row_ptr);
+}
+
+extern "C" int rsk_tally_block_csr(rsk_tally_block *b, const int64_t *total_rays, int64_t *row_ptr) {
+    RSK_REQUIRE(b && total_rays && row_ptr, "rsk_tally_block_csr: null argument");
+    RskScope scope(b->ctx);
+    return rsk_csr_build_impl(b->ctx, b->d, b->n_rows, b->n_cols, nullptr, total_rays, row_ptr);
+}
+
+extern "C" int rsk_csr_fetch(rsk_ctx *ctx, int32_t *cols, double *vals) {
+    RSK_REQUIRE(ctx, "rsk_csr_fetch: null context");
+    RskScope scope(ctx);
+    if (ctx->csr_nnz > 0) {
+        RSK_REQUIRE(cols && vals, "rsk_csr_fetch: null output");
+        RSK_CUDA(cudaMemcpyAsync(cols, ctx->csr_cols, (size_t)ctx->csr_nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        RSK_CUDA(cudaMemcpyAsync(vals, ctx->csr_vals, (size_t)ctx->csr_nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        RSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    rsk_dev_free(ctx->csr_cols); rsk_dev_free(ctx->csr_vals);
+    ctx->csr_cols = nullptr; ctx->csr_vals = nullptr; ctx->csr_nnz = 0;
     return RSK_OK;
 }

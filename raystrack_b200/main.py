@@ -294,10 +294,22 @@ def _plan_chunks(plan: List[Tuple[int, int, int, bool]], n_hist: int) -> List[Li
     return chunks
 
 
+def _csr_from_dense(tallies: np.ndarray, totals: np.ndarray):
+    """Host form of ``rsk_solve_csr``: (row_ptr, cols, vals) of F = tallies / totals over the non-zero bins."""
+    n_rows, n_cols = tallies.shape
+    nz = np.flatnonzero(tallies.reshape(-1))
+    rows = nz // max(n_cols, 1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        vals = tallies.reshape(-1)[nz] / totals[rows].astype(np.float64)              # main.py:1922-1923
+    return np.searchsorted(rows, np.arange(n_rows + 1)).astype(np.int64), (nz - rows * n_cols).astype(np.int32), vals
+
+
 def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_iters, min_iters, interval, tol_mode, tol,
-                   emit_sid=None, min_sid=None, sky=False, discrete=False):
+                   emit_sid=None, min_sid=None, sky=False, discrete=False, want_csr=False):
     """Run the jobs of ``todo`` (emitter indices) on this rank's shard and return full-size, rank-summed integer
-    results: (tallies int64 [n_emit, n_hist], iterations int64 [n_emit], total rays int64 [n_emit])."""
+    results: (tallies int64 [n_emit, n_hist], iterations int64 [n_emit], total rays int64 [n_emit]).  With
+    ``want_csr`` the first element is instead the compressed form of the result rows, ``(row_ptr, cols, vals)`` with
+    vals = tally / total rays (built on the device when the library holds the rank-summed block)."""
     n_emit = active.shape[0]
     n_surf = active.shape[1]
     rank, world = _dist_env()
@@ -309,14 +321,18 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
 
     chunks = _plan_chunks(plan, n_hist)
 
-    single = world == 1 and len(chunks) == 1 and len(plan) == n_emit
+    single = world == 1 and len(chunks) == 1 and len(plan) == n_emit          # every emitter, in order: no scatter needed
+    # one GPU, one solve, emitters in ascending order (some may be missing: emitters without receivers are never
+    # traced): the solve's compressed rows only need empty rows spliced in
+    single_csr = (want_csr and world == 1 and len(chunks) == 1 and hasattr(_native.Solve, "read_csr")
+                  and all(a[0] < b[0] for a, b in zip(plan, plan[1:])))
     # With the library communicator the tally blocks never visit the host before they are summed: every rank scatters
     # the rows of its solves into a zeroed device block, one NCCL all-reduce adds the blocks up over NVLink, and the
     # result comes back in a single copy through pinned memory.
     block = _native.TallyBlock(ctx, n_emit, n_hist) if exchange == "native" else None
     tallies = iters = totals = None
     if not single:
-        tallies = None if block is not None else np.zeros((n_emit, n_hist), np.int64)
+        tallies = None if (block is not None or single_csr) else np.zeros((n_emit, n_hist), np.int64)
         iters = np.zeros(n_emit, np.int64)
         totals = np.zeros(n_emit, np.int64)
     try:
@@ -343,6 +359,9 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
                         it_loc, tot_loc = solve.read_counters()
                         block.add_solve(solve, keep)
                         loc = None
+                    elif single_csr:
+                        it_loc, tot_loc = solve.read_counters()
+                        loc = solve.read_csr()
                     elif single and hasattr(solve, "read_block_view"):
                         loc, it_loc, tot_loc = solve.read_block_view()
                     else:
@@ -350,8 +369,15 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
             finally:
                 with _Phase("solve_end"):
                     solve.close()
+            if single_csr:
+                counts = np.zeros(n_emit, np.int64)
+                counts[ids] = np.diff(loc[0])
+                iters[ids], totals[ids] = it_loc, tot_loc
+                return (np.concatenate([np.zeros(1, np.int64), np.cumsum(counts)]), loc[1], loc[2]), iters, totals
             if single:
-                return loc, it_loc.astype(np.int64), tot_loc      # every emitter, in order: no scatter needed
+                if want_csr:
+                    loc = _csr_from_dense(loc, tot_loc)
+                return loc, it_loc.astype(np.int64), tot_loc
             if keep.any():
                 if loc is not None:
                     tallies[ids[keep]] = loc[keep]
@@ -362,15 +388,16 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
             with _Phase("all_reduce"):
                 if block is not None:
                     block.allreduce()
-                    tallies = block.download()
                     allreduce_sum_([iters, totals])
                 else:
                     allreduce_sum_([tallies, iters, totals], device=getattr(ctx, "device", 0))
-        elif block is not None:
-            tallies = block.download()
+        if block is not None:
+            tallies = block.read_csr(totals) if want_csr else block.download()
     finally:
         if block is not None:
             block.close()
+    if want_csr and not isinstance(tallies, tuple):
+        tallies = _csr_from_dense(tallies, totals)
     return tallies, iters, totals
 
 
@@ -430,7 +457,7 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
             table = _rotation_table(seed, n_surf, max_iters)
         tallies, iters, totals = _solve_sharded(ctx, d_scene, d_em, todo, n_once, active, table, max_iters=max_iters,
                                                 min_iters=min_iters, interval=interval if schedule == "gpu" else 1,
-                                                tol_mode=tol_mode, tol=tol, emit_sid=emit_sid, min_sid=min_sid)
+                                                tol_mode=tol_mode, tol=tol, emit_sid=emit_sid, min_sid=min_sid, want_csr=True)
     elapsed = time.time() - t0
     t_asm = time.perf_counter()
 
@@ -440,21 +467,22 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
     keys = [f"{name}{suffix}" for name, _, _ in meshes for suffix in ("_front", "_back")]
     work = np.asarray(weights) * np.maximum(iters, 1)
     work_sum = max(1.0, float(work.sum()))
-    nz_rows, nz_cols = np.nonzero(tallies)                      # row-major: already grouped by emitter, keys in order
-    with np.errstate(divide="ignore", invalid="ignore"):
-        nz_vals = tallies[nz_rows, nz_cols] / totals[nz_rows].astype(np.float64)         # main.py:1922-1923
-    bounds = np.searchsorted(nz_rows, np.arange(n_surf + 1))
-    cols_all, vals_all = nz_cols.tolist(), nz_vals.tolist()
+    # non-zero bins per emitter: column indices (row-major, i.e. keys in order) and F = hits / total rays (main.py:1922-1923)
+    row_ptr, nz_cols, nz_vals = tallies if isinstance(tallies, tuple) else _csr_from_dense(tallies, totals)
+    bounds = row_ptr.tolist()
+    vals_all = nz_vals.tolist()
+    cols_all = nz_cols.tolist() if reciprocity else None
+    keys_nz = np.asarray(keys, dtype=object)[nz_cols].tolist() if len(keys) else []
     for i, (name_e, _, _) in enumerate(meshes):
         if not has_recv[i]:
             if _hook is None:
                 _log(f"({i+1}/{n_surf}) [{name_e}] 0 iter, 0 rays -> 0.000s  (BVH={label}, device=gpu)")
             continue
-        lo, hi = int(bounds[i]), int(bounds[i + 1])
-        cols_l, vals = cols_all[lo:hi], vals_all[lo:hi]
-        row = dict(zip([keys[c] for c in cols_l], vals))
+        lo, hi = bounds[i], bounds[i + 1]
+        vals = vals_all[lo:hi]
+        row = dict(zip(keys_nz[lo:hi], vals))
         if reciprocity and areas is not None:
-            for c, f in zip(cols_l, vals):
+            for c, f in zip(cols_all[lo:hi], vals):
                 j = c >> 1
                 if not (c & 1) and areas[j] > 0.0:
                     result[meshes[j][0]][f"{name_e}_front"] = f * (areas[i] / areas[j])     # main.py:1926-1927

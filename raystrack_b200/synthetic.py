@@ -108,3 +108,80 @@ def tilted_pair() -> List[Mesh]:
     V2 = np.array([[0.2, 0.1, 2.0], [1.9, 0.0, 2.4], [2.1, 1.8, 1.6], [0.0, 1.6, 2.2]], np.float32)
     F2 = np.array([[0, 2, 1], [0, 3, 2]], np.int32)
     return [("bowl", V1, F1), ("lid", V2, F2)]
+
+
+def _height_grid(name: str, x0: float, y0: float, size: float, n: int, height) -> Mesh:
+    """(n x n) quad grid over [x0, x0+size] x [y0, y0+size] lifted to z = height(x, y); same indexing as quad_grid."""
+    i, j = np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="ij")
+    x = x0 + i * (size / n)
+    y = y0 + j * (size / n)
+    V = np.stack([x, y, height(x, y)], -1).reshape(-1, 3).astype(np.float32)
+    ci, cj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    a = (ci * (n + 1) + cj).reshape(-1)
+    b, d = a + (n + 1), a + 1
+    c = b + 1
+    F = np.stack([np.stack([a, b, c], 1), np.stack([a, c, d], 1)], 1).reshape(-1, 3).astype(np.int32)
+    return name, V, F
+
+
+def _box(name: str, centre, half) -> Mesh:
+    cx, cy, cz = centre
+    hx, hy, hz = half
+    V = np.array([[cx + sx * hx, cy + sy * hy, cz + sz * hz] for sz in (-1, 1) for sy in (-1, 1) for sx in (-1, 1)], np.float32)
+    F = np.array([[0, 2, 1], [1, 2, 3], [4, 5, 6], [5, 7, 6], [0, 1, 4], [1, 5, 4], [2, 6, 3], [3, 6, 7],
+                  [0, 4, 2], [2, 4, 6], [1, 3, 5], [3, 7, 5]], np.int32)           # outward normals
+    return name, V, F
+
+
+def _uv_sphere(name: str, centre, radius: float, n_lon: int = 16, n_lat: int = 8) -> Mesh:
+    th = np.linspace(0.0, np.pi, n_lat + 1)[1:-1]
+    ph = np.linspace(0.0, 2.0 * np.pi, n_lon, endpoint=False)
+    ring = np.stack([np.outer(np.sin(th), np.cos(ph)), np.outer(np.sin(th), np.sin(ph)), np.outer(np.cos(th), np.ones(n_lon))], -1)
+    V = np.concatenate([[[0.0, 0.0, 1.0]], ring.reshape(-1, 3), [[0.0, 0.0, -1.0]]]) * radius + np.asarray(centre)
+    F = []
+    for k in range(n_lon):
+        F.append([0, 1 + k, 1 + (k + 1) % n_lon])
+    for r in range(n_lat - 2):
+        for k in range(n_lon):
+            a, b = 1 + r * n_lon + k, 1 + r * n_lon + (k + 1) % n_lon
+            F += [[a, a + n_lon, b], [b, a + n_lon, b + n_lon]]
+    last = 1 + (n_lat - 2) * n_lon
+    for k in range(n_lon):
+        F.append([last + k, last + n_lon, last + (k + 1) % n_lon])
+    return name, V.astype(np.float32), np.asarray(F, np.int32)
+
+
+def terrain_with_objects(n_tiles: int = 6, tile_grid: int = 118, n_boxes: int = 500, n_spheres: int = 200, n_slabs: int = 12,
+                         seed: int = 0) -> List[Mesh]:
+    """A scene with strongly varying triangle sizes (the opposite of the regular urban grid): rolling terrain in
+    ``n_tiles`` x ``n_tiles`` non-planar patch meshes of 100 m (``tile_grid``^2 quads each, ~0.85 m triangles at the
+    default), boxes of 0.3-3 m (12 triangles each), finely tessellated spheres of 0.2-0.6 m radius (224 triangles of a
+    few centimetres), and a few 40-60 m free-standing slabs of two triangles.  Defaults: 748 meshes, 1 053 352 triangles."""
+    rng = np.random.default_rng(seed)
+    size = 100.0
+    ext = n_tiles * size
+
+    def height(x, y):
+        return 6.0 * np.sin(x / 37.0) * np.cos(y / 53.0) + 2.5 * np.sin((x + 2.0 * y) / 19.0) + 0.02 * x
+
+    meshes: List[Mesh] = []
+    for tx in range(n_tiles):
+        for ty in range(n_tiles):
+            meshes.append(_height_grid(f"terrain_{tx}_{ty}", tx * size, ty * size, size, tile_grid, height))
+    for k in range(n_boxes):
+        x, y = rng.uniform(5.0, ext - 5.0, 2)
+        half = rng.uniform(0.15, 1.5, 3)
+        meshes.append(_box(f"box_{k:03d}", (x, y, float(height(x, y)) + half[2] + 0.05), half))
+    for k in range(n_spheres):
+        x, y = rng.uniform(5.0, ext - 5.0, 2)
+        r = float(rng.uniform(0.2, 0.6))
+        meshes.append(_uv_sphere(f"sphere_{k:03d}", (x, y, float(height(x, y)) + r + rng.uniform(0.1, 3.0)), r))
+    for k in range(n_slabs):
+        x, y = rng.uniform(60.0, ext - 60.0, 2)
+        L, H = rng.uniform(40.0, 60.0), rng.uniform(8.0, 20.0)
+        ang = rng.uniform(0.0, np.pi)
+        dx, dy = 0.5 * L * np.cos(ang), 0.5 * L * np.sin(ang)
+        z0 = float(height(x, y)) - 8.0
+        meshes.append(_quad(f"slab_{k:02d}", [(x - dx, y - dy, z0), (x + dx, y + dy, z0), (x + dx, y + dy, z0 + H + 16.0),
+                                               (x - dx, y - dy, z0 + H + 16.0)], False))
+    return meshes

@@ -13,6 +13,8 @@ Outputs (committed):
   solves_extra.json   further parameter combinations (row-sum enforcement, delta sky, flipped enclosure with BVH, tilted meshes)
   workflow.json       view_factor_outside_workflow / view_factor_matrix_and_sky results (reference api.py, main.py:1209)
   shipped.json        the result files the reference ships (examples/*.json, validation/results/*), verbatim data
+  large_rays.npz      per-ray closest hits of the reference's BVH tracer on a 127 488-triangle urban block (7x7 buildings,
+                      16x16 face grids; reference tree: 32 767 nodes) for a wall, a roof, an inner wall and the ground
 """
 from __future__ import annotations
 
@@ -199,6 +201,49 @@ def stage_vectors():
     print("stage_vectors.npz:", len(z), "arrays")
 
 
+LARGE_SCENE = dict(n_side=7, face_grid=16, ground_grid=32, seed=0)     # 246 meshes, 127 488 triangles
+LARGE_EMITTERS = (0, 4, 122, 245)                                      # edge wall, roof, inner wall, ground
+LARGE_RAYS = 8192
+
+
+def large_rays():
+    """A real-size tree pinned to the reference: trace_cpu_bvh_firsthit (utils/cpu_trace.py:120-277) through the
+    reference's own median-split BVH (utils/bvh.py) over 127 488 triangles, first LARGE_RAYS rays of four emitters."""
+    meshes = synthetic.urban_block(**LARGE_SCENE)
+    scene = prepared.prepare_scene(meshes, use_bvh=True)
+    centers, extents = prepared.PreparedSolver(meshes).get_mesh_bounds()
+    z = {"n_tri": np.array([scene.v0.shape[0]], np.int64), "n_nodes": np.array([scene.left.shape[0]], np.int64)}
+    samples, rays = 4, 16
+    for idx in LARGE_EMITTERS:
+        em = prepared.prepare_emitters([meshes[idx]], samples=samples, rays=rays, flip_faces=False)[0]
+        rng = np.random.default_rng(500 + idx)
+        cpg = rng.random(2, dtype=np.float32)
+        cpd = rng.random(5, dtype=np.float32)
+        n = min(LARGE_RAYS, em.n_cells * rays)
+        o = np.empty((n, 3), np.float32)
+        d = np.empty_like(o)
+        ray_builder.build_rays(em.u_grid, em.v_grid, em.halton_tri[:n], em.halton_u[:n], em.halton_v[:n], em.halton_r1[:n],
+                               em.halton_r2[:n], em.cdf, em.tri_a, em.tri_e1, em.tri_e2, em.tri_u, em.tri_v, em.tri_n,
+                               em.tri_origin_eps, rays, o, d, cpg, cpd)
+        active = ref_main._build_emitter_surface_mask(idx, em, centers, extents)
+        hs = np.empty(n, np.int32)
+        fr = np.empty(n, np.uint8)
+        cpu_trace.trace_cpu_bvh_firsthit(o, d, scene.v0, scene.e1, scene.e2, scene.normals, scene.sid, active, scene.bb_min,
+                                         scene.bb_max, scene.left, scene.right, scene.start, scene.count, idx, 0, hs, fr)
+        hm = np.empty(n, np.uint8)
+        cpu_trace.trace_cpu_bvh_hitmask(o, d, scene.v0, scene.e1, scene.e2, scene.sid, active, scene.bb_min, scene.bb_max,
+                                        scene.left, scene.right, scene.start, scene.count, idx, 0, hm)
+        z[f"e{idx}_cp"] = np.concatenate([cpg, cpd])
+        z[f"e{idx}_active"] = active.astype(np.uint8)
+        z[f"e{idx}_hit"] = hs.astype(np.int16)
+        z[f"e{idx}_front"] = fr
+        z[f"e{idx}_mask"] = hm
+        z[f"e{idx}_rays_sha"] = np.frombuffer(bytes.fromhex(sha(o) + sha(d)), np.uint8)
+        print(f"large emitter {idx}: {n} rays, hit fraction {float(np.mean(hs >= 0)):.3f}, receivers {len(np.unique(hs))}")
+    np.savez_compressed(HERE / "large_rays.npz", **z)
+    print("large_rays.npz", (HERE / "large_rays.npz").stat().st_size, "bytes")
+
+
 def solves():
     out = {}
     canyon = load_meshes_json(str(REF / "examples" / "street_canyon.json"))
@@ -329,7 +374,7 @@ def shipped():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["stage", "solves", "extra", "shipped", "workflow"]
+    what = sys.argv[1:] or ["stage", "solves", "extra", "shipped", "workflow", "large"]
     if "stage" in what:
         stage_vectors()
     if "solves" in what:
@@ -340,3 +385,5 @@ if __name__ == "__main__":
         shipped()
     if "workflow" in what:
         workflow()
+    if "large" in what:
+        large_rays()

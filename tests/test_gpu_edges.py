@@ -251,3 +251,74 @@ def test_random_triangle_soups_per_ray(rb, seed):
             total += 2 * hit.shape[0]
         ps.clear_device_cache()
     assert total > 0 and agree / total >= 0.9999, (agree, total)
+
+
+def test_device_csr_rows_equal_dense_block(rb):
+    """rsk_solve_csr / rsk_tally_block_csr: the compressed result rows built on the device equal the dense tally block
+    divided on the host (same int64 -> float64 conversions, one IEEE division), bit for bit."""
+    from raystrack_b200 import _native, main as M, synthetic
+    from raystrack_b200.prepared import PreparedSolver
+    meshes = synthetic.urban_block(3, 4, 8, 0)
+    ctx = _native.Context.for_device(0)
+    ps = PreparedSolver(meshes)
+    sc = ps.get_device_scene(use_bvh=True, ctx=ctx)
+    em = ps.get_device_emitters(samples=2, rays=16, flip_faces=False, ctx=ctx)
+    ems = ps.get_emitter_summaries(samples=2, rays=16, flip_faces=False, ctx=ctx)
+    n = len(meshes)
+    active = M._surface_masks(ems, *ps.get_mesh_bounds())
+    ids = np.arange(n, dtype=np.int32)
+    solve = _native.Solve(ctx, sc.native, em.native, ids, active, M._rotation_table(5, n, 6), ids.copy(), max_iters=6, min_iters=6,
+                          interval=1, tol_mode="stderr", tol=0.0, emit_sid=ids, min_sid=np.zeros(n, np.int32))
+    try:
+        solve.step(6)
+        dense, iters, totals = solve.read_block()
+        view, iters2, totals2 = solve.read_block_view()
+        assert np.array_equal(view, dense) and np.array_equal(iters, iters2) and np.array_equal(totals, totals2)
+        want = M._csr_from_dense(dense, totals)
+        got = solve.read_csr()
+        for a, b in zip(got, want):
+            assert a.dtype == b.dtype and np.array_equal(a, b)
+        assert got[0][-1] > 100
+        # the same through a tally block: rows scattered by emitter id, jobs with keep == 0 left out
+        blk = _native.TallyBlock(ctx, n, 2 * n)
+        keep = np.ones(n, np.uint8)
+        keep[3] = 0
+        blk.add_solve(solve, keep)
+        blk.allreduce()                                              # no communicator: a no-op
+        dense_k = dense.copy()
+        dense_k[3] = 0
+        assert np.array_equal(blk.download(copy=True), dense_k)
+        for a, b in zip(blk.read_csr(totals), M._csr_from_dense(dense_k, totals)):
+            assert np.array_equal(a, b)
+        blk.close()
+    finally:
+        solve.close()
+
+
+def test_terrain_with_small_objects_per_ray_and_solve(rb):
+    """Strongly varying triangle sizes (0.85 m terrain, centimetre spheres, 50 m slabs; non-planar emitters): per-ray closest
+    hits vs the oracle through the GPU-built tree, and a short whole solve."""
+    from oracle import oracle as O
+    from raystrack_b200 import _native, synthetic
+    from raystrack_b200.prepared import PreparedSolver
+    meshes = synthetic.terrain_with_objects(2, 60, 40, 20, 2, 1)          # 66 meshes, 33 764 triangles
+    ctx = _native.Context.for_device(0)
+    ps = PreparedSolver(meshes)
+    sc = ps.get_device_scene(use_bvh=True, ctx=ctx).native
+    em = ps.get_device_emitters(samples=1, rays=16, flip_faces=False, ctx=ctx).native
+    S = O.OracleSolver(meshes)
+    oem = S.emitters(1, 16, False)
+    centers, extents = S.bounds()
+    scene = S.scene(True)
+    for idx in (0, 3, 4, 30, 44, 50, 64):                                  # terrain tiles, boxes, spheres, a slab
+        cpg, cpd = O.rotation(7, idx, 2)
+        act = O.surface_mask(idx, oem[idx], centers, extents)
+        n = min(oem[idx].n_rays_once, 16384)
+        o, d, hit, front = _native.trace_rays(ctx, sc, em, idx, act, idx, 0, np.concatenate([cpg, cpd]), mode=0, n_rays=n)
+        ro, rd = O.build_rays(oem[idx], cpg, cpd, count=n)
+        assert np.array_equal(o, ro) and np.array_equal(d, rd)
+        rh, rf = O.trace_firsthit(scene, ro, rd, act, idx, 0)
+        assert float(np.mean((hit == rh) & (front == rf))) >= 0.9999, idx
+    params = dict(samples=1, rays=16, seed=4, bvh="builtin", max_iters=4, min_iters=4, tol=0.0, reciprocity=False)
+    got = rb.view_factor_matrix(meshes, rb.MatrixParams(**params))
+    assert _worst(got, S.view_factor_matrix(**params)) <= 1e-4

@@ -381,3 +381,23 @@ def test_shared_ray_solve_equals_separate_solves(rb, scene, bvh, recip, discrete
         m = re.search(r"scene=(\d+) iter, sky=(\d+) iter", line)
         assert int(m.group(1)) == int(re.search(r"\] (\d+) iter", lm).group(1))
         assert int(m.group(2)) == int(re.search(r"\] (\d+) iter", ls).group(1))
+
+
+@pytest.mark.parametrize("idx", [0, 4, 122, 245])
+def test_per_ray_hits_match_reference_on_a_127k_triangle_scene(ctx, idx):
+    """A real-size tree pinned to the REFERENCE (not to the CUDA brute-force path): per-ray closest hits and any-hit flags
+    of the reference's BVH tracer over 127 488 triangles (tests/golden/large_rays.npz, generated by make_golden.py from
+    /root/reference) against the C-ABI per-ray hook through the GPU-built 8-wide BVH."""
+    from pathlib import Path
+    from raystrack_b200 import _native, synthetic
+    z = np.load(Path(__file__).resolve().parent / "golden" / "large_rays.npz")
+    meshes = synthetic.urban_block(7, 16, 32, 0)
+    ps, sc, em = _device_objects(ctx, meshes, 4, 16, False, True)
+    assert sc.info()["n_tri"] == int(z["n_tri"][0])
+    cp, act = z[f"e{idx}_cp"], z[f"e{idx}_active"]
+    n = z[f"e{idx}_hit"].shape[0]
+    _, _, hit, front = _native.trace_rays(ctx, sc, em, idx, act, idx, 0, cp, mode=0, n_rays=n, want_rays=False)
+    agree = float(np.mean((hit == z[f"e{idx}_hit"].astype(np.int32)) & (front == z[f"e{idx}_front"])))
+    assert agree >= PER_RAY_AGREEMENT, agree
+    _, _, anyhit, _ = _native.trace_rays(ctx, sc, em, idx, act, idx, 0, cp, mode=1, n_rays=n, want_rays=False)
+    assert float(np.mean(anyhit == z[f"e{idx}_mask"])) >= PER_RAY_AGREEMENT

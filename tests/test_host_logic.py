@@ -252,3 +252,22 @@ def test_plan_chunks_respects_budget_and_keeps_shared_jobs_together(monkeypatch)
     assert chunks[0] == plan[:2] and all(len(c) == 1 for c in chunks[1:]) and [j for c in chunks for j in c] == plan
     monkeypatch.delenv("RSK_SOLVE_MEMORY_MB")
     assert M._plan_chunks(plan, n_hist) == [plan] and M._plan_chunks([], n_hist) == [[]]
+
+
+def test_csr_from_dense_matches_the_dense_row_loop():
+    """`_csr_from_dense` (the host form of rsk_solve_csr): non-zero bins per row, columns ascending, F = hits / rays."""
+    rng = np.random.default_rng(3)
+    t = np.zeros((7, 12), np.int64)
+    m = rng.random(t.shape) < 0.3
+    t[m] = rng.integers(1, 10**9, int(m.sum()))
+    t[4] = 0                                                       # an emitter that never ran: total 0, no bins
+    totals = np.array([5, 7, 11, 13, 0, 17, 10**12], np.int64)
+    row_ptr, cols, vals = M._csr_from_dense(t, totals)
+    assert row_ptr.dtype == np.int64 and cols.dtype == np.int32 and vals.dtype == np.float64
+    assert row_ptr[0] == 0 and row_ptr[-1] == int(m.sum()) - int(m[4].sum())
+    for i in range(t.shape[0]):
+        nz = np.flatnonzero(t[i])
+        assert cols[row_ptr[i]:row_ptr[i + 1]].tolist() == nz.tolist()
+        assert vals[row_ptr[i]:row_ptr[i + 1]].tolist() == [int(t[i, j]) / float(totals[i]) for j in nz]
+    empty = M._csr_from_dense(np.zeros((0, 4), np.int64), np.zeros(0, np.int64))
+    assert empty[0].tolist() == [0] and empty[1].size == 0

@@ -115,3 +115,27 @@ def test_shipped_result_files(solves, shipped):
             assert {k for k, v in res[name].items() if v != 0.0} == set(row)
             for key, val in row.items():
                 assert res[name][key] == val
+
+
+LARGE_EMITTERS = (0, 4, 122, 245)
+
+
+def test_oracle_matches_reference_on_a_127k_triangle_tree():
+    """tests/golden/large_rays.npz: the reference's trace_cpu_bvh_firsthit / _hitmask through its own median-split BVH over
+    127 488 triangles (7x7 urban block).  The oracle builds the same tree and must reproduce every ray."""
+    from pathlib import Path
+    from raystrack_b200 import synthetic
+    z = np.load(Path(__file__).resolve().parent / "golden" / "large_rays.npz")
+    meshes = synthetic.urban_block(7, 16, 32, 0)
+    S = O.OracleSolver(meshes)
+    scene = S.scene(True)
+    assert scene.v0.shape[0] == int(z["n_tri"][0]) and scene.bvh[2].shape[0] == int(z["n_nodes"][0])
+    for idx in LARGE_EMITTERS:
+        em = O.prepare_emitters([meshes[idx]], 4, 16, False)[0]
+        cp = z[f"e{idx}_cp"]
+        n = z[f"e{idx}_hit"].shape[0]
+        o, d = O.build_rays(em, cp[:2], cp[2:], count=n)
+        act = z[f"e{idx}_active"]
+        hit, front = O.trace_firsthit(scene, o, d, act, idx, 0)
+        assert np.array_equal(hit, z[f"e{idx}_hit"].astype(np.int32)) and np.array_equal(front, z[f"e{idx}_front"])
+        assert np.array_equal(O.trace_hitmask(scene, o, d, act, idx, 0), z[f"e{idx}_mask"])
