@@ -88,7 +88,8 @@ int rsk_scene_download_bvh(rsk_scene *scene, void *nodes, int32_t *tri_index);
  * Replaces prepare_emitters' per-mesh arrays + PreparedSolver.get_device_emitter + the Halton tables
  * (utils/prepared.py:246-321, 405-431; utils/halton.py:9-58).  Triangles of all emitters are concatenated;
  * emitter i owns rows [tri_offset[i], tri_offset[i+1]).  g[i] is the Halton grid side (helpers.py:8-11),
- * rays_per_cell the `rays` parameter: emitter i shoots g[i]^2 * rays_per_cell rays per iteration.
+ * rays_per_cell the `rays` parameter: emitter i shoots g[i]^2 * rays_per_cell rays per iteration.  A negative g[i]
+ * marks a zero-area emitter: grid side -g[i], jitter and Halton values all zero (utils/prepared.py:278-287).
  * The five per-ray Halton dimensions (bases 5,2,3,7,11) and the per-cell jitter grids are generated on the
  * device with the reference's exact float64 operation order and cached in the context. */
 int rsk_emitters_create(rsk_ctx *ctx, int32_t n_emit, const int64_t *tri_offset,

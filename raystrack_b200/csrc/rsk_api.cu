@@ -265,13 +265,14 @@ extern "C" int rsk_emitters_create(rsk_ctx *ctx, int32_t n_emit, const int64_t *
         EmitterDesc &d = em->h_desc[i];
         d.tri_off = (int32_t)tri_offset[i];
         d.n_tri = (int32_t)(tri_offset[i + 1] - tri_offset[i]);
-        d.g = g[i];
+        const bool zero_tables = g[i] < 0;        // -g: the reference's zero-area emitter, all-zero QMC tables
+        d.g = zero_tables ? -g[i] : g[i];
         if (d.g < 1 || d.n_tri < 0) { rsk_set_error("rsk_emitters_create: bad grid/triangle count for emitter %d", i); rc = RSK_ERR_INVALID; break; }
         d.n_rays_once = (int64_t)d.g * d.g * rays_per_cell;
         em->max_rays_once = std::max(em->max_rays_once, d.n_rays_once);
         int64_t off = 0;
         rc = rsk_qmc_ensure_grid(ctx, d.g, &off);
-        d.grid_off = (int32_t)off;
+        d.grid_off = zero_tables ? -1 : (int32_t)off;
     }
     if (rc == RSK_OK) rc = rsk_qmc_ensure_halton(ctx, em->max_rays_once);
     float *raw = nullptr;

@@ -382,7 +382,7 @@ extern "C" int rsk_emitters_from_geometry(rsk_geometry *g, double density, int32
         em->max_rays_once = std::max(em->max_rays_once, d.n_rays_once);
         int64_t off = 0;
         rc = rsk_qmc_ensure_grid(ctx, d.g, &off);
-        d.grid_off = (int32_t)off;
+        d.grid_off = area <= 0.0 ? -1 : (int32_t)off;          // zero area: all-zero QMC tables (prepared.py:278-287)
     }
     if (rc == RSK_OK) rc = rsk_qmc_ensure_halton(ctx, em->max_rays_once);
     if (rc == RSK_OK && g->n_mesh > 0) {

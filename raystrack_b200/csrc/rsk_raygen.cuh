@@ -34,7 +34,7 @@ __device__ __forceinline__ int rsk_cdf_search(const float *__restrict__ cdf, int
         int mid = (lo + hi) >> 1;
         if ((double)__ldg(cdf + mid) < x) lo = mid + 1; else hi = mid - 1;
     }
-    return lo >= n ? n - 1 : lo;
+    return lo >= n ? max(n - 1, 0) : lo;
 }
 
 __device__ __forceinline__ double rsk_mad3(double a, double x, double b, double y, double c, double z) {
@@ -44,16 +44,20 @@ __device__ __forceinline__ double rsk_mad3(double a, double x, double b, double 
 
 // Ray k (0 <= k < n_rays_once) of emitter `e` under rotation cp[0..6] = (cp_grid[0..1], cp_dims[0..4]).
 __device__ __forceinline__ Ray rsk_make_ray(const EmitterView &ev, const EmitterDesc &e, int64_t k, const float *cp) {
+    // A zero-area emitter (grid_off < 0) has all-zero jitter and Halton tables in the reference (prepared.py:278-287):
+    // only the Cranley-Patterson offsets move its rays.
+    const bool zero_tables = e.grid_off < 0;
     const int64_t cell = k / ev.rays_per_cell;
-    const float2 jit = __ldg(ev.grid + e.grid_off + cell);
+    const float2 jit = zero_tables ? make_float2(0.f, 0.f) : __ldg(ev.grid + e.grid_off + cell);
     const double ug = rsk_mod1((double)__fadd_rn(jit.x, cp[0]));                       // :54
     const double vg = rsk_mod1((double)__fadd_rn(jit.y, cp[1]));                       // :55
     const float *h = ev.halton + k;
     const int64_t hs = ev.halton_stride;
-    const double q_tri = rsk_mod1((double)__fadd_rn(RSK_HLOAD(h), cp[2]));                 // :57
+#define RSK_HVAL(p) (zero_tables ? 0.0f : RSK_HLOAD(p))
+    const double q_tri = rsk_mod1((double)__fadd_rn(RSK_HVAL(h), cp[2]));                  // :57
     const int tri = rsk_cdf_search(ev.cdf + e.tri_off, e.n_tri, q_tri);                // :58
-    const double ur = rsk_mod1(__dadd_rn((double)__fadd_rn(RSK_HLOAD(h + hs), cp[3]), ug));     // :60
-    const double vr = rsk_mod1(__dadd_rn((double)__fadd_rn(RSK_HLOAD(h + 2 * hs), cp[4]), vg)); // :61
+    const double ur = rsk_mod1(__dadd_rn((double)__fadd_rn(RSK_HVAL(h + hs), cp[3]), ug));     // :60
+    const double vr = rsk_mod1(__dadd_rn((double)__fadd_rn(RSK_HVAL(h + 2 * hs), cp[4]), vg)); // :61
     const double s = sqrt(ur);                                                         // :63
     const double mix_b = __dmul_rn(s, vr);
     const double mix_c = __dmul_rn(s, __dsub_rn(1.0, vr));
@@ -67,8 +71,8 @@ __device__ __forceinline__ Ray rsk_make_ray(const EmitterView &ev, const Emitter
     const double py = __dadd_rn(__dadd_rn((double)A.y, __dmul_rn(mix_b, (double)E1.y)), __dmul_rn(mix_c, (double)E2.y));
     const double pz = __dadd_rn(__dadd_rn((double)A.z, __dmul_rn(mix_b, (double)E1.z)), __dmul_rn(mix_c, (double)E2.z));
 
-    const double r1 = rsk_mod1((double)__fadd_rn(RSK_HLOAD(h + 3 * hs), cp[5]));           // :75
-    const double r2 = rsk_mod1((double)__fadd_rn(RSK_HLOAD(h + 4 * hs), cp[6]));           // :76
+    const double r1 = rsk_mod1((double)__fadd_rn(RSK_HVAL(h + 3 * hs), cp[5]));           // :75
+    const double r2 = rsk_mod1((double)__fadd_rn(RSK_HVAL(h + 4 * hs), cp[6]));           // :76
     const double sin_t = sqrt(__dsub_rn(1.0, r1));                                     // :78
     const double phi = __dmul_rn(6.283185307179586, r2);
     double sn, cs;
@@ -84,5 +88,6 @@ __device__ __forceinline__ Ray rsk_make_ray(const EmitterView &ev, const Emitter
     r.ox = (float)__dadd_rn(px, (double)__fmul_rn(eps, nx));                           // :89-91
     r.oy = (float)__dadd_rn(py, (double)__fmul_rn(eps, ny));
     r.oz = (float)__dadd_rn(pz, (double)__fmul_rn(eps, nz));
+#undef RSK_HVAL
     return r;
 }

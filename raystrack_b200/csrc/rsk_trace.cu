@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
     if (MODE == MODE_DUAL ? (!want_m && !want_s) : side1_done) return;
 
     const EmitterDesc e = a.ev.desc[a.emit_ids[job]];
+    if (e.n_tri <= 0) return;          // a mesh without triangles shoots nothing (the host never schedules it either)
     const int64_t begin = td.begin;
     const int64_t end = begin + td.count;
 

@@ -60,8 +60,9 @@ def _select_bvh(bvh: Optional[str], total_faces: int) -> bool:
 
 def _resolve_device(device: Optional[str]) -> str:
     """reference main.py:136-147.  Every value runs on the GPU (this package has no CPU path); the returned
-    label only selects the convergence schedule: "cpu" checks after every iteration like the reference's CPU
-    loop (main.py:1889), "gpu" honours ``convergence_interval``."""
+    label selects the convergence schedule -- "cpu" checks after every iteration like the reference's CPU loop
+    (main.py:1889), "gpu" honours ``convergence_interval`` -- and is what the progress lines print after
+    ``device=``, as the reference prints its resolved device (main.py:1938)."""
     dev = (device or "auto").lower()
     if dev not in ("auto", "gpu", "cpu"):
         raise ValueError(f"device must be 'auto', 'gpu', or 'cpu' (got {device!r})")
@@ -446,6 +447,8 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
         has_recv = np.asarray([bool(active[i, i + 1:].any()) for i in range(n_surf)], bool)
     else:
         has_recv = active.any(axis=1)
+    # a mesh without triangles shoots nothing (the reference fails on it; here it reports "0 iter, 0 rays")
+    has_recv = has_recv & np.fromiter((np.asarray(f).shape[0] > 0 for _, _, f in meshes), bool, n_surf)
     todo = [i for i in range(n_surf) if has_recv[i]]
 
     weights = [float(em.n_cells * rays) for em in emitters]
@@ -476,7 +479,7 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
     for i, (name_e, _, _) in enumerate(meshes):
         if not has_recv[i]:
             if _hook is None:
-                _log(f"({i+1}/{n_surf}) [{name_e}] 0 iter, 0 rays -> 0.000s  (BVH={label}, device=gpu)")
+                _log(f"({i+1}/{n_surf}) [{name_e}] 0 iter, 0 rays -> 0.000s  (BVH={label}, device={schedule})")
             continue
         lo, hi = bounds[i], bounds[i + 1]
         vals = vals_all[lo:hi]
@@ -489,11 +492,11 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
         result[name_e].update(row)
         if _hook is None:
             _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {elapsed * work[i] / work_sum:0.3f}s  "
-                 f"(BVH={label}, device=gpu)")
+                 f"(BVH={label}, device={schedule})")
 
     LAST_TIMING["assemble"] = time.perf_counter() - t_asm
     if _hook is not None:
-        _hook.update(iters=iters, totals=totals, n_once=n_once, label=label, elapsed=elapsed)
+        _hook.update(iters=iters, totals=totals, n_once=n_once, label=label, elapsed=elapsed, device=schedule)
         return result
     if p["enforce_reciprocity_rowsum"]:
         from .reciprocity import enforce_reciprocity_and_rowsum
@@ -548,7 +551,8 @@ def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepar
         counts, iters, totals = _hook["precomputed"]
     else:
         table = _rotation_table(seed, n_surf, max_iters)
-        counts, iters, totals = _solve_sharded(ctx, d_scene, d_em, list(range(n_surf)), n_once, active, table, max_iters=max_iters,
+        nonempty = [i for i, (_, _, f) in enumerate(meshes) if np.asarray(f).shape[0] > 0]
+        counts, iters, totals = _solve_sharded(ctx, d_scene, d_em, nonempty, n_once, active, table, max_iters=max_iters,
                                                min_iters=min_iters, interval=interval if schedule == "gpu" else 1,
                                                tol_mode=tol_mode, tol=tol, sky=True, discrete=discrete)
     elapsed = time.time() - t0
@@ -565,9 +569,9 @@ def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepar
             result[name_e]["Sky"] = float(int(counts[i, 0]) / denom)
         if _hook is None:
             _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {elapsed * work[i] / work_sum:0.3f}s  "
-                 f"(BVH={label}, device=gpu)")
+                 f"(BVH={label}, device={schedule})")
     if _hook is not None:
-        _hook.update(iters=iters, totals=totals, n_once=n_once, label=label, elapsed=elapsed)
+        _hook.update(iters=iters, totals=totals, n_once=n_once, label=label, elapsed=elapsed, device=schedule)
     return result
 
 
@@ -703,7 +707,7 @@ def view_factor_matrix_and_sky(meshes: List[Mesh], *, matrix_params: MatrixParam
         traced = max(m_it, s_it)
         _log(f"({i+1}/{n}) [{name_e}] traced {traced} iter, {traced * int(mh['n_once'][i]):,} rays -> "
              f"{(mh['elapsed'] + sh['elapsed']) / max(1, n):0.3f}s  (scene={m_it} iter, sky={s_it} iter, "
-             f"BVH={mh['label']}, device=gpu)")
+             f"BVH={mh['label']}, device={mh['device']})")
     return vf_scene, sky_vf
 
 

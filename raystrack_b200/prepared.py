@@ -68,15 +68,18 @@ class PreparedEmitter:
 
     # The reference stores the QMC tables on every emitter; here they live on the GPU.  Host copies are
     # produced on demand with the same float64 recurrence (utils/halton.py:9-39).
+    # A zero-area emitter has all-zero tables in the reference (prepared.py:278-287).
     @property
     def u_grid(self) -> np.ndarray:
-        return halton_grid_host(self.g)[0]
+        return halton_grid_host(self.g)[0] if self.total_area > 0.0 else np.zeros(self.n_cells, np.float32)
 
     @property
     def v_grid(self) -> np.ndarray:
-        return halton_grid_host(self.g)[1]
+        return halton_grid_host(self.g)[1] if self.total_area > 0.0 else np.zeros(self.n_cells, np.float32)
 
     def _dim(self, base: int) -> np.ndarray:
+        if not self.total_area > 0.0:
+            return np.zeros(self.n_cells * self.rays, np.float32)
         return halton_dim_host(self.n_cells * self.rays, base)
 
     halton_tri = property(lambda self: self._dim(5))
@@ -478,7 +481,8 @@ class PreparedSolver:
                     return np.ascontiguousarray(np.concatenate([getattr(e, name) for e in ems], axis=0), np.float32)
 
                 pack = (off, cat("tri_a", 3), cat("tri_e1", 3), cat("tri_e2", 3), cat("tri_u", 3), cat("tri_v", 3),
-                        cat("tri_n", 3), cat("tri_origin_eps", 0), cat("cdf", 0), np.asarray([e.g for e in ems], np.int32))
+                        cat("tri_n", 3), cat("tri_origin_eps", 0), cat("cdf", 0),
+                        np.asarray([e.g if e.total_area > 0.0 else -e.g for e in ems], np.int32))      # -g: zero-area emitter
                 self._emitter_pack_cache[hkey] = pack
             nat = _native.DeviceEmitters(ctx, *pack, int(rays))
             got = PreparedDeviceEmitters(nat, np.asarray([e.n_cells * int(rays) for e in ems], np.int64))

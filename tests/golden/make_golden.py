@@ -240,6 +240,22 @@ def large_rays():
         z[f"e{idx}_mask"] = hm
         z[f"e{idx}_rays_sha"] = np.frombuffer(bytes.fromhex(sha(o) + sha(d)), np.uint8)
         print(f"large emitter {idx}: {n} rays, hit fraction {float(np.mean(hs >= 0)):.3f}, receivers {len(np.unique(hs))}")
+    # --- a zero-area emitter (collinear corners): all-zero QMC tables, cdf of ones (utils/prepared.py:278-287)
+    Vz = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [3, 0, 0]], np.float32)
+    Fz = np.array([[0, 1, 2], [1, 2, 3]], np.int32)
+    em = prepared.prepare_emitters([("line", Vz, Fz)], samples=4, rays=8, flip_faces=False)[0]
+    assert em.total_area <= 0.0 and em.g == 4 and not em.halton_tri.any()
+    rng = np.random.default_rng(77)
+    cpg = rng.random(2, dtype=np.float32)
+    cpd = rng.random(5, dtype=np.float32)
+    n = em.n_cells * 8
+    o = np.empty((n, 3), np.float32)
+    d = np.empty_like(o)
+    ray_builder.build_rays(em.u_grid, em.v_grid, em.halton_tri, em.halton_u, em.halton_v, em.halton_r1, em.halton_r2, em.cdf, em.tri_a,
+                           em.tri_e1, em.tri_e2, em.tri_u, em.tri_v, em.tri_n, em.tri_origin_eps, 8, o, d, cpg, cpd)
+    z["zero_area_cp"] = np.concatenate([cpg, cpd])
+    z["zero_area_orig"] = o
+    z["zero_area_dir"] = d
     np.savez_compressed(HERE / "large_rays.npz", **z)
     print("large_rays.npz", (HERE / "large_rays.npz").stat().st_size, "bytes")
 

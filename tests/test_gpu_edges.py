@@ -322,3 +322,31 @@ def test_terrain_with_small_objects_per_ray_and_solve(rb):
     params = dict(samples=1, rays=16, seed=4, bvh="builtin", max_iters=4, min_iters=4, tol=0.0, reciprocity=False)
     got = rb.view_factor_matrix(meshes, rb.MatrixParams(**params))
     assert _worst(got, S.view_factor_matrix(**params)) <= 1e-4
+
+
+def test_zero_area_and_empty_emitters(rb):
+    """A zero-area emitter shoots the reference's rays (all-zero QMC tables, prepared.py:278-287) on both preparation
+    routes; a mesh without triangles is never traced and does not disturb its neighbours."""
+    from pathlib import Path
+    from raystrack_b200 import _native, synthetic
+    from raystrack_b200.prepared import PreparedSolver
+    z = np.load(Path(__file__).resolve().parent / "golden" / "large_rays.npz")
+    line = ("line", np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [3, 0, 0]], np.float32), np.array([[0, 1, 2], [1, 2, 3]], np.int32))
+    sq = synthetic.parallel_unit_squares()
+    meshes = [line, sq[0], sq[1]]
+    ctx = _native.Context.for_device(0)
+    for host in (False, True):
+        ps = PreparedSolver(meshes)
+        if host:
+            ps._host_prepare_forced = lambda: True
+        sc = ps.get_device_scene(use_bvh=False, ctx=ctx).native
+        em = ps.get_device_emitters(samples=4, rays=8, flip_faces=False, ctx=ctx).native
+        o, d, _, _ = _native.trace_rays(ctx, sc, em, 0, np.ones(3, np.uint8), 0, 0, z["zero_area_cp"], mode=0)
+        assert np.array_equal(o, z["zero_area_orig"], equal_nan=True) and np.array_equal(d, z["zero_area_dir"], equal_nan=True), host
+    empty = ("nothing", np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32))
+    p = rb.MatrixParams(samples=16, rays=32, seed=3, bvh="off", max_iters=6, min_iters=6, tol=0.0, reciprocity=False)
+    with_empty = rb.view_factor_matrix([sq[0], empty, sq[1]], p)
+    assert with_empty["nothing"] == {} and all("nothing" not in k for row in with_empty.values() for k in row)
+    assert with_empty["A"] == rb.view_factor_matrix(sq, p)["A"]
+    sky = rb.view_factor_to_tregenza_sky([sq[0], empty, sq[1]], rb.SkyParams(samples=16, rays=32, seed=3, bvh="off", max_iters=6, min_iters=6))
+    assert sky["nothing"] == {"Sky": 0.0}

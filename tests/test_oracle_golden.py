@@ -139,3 +139,21 @@ def test_oracle_matches_reference_on_a_127k_triangle_tree():
         hit, front = O.trace_firsthit(scene, o, d, act, idx, 0)
         assert np.array_equal(hit, z[f"e{idx}_hit"].astype(np.int32)) and np.array_equal(front, z[f"e{idx}_front"])
         assert np.array_equal(O.trace_hitmask(scene, o, d, act, idx, 0), z[f"e{idx}_mask"])
+
+
+ZERO_AREA_MESH = ("line", np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [3, 0, 0]], np.float32), np.array([[0, 1, 2], [1, 2, 3]], np.int32))
+
+
+def test_zero_area_emitter_uses_all_zero_tables():
+    """utils/prepared.py:278-287: a zero-area mesh keeps g = 4, a cdf of ones and all-zero jitter / Halton tables, so only
+    the Cranley-Patterson offsets move its rays (reference rays in tests/golden/large_rays.npz)."""
+    from pathlib import Path
+    from raystrack_b200 import prepared as P
+    z = np.load(Path(__file__).resolve().parent / "golden" / "large_rays.npz")
+    em = O.prepare_emitters([ZERO_AREA_MESH], 4, 8, False)[0]
+    cp = z["zero_area_cp"]
+    o, d = O.build_rays(em, cp[:2], cp[2:])
+    assert np.array_equal(o, z["zero_area_orig"], equal_nan=True) and np.array_equal(d, z["zero_area_dir"], equal_nan=True)
+    host = P.prepare_emitters([ZERO_AREA_MESH], samples=4, rays=8, flip_faces=False)[0]
+    assert host.g == 4 and not host.u_grid.any() and not host.halton_tri.any() and not host.halton_r2.any()
+    assert np.array_equal(host.cdf, np.ones(2, np.float32))
