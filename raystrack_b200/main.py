@@ -332,7 +332,7 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
     # result comes back in a single copy through pinned memory.
     block = _native.TallyBlock(ctx, n_emit, n_hist) if exchange == "native" else None
     tallies = iters = totals = None
-    if not single:
+    if single_csr or not single:
         tallies = None if (block is not None or single_csr) else np.zeros((n_emit, n_hist), np.int64)
         iters = np.zeros(n_emit, np.int64)
         totals = np.zeros(n_emit, np.int64)
