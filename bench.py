@@ -8,8 +8,9 @@ One *step* = one Monte-Carlo iteration of every emitter of the scene: 2001 emitt
 generated (QMC sampler), traced to its closest hit through the wide BVH and tallied per receiver x {front, back},
 followed by the on-device statistics/convergence pass.  Prints ONE JSON line (rank 0).
 
-  value     closest-hit Grays/s of the whole job, inputs resident in HBM, timed with CUDA events on the launching
-            stream, max over ranks; L2 is flushed between timed steps
+  value     closest-hit Grays/s of the whole job, inputs resident in HBM: K steps enqueued back to back, CUDA events on
+            the launching streams around all of them, max over ranks; the L2 is evicted before every step (160 MB
+            scratch write on the trace stream, inside the timed region)
   e2e       the same metric through the public API ``view_factor_matrix`` (C ABI underneath) with HOST buffers:
             every call starts from the mesh list alone -- vertices + faces uploaded, triangle/emitter records and the
             BVH built on the GPU, 40 iterations, tally download and result assembly
@@ -201,16 +202,17 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------------------------- GPU arm
 
-def _time_steps(ctx, fn, steps, flush, torch):
-    """CUDA-event time (ms per call) of ``fn`` on the context's stream, L2 flushed before every call."""
-    out = []
+L2_FLUSH_BYTES = 160 * 1024 * 1024      # > the 126 MB L2: written before every trace launch, on its stream, inside the timed region
+
+
+def _time_steps(ctx, fn, steps):
+    """CUDA-event time (ms per call) of ``steps`` back-to-back calls of ``fn`` on the context's streams; the L2 is
+    evicted before every trace launch (Context.set_l2_flush is on while bench.py measures)."""
+    ctx.synchronize()
+    ctx.timer_start()
     for _ in range(steps):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        ctx.timer_start()
         fn()
-        out.append(ctx.timer_stop())
-    return float(np.mean(out))
+    return ctx.timer_stop() / steps
 
 
 def _max_abs_diff(res, gold):
@@ -281,7 +283,7 @@ def parity_block(ctx, rank, world, sc, em, active, n_once, table, args):
     return out
 
 
-def terrain_block(ctx, flush, torch, with_cpu: bool):
+def terrain_block(ctx, with_cpu: bool):
     """A second workload for tree quality: terrain + small objects (synthetic.terrain_with_objects, 1 053 352 triangles of
     0.03 ... 50 m, non-planar emitters), closest-hit throughput of one iteration of all 748 emitters and -- against the
     oracle (median-split reference tree) on a CPU sample -- per-ray agreement."""
@@ -300,7 +302,7 @@ def terrain_block(ctx, flush, torch, with_cpu: bool):
     solve = _native.Solve(ctx, sc.native, em.native, ids, active, M._rotation_table(seed, n, 64), ids.copy(), max_iters=64, min_iters=64,
                           interval=1, tol_mode="stderr", tol=0.0, emit_sid=ids, min_sid=np.zeros(n, np.int32))
     solve.step(2)
-    ms = _time_steps(ctx, lambda: solve.step(1), 3, flush, torch)
+    ms = _time_steps(ctx, lambda: solve.step(1), 3)
     solve.close()
     info = sc.info()
     out = {"workload": f"terrain + small objects: {n} meshes, {ps.total_faces} triangles, samples={samples} rays={rays} "
@@ -330,9 +332,9 @@ def terrain_block(ctx, flush, torch, with_cpu: bool):
     return out
 
 
-def secondary_block(ctx, sc, em, active, n_once, table, rays_per_step, flush, torch):
+def secondary_block(ctx, sc, em, active, n_once, table, rays_per_step):
     """The other kernels of the path on the same scene and step definition (one iteration of every emitter), CUDA-event
-    timed, L2 flushed: discrete-sky any-hit, dual (closest hit + any-hit flag from one walk), and the API-default
+    timed over 3 back-to-back steps, L2 evicted before every trace: discrete-sky any-hit, dual (closest hit + any-hit flag from one walk), and the API-default
     reciprocity=True schedule (emitter i ignores meshes j <= i; the last emitter has no receivers)."""
     from raystrack_b200 import _native
     n = active.shape[0]
@@ -343,7 +345,7 @@ def secondary_block(ctx, sc, em, active, n_once, table, rays_per_step, flush, to
 
     def run(name, solve, rays):
         solve.step(2)
-        ms = _time_steps(ctx, lambda: solve.step(1), 3, flush, torch)
+        ms = _time_steps(ctx, lambda: solve.step(1), 3)
         out[name] = {"value": rays / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms}
         solve.close()
 
@@ -400,7 +402,7 @@ def run_ours(args):
     solve = _native.Solve(ctx, sc.native, em.native, ids, active[ids], table, ids.copy(), max_iters=total_iters,
                           min_iters=total_iters, interval=1, tol_mode="stderr", tol=0.0,
                           emit_sid=ids, min_sid=np.zeros(len(ids), np.int32), ray_range=ranges)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local}")     # > 126 MB L2
+    ctx.set_l2_flush(L2_FLUSH_BYTES)        # from here on every trace launch is preceded by a 160 MB scratch write
 
     def one_step(trace_only_timer=None):
         if trace_only_timer is not None:
@@ -409,7 +411,7 @@ def run_ours(args):
         if trace_only_timer is not None:
             trace_only_timer.append(ctx.timer_stop())
         if world > 1 and n_shared:
-            solve.allreduce_iter_tallies(n_shared)              # NCCL on the context's stream, between trace and fold
+            solve.allreduce_iter_tallies(n_shared)              # NCCL on the iteration's stream, between trace and fold
         solve.enqueue_fold()
 
     for _ in range(max(args.warmup, 3)):
@@ -422,31 +424,30 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count()
-    step_ms = []
+    # the timed region: exactly K steps, enqueued back to back (iterations are pipelined over two streams inside the
+    # library; statistics still fold in iteration order), CUDA events on the context's streams around all of them
+    ctx.timer_start()
     for _ in range(args.steps):
-        flush.fill_(1)                      # L2 flush between timed iterations (not timed)
-        torch.cuda.synchronize()
-        ctx.timer_start()
         one_step()
-        step_ms.append(ctx.timer_stop())
+    local_ms = ctx.timer_stop()
     launches = ctx.launch_count() - launches0
     torch.cuda.synchronize()
     if world > 1:
         D.barrier()
-    total_ms = D.max_over_ranks(float(sum(step_ms)))
+    total_ms = D.max_over_ranks(float(local_ms))
     value = rays_per_step * args.steps / (total_ms * 1e-3) / 1e9
 
     # dominant kernel alone (same stream, CUDA events around the trace launch only)
     trace_ms = []
     for _ in range(args.steps):
-        flush.fill_(1)
-        torch.cuda.synchronize()
+        ctx.synchronize()
         one_step(trace_ms)
     ctx.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     my_rays = int(sum(j[2] - j[1] for j in plan))
     trace_avg_ms = float(np.mean(trace_ms))
     solve.close()
+    ctx.set_l2_flush(0)                     # the public-API calls below run as a user's would
 
     # ---- e2e through the public API with host buffers: the BASELINE config-#5 call (fixed iteration count so every
     # implementation traces identical rays).  Every timed call starts from the caller's mesh list alone: flattening,
@@ -477,8 +478,10 @@ def run_ours(args):
         if not args.no_parity:
             parity = parity_block(ctx, rank, world, sc, em, active, n_once, table, args)
         if world == 1 and not args.no_secondary:
-            secondary = secondary_block(ctx, sc, em, active, n_once, table, rays_per_step, flush, torch)
-            secondary["terrain_scene"] = terrain_block(ctx, flush, torch, with_cpu=not args.no_cpu)
+            ctx.set_l2_flush(L2_FLUSH_BYTES)
+            secondary = secondary_block(ctx, sc, em, active, n_once, table, rays_per_step)
+            secondary["terrain_scene"] = terrain_block(ctx, with_cpu=not args.no_cpu)
+            ctx.set_l2_flush(0)
     finally:
         M._log = old_log
     e2e_value = rays_per_step * args.e2e_iters / float(np.mean(e2e_times)) / 1e9 if e2e_times else None
@@ -500,7 +503,7 @@ def run_ours(args):
             "dtype": "f32 (f64 ray generation)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "step": "one Monte-Carlo iteration of all 2001 emitters", "rays_per_step": rays_per_step,
                        "bvh": f"GPU LBVH -> 8-wide quantised, {info['n_nodes']} nodes, depth {info['depth']}, built in {info['build_us']/1e3:.1f} ms",
-                       "l2": "flushed between timed steps (256 MB write)", "sharding": f"emitters over {world} GPU(s), {n_shared} ray-split",
+                       "l2": "evicted before every iteration: 160 MB scratch write on the trace stream, inside the timed region", "sharding": f"emitters over {world} GPU(s), {n_shared} ray-split",
                        "collectives": None if comm is None else f"librsk_b200 rsk_comm (NCCL {comm['nccl_version']}, {comm['nranks']} ranks) on the kernel stream",
                        "upload_prepare_build_s": round(prep_s, 3)},
             "gpu_launches": int(launches), "clocks": clocks,

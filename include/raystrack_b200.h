@@ -59,7 +59,10 @@ int rsk_device_count(int *count);
 int rsk_ctx_create(int device_ordinal, void *stream, rsk_ctx **out);
 int rsk_ctx_destroy(rsk_ctx *ctx);
 int rsk_ctx_synchronize(rsk_ctx *ctx);
-/* CUDA-event stopwatch on the context stream (bench.py times the kernels with it). */
+/* Benchmark aid: with bytes > 0 every trace launch of the context is preceded, on the same stream, by a write of that
+ * many bytes of scratch memory (larger than the L2: the scene is then re-read from HBM in every iteration).  0 = off. */
+int rsk_ctx_set_l2_flush(rsk_ctx *ctx, int64_t bytes);
+/* CUDA-event stopwatch on the context stream (bench.py times the kernels with it); covers pipelined solves. */
 int rsk_ctx_timer_start(rsk_ctx *ctx);
 int rsk_ctx_timer_stop(rsk_ctx *ctx, float *elapsed_ms);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
@@ -190,6 +193,10 @@ int rsk_matrix_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em,
                      const uint8_t *surf_active, const int32_t *emit_sid, const int32_t *min_sid,
                      const float *cp_table, int32_t n_rot, const int32_t *rot_base, const int64_t *ray_range,
                      const rsk_solve_params *params, rsk_solve **out);
+/* Iterations are pipelined: iteration i is traced and folded on stream (i & 1) of the context with its own tally
+ * buffer, so the trace of iteration i + 1 occupies the SMs while iteration i drains and its statistics run (statistics
+ * are still folded strictly in iteration order).  A job that stops at iteration i may be traced once more before its
+ * stop decision is known; those tallies are discarded, so results do not depend on the overlap.  RSK_PIPELINE=0 disables. */
 int rsk_matrix_step(rsk_solve *solve, int32_t n_iters, int32_t *n_active);
 /* hits_front/hits_back: int64[n_local][n_surf]; iters: int32[n_local]; total_rays: int64[n_local];
  * stderr_front/back: float64[n_local][n_surf] replicate standard errors (may be NULL). */

@@ -38,7 +38,7 @@ EXPORTS = (
     "rsk_solve_allreduce_iter_tallies",
     "rsk_tally_block_create", "rsk_tally_block_add_solve", "rsk_tally_block_allreduce", "rsk_tally_block_device",
     "rsk_tally_block_download", "rsk_tally_block_destroy",
-    "rsk_solve_csr", "rsk_tally_block_csr", "rsk_csr_fetch",
+    "rsk_solve_csr", "rsk_tally_block_csr", "rsk_csr_fetch", "rsk_ctx_set_l2_flush",
 )
 COMM_ID_BYTES = 128
 
@@ -140,6 +140,10 @@ class Context:
 
     def synchronize(self) -> None:
         check(self.lib.rsk_ctx_synchronize(self.handle))
+
+    def set_l2_flush(self, n_bytes: int) -> None:
+        """Benchmark aid: write ``n_bytes`` of scratch (> L2) before every trace launch, on its stream; 0 = off."""
+        check(self.lib.rsk_ctx_set_l2_flush(self.handle, C.c_int64(n_bytes)), "rsk_ctx_set_l2_flush")
 
     def timer_start(self) -> None:
         check(self.lib.rsk_ctx_timer_start(self.handle))

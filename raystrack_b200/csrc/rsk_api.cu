@@ -90,6 +90,8 @@ extern "C" int rsk_ctx_destroy(rsk_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->stage) cudaFreeHost(ctx->stage);
+    if (ctx->l2_flush) cudaFree(ctx->l2_flush);
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_join); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -97,9 +99,39 @@ extern "C" int rsk_ctx_destroy(rsk_ctx *ctx) {
     return RSK_OK;
 }
 
+// Second stream of pipelined solves, and the event that orders `stream` after whatever was enqueued on it.
+int rsk_ctx_stream2(rsk_ctx *ctx, cudaStream_t *out) {
+    if (!ctx->stream2) {
+        RSK_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        RSK_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    *out = ctx->stream2;
+    return RSK_OK;
+}
+
+int rsk_ctx_join(rsk_ctx *ctx) {
+    if (!ctx->stream2) return RSK_OK;
+    RSK_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream2));
+    RSK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    return RSK_OK;
+}
+
 extern "C" int rsk_ctx_synchronize(rsk_ctx *ctx) {
     RSK_REQUIRE(ctx, "null context");
+    if (ctx->stream2) RSK_CUDA(cudaStreamSynchronize(ctx->stream2));
     RSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RSK_OK;
+}
+
+extern "C" int rsk_ctx_set_l2_flush(rsk_ctx *ctx, int64_t bytes) {
+    RSK_REQUIRE(ctx && bytes >= 0, "rsk_ctx_set_l2_flush: bad arguments");
+    RskScope scope(ctx);
+    RSK_TRY(rsk_ctx_synchronize(ctx));
+    if (ctx->l2_flush) { cudaFree(ctx->l2_flush); ctx->l2_flush = nullptr; ctx->l2_flush_bytes = 0; }
+    if (bytes > 0) {
+        RSK_CUDA(cudaMalloc(&ctx->l2_flush, (size_t)bytes));
+        ctx->l2_flush_bytes = (size_t)bytes;
+    }
     return RSK_OK;
 }
 
@@ -111,6 +143,7 @@ extern "C" int rsk_ctx_timer_start(rsk_ctx *ctx) {
 
 extern "C" int rsk_ctx_timer_stop(rsk_ctx *ctx, float *ms) {
     RSK_REQUIRE(ctx && ms, "rsk_ctx_timer_stop: bad arguments");
+    RSK_TRY(rsk_ctx_join(ctx));                    // the stopwatch covers the work of pipelined solves on the second stream
     RSK_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     RSK_CUDA(cudaEventSynchronize(ctx->ev1));
     RSK_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
@@ -404,11 +437,11 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
     a.sc = scene->view();
     a.ev = em->view();
     a.emit_ids = d_ids; a.tiles = d_tiles; a.n_local = 1; a.tile_rays = tile_rays; a.surf_mask = d_mask;
-    a.cp_table = d_cp; a.rot_base = d_zero; a.iters_done = d_zero; a.done = nullptr; a.tally = nullptr;
+    a.cp_table = d_cp; a.rot_base = d_zero; a.iters_done = d_zero; a.iter_index = -1; a.done = nullptr; a.tally = nullptr;
     a.n_hist = mode == MODE_MATRIX ? 2 * scene->n_surf : RSK_TREGENZA_BINS;
     a.ray_begin = d_range; a.ray_end = d_range + 1; a.dbg_base = first_ray; a.min_sid = d_msid;
     a.dbg_orig = d_orig; a.dbg_dirs = d_dirs; a.dbg_hit = d_hit; a.dbg_front = d_front;
-    T_TRY(rsk_launch_trace(ctx, a, mode, n_tiles));
+    T_TRY(rsk_launch_trace(ctx, a, mode, n_tiles, ctx->stream));
     if (orig) T_CUDA(cudaMemcpyAsync(orig, d_orig, (size_t)n_rays * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (dirs) T_CUDA(cudaMemcpyAsync(dirs, d_dirs, (size_t)n_rays * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (hit_sid) T_CUDA(cudaMemcpyAsync(hit_sid, d_hit, (size_t)n_rays * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -499,6 +532,20 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
 #undef S_TRY
 #undef S_CUDA
     s->last_active = (params->max_iters > 0) ? n_local : 0;
+    // Pipelined stepping (RSK_PIPELINE=0 turns it off): a second tally buffer for the odd iterations
+    {
+        static int want = -1;
+        if (want < 0) { const char *e = getenv("RSK_PIPELINE"); want = (e && atoi(e) == 0) ? 0 : 1; }
+        if (want && n_local > 0 && params->max_iters > 1) {
+            cudaStream_t s2;
+            bool ok = rsk_ctx_stream2(ctx, &s2) == RSK_OK && rsk_dev_alloc(&s->iter_tally2, nh) == RSK_OK;
+            ok = ok && cudaMemsetAsync(s->iter_tally2, 0, std::max(nh, (size_t)1) * 8, ctx->stream) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&s->ev_fold, cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+            if (!ok) { rsk_set_error("solve begin: pipeline buffers: %s", cudaGetErrorString(cudaGetLastError())); return fail(RSK_ERR_CUDA); }
+            s->pipelined = true;
+        }
+    }
     *out = s;
     return RSK_OK;
 }
@@ -506,30 +553,57 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
 // One iteration = phase A (fused raygen+trace+tally of every unconverged job) + phase B (fold the iteration
 // tallies into totals / Welford statistics, decide convergence per job).  The phases are separate entry points
 // so that a multi-GPU caller can all-reduce the iteration tallies of ray-split emitters in between.
+// Stream and tally buffer of the iteration that is being enqueued.  A dual solve keeps the pipeline state on its
+// matrix side (`primary`); both sides must be pipelined for the pair to be.
+static inline rsk_solve *rsk_pipe_owner(rsk_solve *s) { return s->primary ? s->primary : s; }
+static inline bool rsk_pipe_on(rsk_solve *s) {
+    rsk_solve *o = rsk_pipe_owner(s);
+    return o->pipelined && (!o->twin || o->twin->pipelined);
+}
+static inline cudaStream_t rsk_pipe_stream(rsk_solve *s) {
+    rsk_solve *o = rsk_pipe_owner(s);
+    return (rsk_pipe_on(s) && o->cur) ? s->ctx->stream2 : s->ctx->stream;
+}
+static inline unsigned long long *rsk_pipe_tally(rsk_solve *s) {
+    rsk_solve *o = rsk_pipe_owner(s);
+    return (rsk_pipe_on(s) && o->cur) ? s->iter_tally2 : s->iter_tally;
+}
+
+cudaStream_t rsk_solve_current_stream(rsk_solve *s) { return rsk_pipe_stream(s); }
+
 static int rsk_solve_enqueue_trace_impl(rsk_solve *s) {
     rsk_ctx *ctx = s->ctx;
     if (s->n_local == 0 || (s->p.max_iters <= 0 && !(s->twin && s->twin->p.max_iters > 0))) return RSK_OK;
+    if (rsk_pipe_on(s)) s->cur = s->enq_iters & 1;
     TraceArgs a;
     memset(&a, 0, sizeof(a));
     a.sc = s->scene->view();
     a.ev = s->em->view();
     a.emit_ids = s->emit_ids; a.tiles = s->tiles; a.n_local = s->n_local; a.tile_rays = s->tile_rays; a.surf_mask = s->mask;
     a.cp_table = s->cp_table; a.rot_base = s->rot_base; a.iters_done = s->iters_done; a.done = s->done;
-    a.tally = s->iter_tally; a.n_hist = s->n_hist; a.ray_begin = s->ray_begin; a.ray_end = s->ray_end; a.min_sid = s->min_sid;
+    // every running job of a solve is at the same iteration: the number of iterations enqueued so far.  A pipelined
+    // trace must not read it from the device (the previous iteration's statistics may still be in flight).
+    a.iter_index = rsk_pipe_on(s) ? s->enq_iters : -1;
+    a.tally = rsk_pipe_tally(s); a.n_hist = s->n_hist; a.ray_begin = s->ray_begin; a.ray_end = s->ray_end; a.min_sid = s->min_sid;
+    s->enq_iters++;
     if (s->twin) {
-        const rsk_solve *k = s->twin;
-        a.surf_mask2 = k->mask; a.iters_done2 = k->iters_done; a.done2 = k->done; a.tally2 = k->iter_tally; a.n_hist2 = k->n_hist;
-        return rsk_launch_trace(ctx, a, MODE_DUAL, s->n_tiles);
+        rsk_solve *k = s->twin;
+        a.surf_mask2 = k->mask; a.iters_done2 = k->iters_done; a.done2 = k->done; a.tally2 = rsk_pipe_tally(k); a.n_hist2 = k->n_hist;
+        return rsk_launch_trace(ctx, a, MODE_DUAL, s->n_tiles, rsk_pipe_stream(s));
     }
-    return rsk_launch_trace(ctx, a, s->mode, s->n_tiles);
+    return rsk_launch_trace(ctx, a, s->mode, s->n_tiles, rsk_pipe_stream(s));
 }
 
 static int rsk_solve_enqueue_fold_impl(rsk_solve *s) {
     rsk_ctx *ctx = s->ctx;
     if (s->n_local == 0 || s->p.max_iters <= 0) return RSK_OK;
+    const bool pipe = rsk_pipe_on(s);
+    cudaStream_t st = rsk_pipe_stream(s);
+    // statistics are folded in iteration order: wait for the previous iteration's fold (it ran on the other stream)
+    if (pipe && s->has_fold) RSK_CUDA(cudaStreamWaitEvent(st, s->ev_fold, 0));
     FoldArgs f;
     memset(&f, 0, sizeof(f));
-    f.iter_tally = s->iter_tally; f.total = s->total; f.mean = s->mean; f.m2 = s->m2; f.prev = s->prev;
+    f.iter_tally = rsk_pipe_tally(s); f.total = s->total; f.mean = s->mean; f.m2 = s->m2; f.prev = s->prev;
     f.surf_mask = s->mode == MODE_MATRIX ? s->mask : nullptr;
     f.n_rays_once = s->n_rays_once; f.iters_done = s->iters_done; f.total_rays = s->total_rays; f.done = s->done;
     f.not_converged = s->not_conv; f.n_local = s->n_local; f.n_hist = s->n_hist; f.n_surf = s->scene->n_surf;
@@ -544,9 +618,13 @@ static int rsk_solve_enqueue_fold_impl(rsk_solve *s) {
     d.ray_begin = s->ray_begin; d.ray_end = s->ray_end;
     d.n_local = s->n_local; d.max_iters = s->p.max_iters; d.min_iters = s->p.min_iters; d.interval = s->p.interval;
     d.tol_mode = s->p.tol_mode;
-    RSK_TRY(rsk_launch_fold(ctx, f));
-    RSK_CUDA(cudaMemsetAsync(s->n_active, 0, sizeof(int32_t), ctx->stream));
-    RSK_TRY(rsk_launch_decide(ctx, d));
+    RSK_TRY(rsk_launch_fold(ctx, f, st));
+    RSK_CUDA(cudaMemsetAsync(s->n_active, 0, sizeof(int32_t), st));
+    RSK_TRY(rsk_launch_decide(ctx, d, st));
+    if (pipe) {
+        RSK_CUDA(cudaEventRecord(s->ev_fold, st));
+        s->has_fold = true;
+    }
     return RSK_OK;
 }
 
@@ -556,6 +634,7 @@ static int rsk_solve_poll_impl(rsk_solve *s, int32_t *n_active) {
         if (n_active) *n_active = s->last_active;
         return RSK_OK;
     }
+    RSK_TRY(rsk_ctx_join(ctx));                    // order `stream` after the iterations enqueued on the second stream
     RSK_CUDA(cudaMemcpyAsync(s->h_pinned, s->n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     RSK_CUDA(cudaStreamSynchronize(ctx->stream));
     RSK_CUDA(cudaGetLastError());
@@ -604,13 +683,14 @@ extern "C" int rsk_solve_set_iter_tally_buffer(rsk_solve *s, void *device_ptr, i
     if (!s->external_tally) rsk_dev_free(s->iter_tally);
     s->iter_tally = (unsigned long long *)device_ptr;
     s->external_tally = true;
+    s->pipelined = false;            // one caller-owned buffer: iterations run strictly one after the other
     RSK_CUDA(cudaMemsetAsync(s->iter_tally, 0, (size_t)s->n_local * s->n_hist * 8, s->ctx->stream));
     return RSK_OK;
 }
 
 extern "C" int rsk_solve_device_iter_tallies(rsk_solve *s, void **device_ptr, int64_t *n_per_job) {
     RSK_REQUIRE(s && device_ptr && n_per_job, "rsk_solve_device_iter_tallies: bad arguments");
-    *device_ptr = s->iter_tally;
+    *device_ptr = rsk_pipe_tally(s);      // the buffer of the iteration enqueued last
     *n_per_job = s->n_hist;
     return RSK_OK;
 }
@@ -729,6 +809,7 @@ extern "C" int rsk_dual_begin_sliced(rsk_ctx *ctx, rsk_scene *scene, rsk_emitter
                              rot_base, ray_range, sky_params, &k);
     if (rc != RSK_OK) { rsk_solve_destroy(m); return rc; }
     m->twin = k;
+    k->primary = m;
     // an emitter without receivers never starts its matrix side (main.py:1285-1287): mark it done up front
     RskScope scope(ctx);
     std::vector<int32_t> done(std::max(n_local, 1), 0);
@@ -812,6 +893,9 @@ extern "C" int rsk_solve_destroy(rsk_solve *s) {
     if (!s) return RSK_OK;
     if (s->twin) { rsk_solve_destroy(s->twin); s->twin = nullptr; }
     RskScope scope(s->ctx);
+    rsk_ctx_join(s->ctx);             // frees are ordered on `stream`: after the iterations still running on the second one
+    rsk_dev_free(s->iter_tally2);
+    if (s->ev_fold) cudaEventDestroy(s->ev_fold);
     rsk_dev_free(s->emit_ids); rsk_dev_free(s->min_sid); rsk_dev_free(s->rot_base); rsk_dev_free(s->iters_done); rsk_dev_free(s->done); rsk_dev_free(s->not_conv);
     rsk_dev_free(s->have_prev); rsk_dev_free(s->tiles); rsk_dev_free(s->n_rays_once); rsk_dev_free(s->total_rays); rsk_dev_free(s->ray_begin); rsk_dev_free(s->ray_end); rsk_dev_free(s->mask);
     rsk_dev_free(s->cp_table); if (!s->external_tally) rsk_dev_free(s->iter_tally); rsk_dev_free(s->rays_traced); rsk_dev_free(s->total); rsk_dev_free(s->mean);

@@ -121,11 +121,11 @@ extern "C" int rsk_comm_info(rsk_ctx *ctx, int32_t *rank, int32_t *nranks, int32
     return RSK_OK;
 }
 
-static int rsk_allreduce_impl(rsk_ctx *ctx, void *device_ptr, int64_t n, int32_t op) {
+static int rsk_allreduce_impl(rsk_ctx *ctx, void *device_ptr, int64_t n, int32_t op, cudaStream_t stream = nullptr) {
     RSK_REQUIRE(op == 0 || op == 1, "all-reduce: op must be 0 (sum) or 1 (max)");
     if (n <= 0 || !ctx->comm || ctx->comm_size <= 1) return RSK_OK;
     RSK_NCCL(g_nccl.AllReduce(device_ptr, device_ptr, (size_t)n, NCCL_INT64, op == 0 ? NCCL_SUM : NCCL_MAX, (ncclComm_t)ctx->comm,
-                              ctx->stream));
+                              stream ? stream : ctx->stream));
     return RSK_OK;
 }
 
@@ -152,7 +152,11 @@ extern "C" int rsk_allreduce_host_i64(rsk_ctx *ctx, int64_t *values, int64_t n, 
 extern "C" int rsk_solve_allreduce_iter_tallies(rsk_solve *s, int32_t n_jobs) {
     RSK_REQUIRE(s && n_jobs >= 0 && n_jobs <= s->n_local, "rsk_solve_allreduce_iter_tallies: bad arguments");
     RskScope scope(s->ctx);
-    return rsk_allreduce_impl(s->ctx, s->iter_tally, (int64_t)n_jobs * s->n_hist, 0);
+    // a pipelined solve traced this iteration on one of two streams into one of two buffers: reduce there
+    void *buf = nullptr;
+    int64_t per_job = 0;
+    RSK_TRY(rsk_solve_device_iter_tallies(s, &buf, &per_job));
+    return rsk_allreduce_impl(s->ctx, buf, (int64_t)n_jobs * per_job, 0, rsk_solve_current_stream(s));
 }
 
 // ----------------------------------------------------------------------------- tally block

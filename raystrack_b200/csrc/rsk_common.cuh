@@ -127,6 +127,10 @@ struct rsk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t stream2 = nullptr;   // second stream of pipelined solves (odd iterations), created on first use
+    cudaEvent_t ev_join = nullptr;    // orders `stream` after the work enqueued on stream2
+    void *l2_flush = nullptr;         // bench.py: scratch written before every trace launch (rsk_ctx_set_l2_flush)
+    size_t l2_flush_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     int sm_count = 0;
@@ -211,6 +215,7 @@ struct TraceArgs {
     const float *cp_table;          // [n_rot][7]
     const int32_t *rot_base;        // [n_local]
     const int32_t *iters_done;      // [n_local] (device state)
+    int32_t iter_index;             // >= 0: the iteration every running job is at (pipelined solves), else read iters_done
     const int32_t *done;            // [n_local] (device state), may be null
     const int32_t *min_sid;         // [n_local] surfaces with a smaller id are ignored (reciprocity), may be null (= 0)
     unsigned long long *tally;      // [n_local][n_hist]
@@ -233,7 +238,9 @@ struct TraceArgs {
 enum { MODE_MATRIX = 0, MODE_SKY = 1, MODE_DUAL = 2 };
 
 // internal entry points shared between translation units
-int rsk_launch_trace(rsk_ctx *ctx, TraceArgs &a, int mode, int64_t n_tiles);
+int rsk_launch_trace(rsk_ctx *ctx, TraceArgs &a, int mode, int64_t n_tiles, cudaStream_t stream);
+int rsk_ctx_stream2(rsk_ctx *ctx, cudaStream_t *out);
+int rsk_ctx_join(rsk_ctx *ctx);
 // Tile size for a launch over `total_rays` rays: large tiles amortise the per-CTA prologue/flush (8192: +2 % on C5),
 // small tiles keep all SMs busy when a scene shoots few rays per iteration and shorten the tail of the launch.
 static inline int rsk_pick_tile_rays(int64_t total_rays, int sm_count) {

@@ -27,6 +27,15 @@ struct rsk_solve {
     bool stepped = false;
     bool external_tally = false;     // iter_tally belongs to the caller (rsk_solve_set_iter_tally_buffer)
     rsk_solve *twin = nullptr;       // dual solves: the sky side (this object is the matrix side)
+    rsk_solve *primary = nullptr;    // dual solves, sky side: the matrix side (owner of the pipeline state below)
+    // Pipelined stepping: iteration i is traced and folded on stream (i & 1) with its own tally buffer, so the trace
+    // of iteration i + 1 fills the SMs while iteration i drains and its statistics run (rsk_api.cu).
+    bool pipelined = false;
+    unsigned long long *iter_tally2 = nullptr;   // tallies of odd iterations
+    cudaEvent_t ev_fold = nullptr;   // recorded after every fold/decide of this solve
+    int32_t enq_iters = 0;           // iterations enqueued so far = the iteration index every running job is at
+    int32_t cur = 0;                 // stream / buffer of the iteration being enqueued (0 or 1)
+    bool has_fold = false;
 };
 
 // Device-resident int64 [n_rows][n_cols] block in which the ranks of a sharded solve assemble their results (rsk_comm.cu).
@@ -35,3 +44,6 @@ struct rsk_tally_block {
     int64_t n_rows = 0, n_cols = 0;
     long long *d = nullptr;
 };
+
+// stream on which the iteration enqueued last runs (rsk_api.cu)
+cudaStream_t rsk_solve_current_stream(rsk_solve *s);

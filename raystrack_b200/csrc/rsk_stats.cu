@@ -24,7 +24,11 @@ __global__ void rsk_fold_kernel(const FoldArgs a) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)a.n_local * a.n_hist) return;
     const int k = (int)(idx / a.n_hist), j = (int)(idx % a.n_hist);
-    if (a.done[k]) return;
+    if (a.done[k]) {
+        // a pipelined solve may have traced this job once more before its stop decision was known: drop those tallies
+        if (a.iter_tally[idx] != 0ull) a.iter_tally[idx] = 0ull;
+        return;
+    }
     const unsigned long long cnt = a.iter_tally[idx];
     const long long tot0 = a.total[idx];
     // A bin that has never been hit stays all-zero (x = 0, mean = M2 = 0, standard error 0, cumulative estimate 0) and
@@ -92,18 +96,18 @@ __global__ void rsk_decide_kernel(const DecideArgs a) {
     if (!stop) atomicAdd(a.n_active, 1);
 }
 
-int rsk_launch_fold(rsk_ctx *ctx, const FoldArgs &a) {
+int rsk_launch_fold(rsk_ctx *ctx, const FoldArgs &a, cudaStream_t stream) {
     const int64_t n = (int64_t)a.n_local * a.n_hist;
     if (n == 0) return RSK_OK;
-    rsk_fold_kernel<<<rsk_blocks(n, 256), 256, 0, ctx->stream>>>(a);
+    rsk_fold_kernel<<<rsk_blocks(n, 256), 256, 0, stream>>>(a);
     ctx->launches++;
     RSK_CUDA(cudaGetLastError());
     return RSK_OK;
 }
 
-int rsk_launch_decide(rsk_ctx *ctx, const DecideArgs &a) {
+int rsk_launch_decide(rsk_ctx *ctx, const DecideArgs &a, cudaStream_t stream) {
     if (a.n_local == 0) return RSK_OK;
-    rsk_decide_kernel<<<rsk_blocks(a.n_local, 128), 128, 0, ctx->stream>>>(a);
+    rsk_decide_kernel<<<rsk_blocks(a.n_local, 128), 128, 0, stream>>>(a);
     ctx->launches++;
     RSK_CUDA(cudaGetLastError());
     return RSK_OK;

@@ -33,5 +33,5 @@ struct DecideArgs {
     int32_t max_iters, min_iters, interval, tol_mode;
 };
 
-int rsk_launch_fold(rsk_ctx *ctx, const FoldArgs &a);
-int rsk_launch_decide(rsk_ctx *ctx, const DecideArgs &a);
+int rsk_launch_fold(rsk_ctx *ctx, const FoldArgs &a, cudaStream_t stream);
+int rsk_launch_decide(rsk_ctx *ctx, const DecideArgs &a, cudaStream_t stream);

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
     float cp[7];
     {
         // both sides of a dual job run the same iteration number while both are alive
-        const int it = (MODE == MODE_DUAL && !want_m) ? a.iters_done2[job] : a.iters_done[job];
+        const int it = a.iter_index >= 0 ? a.iter_index : ((MODE == MODE_DUAL && !want_m) ? a.iters_done2[job] : a.iters_done[job]);
         const float *row = a.cp_table + 7 * (int64_t)(a.rot_base[job] + it);
 #pragma unroll
         for (int i = 0; i < 7; ++i) cp[i] = __ldg(row + i);
@@ -379,26 +379,28 @@ static size_t rsk_trace_smem(const TraceArgs &a, bool bvh, bool dual) {
 }
 
 template <int MODE, bool BVH>
-static int rsk_launch_one(rsk_ctx *ctx, const TraceArgs &a, int64_t n_tiles) {
+static int rsk_launch_one(rsk_ctx *ctx, const TraceArgs &a, int64_t n_tiles, cudaStream_t stream) {
     const size_t smem = rsk_trace_smem(a, BVH, MODE == MODE_DUAL);
     if (smem > 48 * 1024)
         RSK_CUDA(cudaFuncSetAttribute(rsk_trace_kernel<MODE, BVH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rsk_trace_kernel<MODE, BVH><<<(unsigned)n_tiles, RSK_TILE_THREADS, smem, ctx->stream>>>(a);
+    rsk_trace_kernel<MODE, BVH><<<(unsigned)n_tiles, RSK_TILE_THREADS, smem, stream>>>(a);
     ctx->launches++;
     RSK_CUDA(cudaGetLastError());
     return RSK_OK;
 }
 
-int rsk_launch_trace(rsk_ctx *ctx, TraceArgs &a, int mode, int64_t n_tiles) {
+int rsk_launch_trace(rsk_ctx *ctx, TraceArgs &a, int mode, int64_t n_tiles, cudaStream_t stream) {
     if (n_tiles <= 0) return RSK_OK;
+    if (ctx->l2_flush)          // benchmark mode: evict the L2 before every iteration's trace (counted in the timed region)
+        RSK_CUDA(cudaMemsetAsync(ctx->l2_flush, (int)(ctx->launches & 0xff), ctx->l2_flush_bytes, stream));
     RSK_REQUIRE(n_tiles < ((int64_t)1 << 31), "too many ray tiles in one launch");
     // shared-memory histogram when it leaves room for >= 2 CTAs per SM, else warp-aggregated global atomics
     a.hist_in_smem = (((size_t)a.n_hist + (mode == MODE_DUAL ? a.n_hist2 : 0)) * 4 <= 96 * 1024) ? 1 : 0;
     const bool bvh = a.sc.use_bvh != 0;
     a.class_mod = rsk_pick_class_mod(a.tile_rays);
-    if (mode == MODE_DUAL) return bvh ? rsk_launch_one<MODE_DUAL, true>(ctx, a, n_tiles) : rsk_launch_one<MODE_DUAL, false>(ctx, a, n_tiles);
-    if (mode == MODE_MATRIX) return bvh ? rsk_launch_one<MODE_MATRIX, true>(ctx, a, n_tiles) : rsk_launch_one<MODE_MATRIX, false>(ctx, a, n_tiles);
-    return bvh ? rsk_launch_one<MODE_SKY, true>(ctx, a, n_tiles) : rsk_launch_one<MODE_SKY, false>(ctx, a, n_tiles);
+    if (mode == MODE_DUAL) return bvh ? rsk_launch_one<MODE_DUAL, true>(ctx, a, n_tiles, stream) : rsk_launch_one<MODE_DUAL, false>(ctx, a, n_tiles, stream);
+    if (mode == MODE_MATRIX) return bvh ? rsk_launch_one<MODE_MATRIX, true>(ctx, a, n_tiles, stream) : rsk_launch_one<MODE_MATRIX, false>(ctx, a, n_tiles, stream);
+    return bvh ? rsk_launch_one<MODE_SKY, true>(ctx, a, n_tiles, stream) : rsk_launch_one<MODE_SKY, false>(ctx, a, n_tiles, stream);
 }
 
 // Diagnostic work counters of the trace kernels since the last reset (all zero unless the library was built with

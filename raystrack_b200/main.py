@@ -279,12 +279,12 @@ def _exchange_kind(ctx, world: int) -> Optional[str]:
 
 
 def _plan_chunks(plan: List[Tuple[int, int, int, bool]], n_hist: int) -> List[List[Tuple[int, int, int, bool]]]:
-    """The device keeps ~40 bytes per (job, bin): iteration tally, total, Welford mean/M2 (+ previous estimate).  Jobs
+    """The device keeps ~48 bytes per (job, bin): two iteration tallies, total, Welford mean/M2 (+ previous estimate).  Jobs
     are solved in chunks that fit a memory budget (RSK_SOLVE_MEMORY_MB, default 16384); emitters are independent, so
     chunking cannot change any result.  Ray-split jobs (first in every rank's list, same order everywhere) stay
     together in the first chunk."""
     budget = max(1.0, float(os.environ.get("RSK_SOLVE_MEMORY_MB", "16384")) * (1 << 20))
-    max_jobs = max(1, int(budget // (40 * max(1, n_hist))))
+    max_jobs = max(1, int(budget // (48 * max(1, n_hist))))
     n_shared = sum(1 for j in plan if j[3])
     chunks: List[List[Tuple[int, int, int, bool]]] = []
     head = plan[:max(n_shared, min(len(plan), max_jobs))] if plan else []

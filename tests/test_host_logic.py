@@ -239,15 +239,15 @@ def test_prepared_solver_mesh_bounds_match_per_mesh_loop():
 
 
 def test_plan_chunks_respects_budget_and_keeps_shared_jobs_together(monkeypatch):
-    """_plan_chunks: every job in exactly one chunk, order preserved, at most budget/(40*bins) jobs per chunk -- except
+    """_plan_chunks: every job in exactly one chunk, order preserved, at most budget/(48*bins) jobs per chunk -- except
     that all ray-split (shared) jobs stay in the first chunk, because every rank must step them in lockstep."""
     plan = [(0, 0, 8192, True), (3, 0, 4096, True), (1, 0, 100, False), (2, 0, 100, False), (4, 0, 100, False), (5, 0, 100, False), (6, 0, 100, False)]
-    n_hist = 100                                                    # 4000 bytes of solve state per job
-    monkeypatch.setenv("RSK_SOLVE_MEMORY_MB", str(3 * 4000 / (1 << 20)))      # three jobs per chunk
+    n_hist = 100                                                    # 4800 bytes of solve state per job
+    monkeypatch.setenv("RSK_SOLVE_MEMORY_MB", str(3 * 4800 / (1 << 20)))      # three jobs per chunk
     chunks = M._plan_chunks(plan, n_hist)
     assert [j for c in chunks for j in c] == plan
     assert all(len(c) <= 3 for c in chunks) and len(chunks) == 3
-    monkeypatch.setenv("RSK_SOLVE_MEMORY_MB", str(1 * 4000 / (1 << 20)))      # one job per chunk, but two shared jobs
+    monkeypatch.setenv("RSK_SOLVE_MEMORY_MB", str(1 * 4800 / (1 << 20)))      # one job per chunk, but two shared jobs
     chunks = M._plan_chunks(plan, n_hist)
     assert chunks[0] == plan[:2] and all(len(c) == 1 for c in chunks[1:]) and [j for c in chunks for j in c] == plan
     monkeypatch.delenv("RSK_SOLVE_MEMORY_MB")
