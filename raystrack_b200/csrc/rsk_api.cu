@@ -489,7 +489,10 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
         rend[k] = ray_range ? ray_range[2 * k + 1] : once[k];
         if (rbeg[k] < 0 || rend[k] < rbeg[k] || rend[k] > once[k]) { rsk_set_error("solve begin: ray range out of bounds"); rc = RSK_ERR_INVALID; break; }
     }
-    if (rc == RSK_OK) rsk_build_tiles(rbeg.data(), rend.data(), n_local, ctx->sm_count, tiles, &s->tile_rays);
+    static int want_pipeline = -1;           // RSK_PIPELINE=0 turns pipelined stepping off
+    if (want_pipeline < 0) { const char *e = getenv("RSK_PIPELINE"); want_pipeline = (e && atoi(e) == 0) ? 0 : 1; }
+    const bool pipeline = want_pipeline && n_local > 0 && params->max_iters > 1;
+    if (rc == RSK_OK) rsk_build_tiles(rbeg.data(), rend.data(), n_local, ctx->sm_count, tiles, &s->tile_rays, pipeline);
     s->n_tiles = (int64_t)tiles.size();
     const size_t nh = (size_t)n_local * s->n_hist;
     auto fail = [&](int code) { rsk_solve_destroy(s); return code; };
@@ -534,9 +537,7 @@ static int rsk_solve_begin(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int
     s->last_active = (params->max_iters > 0) ? n_local : 0;
     // Pipelined stepping (RSK_PIPELINE=0 turns it off): a second tally buffer for the odd iterations
     {
-        static int want = -1;
-        if (want < 0) { const char *e = getenv("RSK_PIPELINE"); want = (e && atoi(e) == 0) ? 0 : 1; }
-        if (want && n_local > 0 && params->max_iters > 1) {
+        if (pipeline) {
             cudaStream_t s2;
             bool ok = rsk_ctx_stream2(ctx, &s2) == RSK_OK && rsk_dev_alloc(&s->iter_tally2, nh) == RSK_OK;
             ok = ok && cudaMemsetAsync(s->iter_tally2, 0, std::max(nh, (size_t)1) * 8, ctx->stream) == cudaSuccess;

@@ -243,7 +243,7 @@ int rsk_ctx_stream2(rsk_ctx *ctx, cudaStream_t *out);
 int rsk_ctx_join(rsk_ctx *ctx);
 // Tile size for a launch over `total_rays` rays: large tiles amortise the per-CTA prologue/flush (8192: +2 % on C5),
 // small tiles keep all SMs busy when a scene shoots few rays per iteration and shorten the tail of the launch.
-static inline int rsk_pick_tile_rays(int64_t total_rays, int sm_count) {
+static inline int rsk_pick_tile_rays(int64_t total_rays, int sm_count, bool pipelined = false) {
     static int forced = -1;                 // RSK_TILE_RAYS=<512..8192, power of two>: tuning override
     if (forced < 0) {
         const char *e = getenv("RSK_TILE_RAYS");
@@ -255,7 +255,8 @@ static inline int rsk_pick_tile_rays(int64_t total_rays, int sm_count) {
     int t = RSK_TILE_RAYS_MAX;
     // The last wave leaves the SMs idle for about half a tile's run time: the largest tile only pays with >= 8 waves
     // (a 1/8 shard of the bench scene: 4096-ray tiles +1.5 %), below that at least two full waves are kept.
-    if (t > 4096 && total_rays / t < 8 * wave) t = 4096;
+    // (a pipelined solve fills the last wave with the next iteration's tiles: two waves are enough there, 1/8 shard +0.7 %)
+    if (t > 4096 && total_rays / t < (pipelined ? 2 : 8) * wave) t = 4096;
     while (t > 512 && total_rays / t < 2 * wave) t >>= 1;
     return t;
 }
@@ -275,35 +276,48 @@ static inline int rsk_pick_class_mod(int tile_rays) {
     return 1;
 }
 // Cut the ray ranges [rbeg[k], rend[k]) of n_local jobs into the CTA tiles of one launch: regular tiles of
-// rsk_pick_tile_rays() rays in job order, followed by a tail of small tiles (taken from the ends of the last jobs, about
-// two waves of CTAs) -- the SMs then idle for half a SMALL tile at the end of the launch instead of half a regular one.
-// RSK_TAIL_TILE_RAYS overrides the small size (0 = no tail tiles).
+// rsk_pick_tile_rays() rays in job order, then a tail whose tiles shrink with the work that is left (guided
+// self-scheduling: each tail tile takes remaining / (2 x resident CTAs) rays, at least RSK_TAIL_TILE_RAYS) -- all CTA
+// slots then run dry within one SMALL tile's time of each other instead of idling for up to a regular tile's time
+// (1.4 ms at 8192 rays).  The tail is taken from the ends of the last jobs and amounts to about 1.5 waves of regular
+// tiles.  RSK_TAIL_TILE_RAYS overrides the smallest size (default 512; 0 = no tail).
+// A pipelined solve (rsk_api.cu) needs no tail: the next iteration's tiles take the slots that run dry.
 static inline void rsk_build_tiles(const int64_t *rbeg, const int64_t *rend, int n_local, int sm_count, std::vector<TileDesc> &out,
-                                   int *tile_rays_out) {
-    static int tail_size = -1;
-    if (tail_size < 0) {
+                                   int *tile_rays_out, bool pipelined = false) {
+    static int tail_min = -1;
+    if (tail_min < 0) {
         const char *e = getenv("RSK_TAIL_TILE_RAYS");
-        tail_size = e ? atoi(e) : 1024;
-        if (tail_size != 0 && (tail_size < 256 || tail_size > RSK_TILE_RAYS_MAX)) tail_size = 1024;
+        tail_min = e ? atoi(e) : 512;
+        if (tail_min != 0 && (tail_min < 256 || tail_min > RSK_TILE_RAYS_MAX)) tail_min = 512;
     }
     int64_t total = 0;
     for (int k = 0; k < n_local; ++k) total += rend[k] - rbeg[k];
-    const int T = rsk_pick_tile_rays(total, sm_count);
+    const int T = rsk_pick_tile_rays(total, sm_count, pipelined);
     if (tile_rays_out) *tile_rays_out = T;
     const int64_t wave = 4 * (int64_t)(sm_count > 0 ? sm_count : 148);
-    int64_t tail = (tail_size > 0 && tail_size < T) ? std::min<int64_t>(total / 4, 2 * wave * tail_size) : 0;
+    int64_t tail = (!pipelined && tail_min > 0 && tail_min < T) ? std::min<int64_t>(total / 2, 3 * wave * T / 2) : 0;
     std::vector<int64_t> take(n_local, 0);
-    for (int k = n_local - 1; k >= 0 && tail > 0; --k) {
-        take[k] = std::min<int64_t>(rend[k] - rbeg[k], tail);
-        tail -= take[k];
+    int64_t left = tail;
+    for (int k = n_local - 1; k >= 0 && left > 0; --k) {
+        take[k] = std::min<int64_t>(rend[k] - rbeg[k], left);
+        left -= take[k];
     }
     out.clear();
     for (int k = 0; k < n_local; ++k)
         for (int64_t b = rbeg[k]; b < rend[k] - take[k]; b += T)
             out.push_back(TileDesc{k, (int32_t)std::min<int64_t>(T, rend[k] - take[k] - b), b});
-    for (int k = 0; k < n_local; ++k)
-        for (int64_t b = rend[k] - take[k]; b < rend[k]; b += tail_size)
-            out.push_back(TileDesc{k, (int32_t)std::min<int64_t>(tail_size, rend[k] - b), b});
+    int64_t remaining = tail;
+    for (int k = 0; k < n_local; ++k) {
+        int64_t b = rend[k] - take[k];
+        while (b < rend[k]) {
+            int64_t sz = remaining / (2 * wave);
+            sz = std::max<int64_t>(tail_min, std::min<int64_t>(T, (sz / 256) * 256));
+            sz = std::min<int64_t>(sz, rend[k] - b);
+            out.push_back(TileDesc{k, (int32_t)sz, b});
+            b += sz;
+            remaining -= sz;
+        }
+    }
 }
 int rsk_qmc_ensure_halton(rsk_ctx *ctx, int64_t n);
 int rsk_qmc_ensure_grid(rsk_ctx *ctx, int g, int64_t *offset);
