@@ -10,6 +10,7 @@ reads "how many emitters are still running".
 from __future__ import annotations
 
 import functools
+import heapq
 from concurrent.futures import ThreadPoolExecutor
 import os
 import time
@@ -181,7 +182,8 @@ def plan_shards(todo: Sequence[int], n_rays_once: Sequence[int], world: int,
     total = float(sum(int(n_rays_once[i]) for i in todo))
     limit = total / (8.0 * world)
     shared = [int(i) for i in todo if allow_split and n_rays_once[i] > limit and n_rays_once[i] >= 2 * world * TILE_RAYS]
-    whole = [int(i) for i in todo if int(i) not in set(shared)]
+    shared_set = set(shared)
+    whole = [int(i) for i in todo if int(i) not in shared_set]
     loads = [0.0] * world
     for i in shared:
         n = int(n_rays_once[i])
@@ -191,9 +193,11 @@ def plan_shards(todo: Sequence[int], n_rays_once: Sequence[int], world: int,
             plans[r].append((i, cuts[r], cuts[r + 1], True))
             loads[r] += cuts[r + 1] - cuts[r]
     per_rank: List[List[int]] = [[] for _ in range(world)]
+    heap = [(loads[q], q) for q in range(world)]                 # least loaded rank first, ties to the lower rank
+    heapq.heapify(heap)
     for i in sorted(whole, key=lambda k: (-int(n_rays_once[k]), k)):
-        r = min(range(world), key=lambda q: (loads[q], q))
-        loads[r] += int(n_rays_once[i])
+        load, r = heapq.heappop(heap)
+        heapq.heappush(heap, (load + int(n_rays_once[i]), r))
         per_rank[r].append(i)
     for r in range(world):
         plans[r].extend((i, 0, int(n_rays_once[i]), False) for i in sorted(per_rank[r]))
@@ -476,6 +480,10 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
     vals_all = nz_vals.tolist()
     cols_all = nz_cols.tolist() if reciprocity else None
     keys_nz = np.asarray(keys, dtype=object)[nz_cols].tolist() if len(keys) else []
+    iters_l, totals_l = iters.tolist(), totals.tolist()                  # plain Python numbers for the log lines
+    share_l = (elapsed * work / work_sum).tolist()
+    has_recv = has_recv.tolist()
+    tail = f"(BVH={label}, device={schedule})"
     for i, (name_e, _, _) in enumerate(meshes):
         if not has_recv[i]:
             if _hook is None:
@@ -491,8 +499,7 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
                     result[meshes[j][0]][f"{name_e}_front"] = f * (areas[i] / areas[j])     # main.py:1926-1927
         result[name_e].update(row)
         if _hook is None:
-            _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {elapsed * work[i] / work_sum:0.3f}s  "
-                 f"(BVH={label}, device={schedule})")
+            _log(f"({i+1}/{n_surf}) [{name_e}] {iters_l[i]} iter, {totals_l[i]:,} rays -> {share_l[i]:0.3f}s  {tail}")
 
     LAST_TIMING["assemble"] = time.perf_counter() - t_asm
     if _hook is not None:

@@ -259,7 +259,8 @@ def flatten_meshes(meshes: List[Mesh]):
     np.cumsum([np.shape(F)[0] for _, _, F in meshes], out=to[1:])
     verts = np.concatenate([np.asarray(V, dtype=np.float32).reshape(-1, 3) for _, V, _ in meshes], axis=0)
     faces64 = np.concatenate([np.asarray(F).reshape(-1, 3) for _, _, F in meshes], axis=0)
-    if faces64.size and (faces64.max() > 0x7fffffff or faces64.min() < -0x80000000):
+    narrow = faces64.dtype == np.int32 or (faces64.dtype.kind in "iu" and faces64.dtype.itemsize < 4)     # cannot overflow
+    if not narrow and faces64.size and (faces64.max() > 0x7fffffff or faces64.min() < -0x80000000):
         raise IndexError("face index does not fit in int32")
     return np.ascontiguousarray(verts), vo, np.ascontiguousarray(faces64.astype(np.int32, copy=False)), to
 
