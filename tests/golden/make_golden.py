@@ -333,6 +333,11 @@ def solves_extra():
         MatrixParams(samples=32, rays=64, seed=8, bvh="builtin", device="cpu", max_iters=30, min_iters=5, tol=1e-3, reciprocity=False))
     add("X5_tilted_sky", view_factor_to_tregenza_sky, tilted,
         SkyParams(samples=32, rays=64, seed=8, bvh="off", device="cpu", max_iters=12, min_iters=4, tol=1e-3, discrete=False))
+    # BASELINE config #4 "at high ray count to convergence tolerance": the ex04 cube with 16 384 rays per iteration, run
+    # until the replicate standard error of every entry is <= 1e-4 (hundreds of iterations)
+    add("X3_cube_converged_1e-4", view_factor_matrix, cube,
+        MatrixParams(samples=64, rays=256, seed=42, bvh="auto", device="cpu", flip_faces=True, reciprocity=False, max_iters=4000,
+                     min_iters=10, tol=1e-4))
     (HERE / "solves_extra.json").write_text(json.dumps(out, indent=1, sort_keys=True))
 
 

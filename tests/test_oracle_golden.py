@@ -88,7 +88,8 @@ def test_tregenza_patch_ids_bit_exact(stage):
 @pytest.mark.parametrize("case", ["C1_readme_squares", "C2_canyon_ex01", "C2b_canyon_delta_norecip",
                                   "C3_canyon_sky_discrete", "C3b_canyon_sky_merged", "C4_cube_ex04",
                                   "U3_urban_matrix_recip", "U3_urban_sky",
-                                  "X2_canyon_sky_delta", "X3_cube_flip_bvh", "X4_urban_delta_recip", "X5_tilted_matrix", "X5_tilted_sky"])
+                                  "X2_canyon_sky_delta", "X3_cube_flip_bvh", "X4_urban_delta_recip", "X5_tilted_matrix", "X5_tilted_sky",
+                                  "X3_cube_converged_1e-4"])
 def test_whole_solve_matches_reference(solves, case):
     g = solves[case]
     S = O.OracleSolver(scene_for(case))
