@@ -5,6 +5,7 @@
 
 static thread_local char g_error[1024] = "";
 thread_local cudaStream_t rsk_tl_stream = nullptr;
+thread_local cudaMemPool_t rsk_tl_pool = nullptr;
 
 void rsk_set_error(const char *fmt, ...) {
     va_list ap;
@@ -68,12 +69,22 @@ extern "C" int rsk_ctx_create(int device, void *stream, rsk_ctx **out) {
         }
     }
     {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaError_t e = cudaMemPoolCreate(&ctx->pool, &props);
+        if (e == cudaSuccess) {
             unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            e = cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
-        cudaGetLastError();
+        if (e != cudaSuccess) {
+            rsk_set_error("rsk_ctx_create: memory pool: %s", cudaGetErrorString(e));
+            rsk_ctx_destroy(ctx);
+            return RSK_ERR_CUDA;
+        }
     }
     *out = ctx;
     return RSK_OK;
@@ -94,6 +105,7 @@ extern "C" int rsk_ctx_destroy(rsk_ctx *ctx) {
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_join); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RSK_OK;

@@ -127,6 +127,7 @@ struct rsk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaMemPool_t pool = nullptr;     // private stream-ordered memory pool (see rsk_dev_alloc)
     cudaStream_t stream2 = nullptr;   // second stream of pipelined solves (odd iterations), created on first use
     cudaEvent_t ev_join = nullptr;    // orders `stream` after the work enqueued on stream2
     void *l2_flush = nullptr;         // bench.py: scratch written before every trace launch (rsk_ctx_set_l2_flush)
@@ -324,16 +325,19 @@ int rsk_qmc_ensure_grid(rsk_ctx *ctx, int g, int64_t *offset);
 int rsk_bvh_build(rsk_scene *scene, const float4 *tri_in, const float4 *nrm_in);
 int rsk_scene_adopt(rsk_ctx *ctx, float4 *d_tri, float4 *d_nrm, int64_t n_tri, int32_t n_surf, int32_t use_bvh, rsk_scene **out);
 
-// Device memory comes from the device's default stream-ordered pool (cudaMallocAsync) with an unlimited release
-// threshold: repeated solves reuse the same blocks without ever calling cudaMalloc/cudaFree (both of which
-// synchronise the device and cost 0.1-0.7 s for the buffers of a million-triangle scene).  Allocation and release
-// are ordered on the stream of the context that is current on the calling thread (RskScope).
+// Device memory comes from a stream-ordered memory pool that belongs to the context (cudaMallocFromPoolAsync) with an
+// unlimited release threshold: repeated solves reuse the same blocks without ever calling cudaMalloc/cudaFree (both of
+// which synchronise the device and cost 0.1-0.7 s for the buffers of a million-triangle scene).  The pool is private:
+// the device's default pool, which other libraries in the process may use, keeps its settings.  Allocation and
+// release are ordered on the stream of the context that is current on the calling thread (RskScope).
 extern thread_local cudaStream_t rsk_tl_stream;
+extern thread_local cudaMemPool_t rsk_tl_pool;
 
 struct RskScope {
     explicit RskScope(const rsk_ctx *ctx) {
         cudaSetDevice(ctx->device);
         rsk_tl_stream = ctx->stream;
+        rsk_tl_pool = ctx->pool;
     }
 };
 
@@ -341,7 +345,8 @@ template <typename T>
 static inline int rsk_dev_alloc(T **ptr, size_t count) {
     *ptr = nullptr;
     if (count == 0) count = 1;
-    RSK_CUDA(cudaMallocAsync((void **)ptr, count * sizeof(T), rsk_tl_stream));
+    if (rsk_tl_pool) RSK_CUDA(cudaMallocFromPoolAsync((void **)ptr, count * sizeof(T), rsk_tl_pool, rsk_tl_stream));
+    else RSK_CUDA(cudaMallocAsync((void **)ptr, count * sizeof(T), rsk_tl_stream));
     return RSK_OK;
 }
 
