@@ -68,7 +68,15 @@ extern "C" int rsk_ctx_create(int device, void *stream, rsk_ctx **out) {
             return e == cudaErrorMemoryAllocation ? RSK_ERR_OOM : RSK_ERR_CUDA;
         }
     }
-    {
+    const char *pool_env = getenv("RSK_PRIVATE_POOL");      // 0: allocate from the device's default pool instead (A/B timing)
+    if (pool_env && atoi(pool_env) == 0) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    } else {
         cudaMemPoolProps props;
         memset(&props, 0, sizeof(props));
         props.allocType = cudaMemAllocationTypePinned;
