@@ -32,6 +32,12 @@ __device__ unsigned long long rsk_work_counters[8];
 #ifndef RSK_POSTPONE_IDLE
 #define RSK_POSTPONE_IDLE 4   // ... or once this many lanes have nothing else to do
 #endif
+#ifndef RSK_TRI_PAIRS
+#define RSK_TRI_PAIRS 2       // triangles a closest-hit walk fetches per trip of its triangle loop (0: one, loaded inside the test)
+#endif
+#ifndef RSK_TRI_PAIRS_SKY
+#define RSK_TRI_PAIRS_SKY 1   // the any-hit walk does the same in its immediate triangle loop
+#endif
 #ifndef RSK_REFILL_BELOW
 #define RSK_REFILL_BELOW 24   // leave the traversal loop to fetch new rays when fewer lanes are busy (24-27 measured best)
 #endif
@@ -188,6 +194,19 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
 
     // One triangle of a pending group against the current ray (Moeller-Trumbore, cpu_trace.py:88-114).  Returns true
     // when the ray is settled by it (sky-only walks stop at the first hit).
+    auto test_loaded = [&](int tri, const float4 &V0, const float4 &E1, const float4 &E2) -> bool {
+        const int sid = __float_as_int(V0.w);
+        if (!rsk_surface_on_s(mask_addr, sid)) { RSK_COUNT(2); return false; }
+        RSK_COUNT(1);
+        float t;
+        if (!rsk_tri_hit(V0, E1, E2, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, t) || !(t > 1e-6f)) return false;
+        if (want_s) {
+            any_hit = true;
+            if (!want_m) return true;
+        }
+        if (want_m && t < w.best && (MODE != MODE_DUAL || rsk_surface_on_s(recv_addr, sid))) { w.best = t; w.best_tri = tri; }
+        return false;
+    };
     auto test_triangle = [&](int tri) -> bool {
         const float4 *tp = a.sc.tri + 3 * (int64_t)tri;
         const float4 V0 = __ldg(tp), E1 = __ldg(tp + 1), E2 = __ldg(tp + 2);
@@ -292,11 +311,36 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
                 const unsigned idle = __ballot_sync(in_loop, !more);
                 if (__popc(pend) >= flush_at || full || __popc(idle) >= RSK_POSTPONE_IDLE || idle == in_loop) {
                     if (ptg.hits) RSK_COUNT(4);
+#if RSK_TRI_PAIRS
+                    // RSK_TRI_PAIRS (2) triangles per trip: all are fetched before any is tested, so a lane with several
+                    // pending triangles waits for memory once per trip instead of once per triangle (the loop is
+                    // latency-bound: a third of the kernel's stall samples at ~9 active lanes)
+                    while (ptg.hits) {
+                        int tri[RSK_TRI_PAIRS];
+                        float4 T0[RSK_TRI_PAIRS], T1[RSK_TRI_PAIRS], T2[RSK_TRI_PAIRS];
+                        bool have[RSK_TRI_PAIRS];
+#pragma unroll
+                        for (int u = 0; u < RSK_TRI_PAIRS; ++u) {
+                            have[u] = ptg.hits != 0u;
+                            const int b = have[u] ? __ffs(ptg.hits) - 1 : 0;
+                            ptg.hits &= ptg.hits - 1u;
+                            tri[u] = (int)(ptg.base + __popc(ptg.leaf_bits & ((1u << b) - 1u)));
+                            const float4 *tp = a.sc.tri + 3 * (int64_t)tri[u];
+                            T0[u] = __ldg(tp); T1[u] = __ldg(tp + 1); T2[u] = __ldg(tp + 2);
+                        }
+                        bool stop = false;
+#pragma unroll
+                        for (int u = 0; u < RSK_TRI_PAIRS; ++u)
+                            if (!stop && have[u] && test_loaded(tri[u], T0[u], T1[u], T2[u])) stop = true;
+                        if (stop) { ptg.hits = 0u; break; }
+                    }
+#else
                     while (ptg.hits) {
                         const int b = __ffs(ptg.hits) - 1;
                         ptg.hits &= ptg.hits - 1u;
                         if (test_triangle((int)(ptg.base + __popc(ptg.leaf_bits & ((1u << b) - 1u))))) { ptg.hits = 0u; break; }
                     }
+#endif
                     if (tg.hits) ptg = tg;
                 }
                 if ((any_hit && !want_m) || (w.ng.y <= 0x00ffffffu && w.sp == stack_base && !ptg.hits)) {
@@ -322,11 +366,27 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
                     TriGroup tg;
                     rsk_test_node(a.sc.nodes, node, w, RSK_INF, ng2, tg, mask_addr, job_min_sid);
                     w.ng = ng2;
+#if RSK_TRI_PAIRS_SKY
+                    while (tg.hits) {       // two triangles per trip, fetched together (see the closest-hit loop)
+                        const int b0 = __ffs(tg.hits) - 1;
+                        tg.hits &= tg.hits - 1u;
+                        const bool two = tg.hits != 0u;
+                        const int b1 = two ? __ffs(tg.hits) - 1 : b0;
+                        tg.hits &= tg.hits - 1u;
+                        const int tri0 = (int)(tg.base + __popc(tg.leaf_bits & ((1u << b0) - 1u)));
+                        const int tri1 = (int)(tg.base + __popc(tg.leaf_bits & ((1u << b1) - 1u)));
+                        const float4 *tp0 = a.sc.tri + 3 * (int64_t)tri0, *tp1 = a.sc.tri + 3 * (int64_t)tri1;
+                        const float4 A0 = __ldg(tp0), A1 = __ldg(tp0 + 1), A2 = __ldg(tp0 + 2);
+                        const float4 B0 = __ldg(tp1), B1 = __ldg(tp1 + 1), B2 = __ldg(tp1 + 2);
+                        if (test_loaded(tri0, A0, A1, A2) || (two && test_loaded(tri1, B0, B1, B2))) { finished = true; break; }
+                    }
+#else
                     while (tg.hits) {
                         const int b = __ffs(tg.hits) - 1;
                         tg.hits &= tg.hits - 1u;
                         if (test_triangle((int)(tg.base + __popc(tg.leaf_bits & ((1u << b) - 1u))))) { finished = true; break; }
                     }
+#endif
                 }
                 if (finished) {
                     key = rsk_result_key(a, w, want_m, want_s, any_hit, sky_base, n_sky);

@@ -13,18 +13,19 @@ sys.path.insert(0, str(ROOT))
 VARIANTS = {      # compile-time knobs of csrc/rsk_trace.cu(h) and csrc/rsk_bvh.cu; the product is built with the defaults
     "shipped": (),
     "counters": ("RSK_COUNTERS=1",),
+    "tri_single": ("RSK_TRI_PAIRS=0",),
+    "sky_single": ("RSK_TRI_PAIRS_SKY=0",),
+    "tri3": ("RSK_TRI_PAIRS=3",),
+    "tri4": ("RSK_TRI_PAIRS=4",),
     "stack4": ("RSK_SMEM_STACK_N=4",),
-    "stack6": ("RSK_SMEM_STACK_N=6",),
     "refill20": ("RSK_REFILL_BELOW=20",),
     "refill28": ("RSK_REFILL_BELOW=28",),
     "postpone6": ("RSK_POSTPONE=6",),
     "postpone16": ("RSK_POSTPONE=16",),
+    "postpone24": ("RSK_POSTPONE=24",),
     "idle2": ("RSK_POSTPONE_IDLE=2",),
     "idle8": ("RSK_POSTPONE_IDLE=8",),
-    "ctas5": ("RSK_MIN_CTAS_PER_SM=5",),
-    "prmt6": ("RSK_PRMT_AXES=6",),
-    "prmt0": ("RSK_PRMT_AXES=0",),
-    "prmt7": ("RSK_PRMT_AXES=7",),
+    "stack6": ("RSK_SMEM_STACK_N=6",),
 }
 OUT = ROOT / "raystrack_b200" / "_lib" / "variants"
 
