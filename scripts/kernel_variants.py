@@ -15,6 +15,9 @@ VARIANTS = {      # compile-time knobs of csrc/rsk_trace.cu(h) and csrc/rsk_bvh.
     "counters": ("RSK_COUNTERS=1",),
     "tri_single": ("RSK_TRI_PAIRS=0",),
     "sky_single": ("RSK_TRI_PAIRS_SKY=0",),
+    "ctas3": ("RSK_MIN_CTAS_PER_SM=3",),
+    "ctas3_tri3": ("RSK_MIN_CTAS_PER_SM=3", "RSK_TRI_PAIRS=3"),
+    "ctas3_tri4": ("RSK_MIN_CTAS_PER_SM=3", "RSK_TRI_PAIRS=4"),
     "tri3": ("RSK_TRI_PAIRS=3",),
     "tri4": ("RSK_TRI_PAIRS=4",),
     "stack4": ("RSK_SMEM_STACK_N=4",),
