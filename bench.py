@@ -205,13 +205,13 @@ def run_reference(args):
 L2_FLUSH_BYTES = 160 * 1024 * 1024      # > the 126 MB L2: written before every trace launch, on its stream, inside the timed region
 
 
-def _time_steps(ctx, fn, steps):
-    """CUDA-event time (ms per call) of ``steps`` back-to-back calls of ``fn`` on the context's streams; the L2 is
-    evicted before every trace launch (Context.set_l2_flush is on while bench.py measures)."""
+def _time_steps(ctx, solve, steps):
+    """CUDA-event time (ms per step) of ``steps`` iterations enqueued back to back (``solve.step(steps)``: pipelined
+    over the context's two streams, one host round trip at the end); the L2 is evicted before every trace launch
+    (Context.set_l2_flush is on while bench.py measures)."""
     ctx.synchronize()
     ctx.timer_start()
-    for _ in range(steps):
-        fn()
+    solve.step(steps)
     return ctx.timer_stop() / steps
 
 
@@ -302,7 +302,7 @@ def terrain_block(ctx, with_cpu: bool):
     solve = _native.Solve(ctx, sc.native, em.native, ids, active, M._rotation_table(seed, n, 64), ids.copy(), max_iters=64, min_iters=64,
                           interval=1, tol_mode="stderr", tol=0.0, emit_sid=ids, min_sid=np.zeros(n, np.int32))
     solve.step(2)
-    ms = _time_steps(ctx, lambda: solve.step(1), 3)
+    ms = _time_steps(ctx, solve, 10)
     solve.close()
     info = sc.info()
     out = {"workload": f"terrain + small objects: {n} meshes, {ps.total_faces} triangles, samples={samples} rays={rays} "
@@ -334,7 +334,7 @@ def terrain_block(ctx, with_cpu: bool):
 
 def secondary_block(ctx, sc, em, active, n_once, table, rays_per_step):
     """The other kernels of the path on the same scene and step definition (one iteration of every emitter), CUDA-event
-    timed over 3 back-to-back steps, L2 evicted before every trace: discrete-sky any-hit, dual (closest hit + any-hit flag from one walk), and the API-default
+    timed over 5 back-to-back steps, L2 evicted before every trace: discrete-sky any-hit, dual (closest hit + any-hit flag from one walk), and the API-default
     reciprocity=True schedule (emitter i ignores meshes j <= i; the last emitter has no receivers)."""
     from raystrack_b200 import _native
     n = active.shape[0]
@@ -345,7 +345,7 @@ def secondary_block(ctx, sc, em, active, n_once, table, rays_per_step):
 
     def run(name, solve, rays):
         solve.step(2)
-        ms = _time_steps(ctx, lambda: solve.step(1), 3)
+        ms = _time_steps(ctx, solve, 5)
         out[name] = {"value": rays / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms}
         solve.close()
 

@@ -17,6 +17,7 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--samples", type=int, default=4)
 ap.add_argument("--rays", type=int, default=64)
 ap.add_argument("--sky", action="store_true")
+ap.add_argument("--terrain", action="store_true", help="the terrain + small objects scene instead of the urban block")
 ap.add_argument("--ground-grid", type=int, default=32, help="quads per side of the ground mesh (32 = C5)")
 ap.add_argument("--face-grid", type=int, default=16, help="quads per side of every wall / roof (16 = C5)")
 ap.add_argument("--recip", action="store_true", help="reciprocity schedule: emitter i ignores meshes j <= i")
@@ -25,7 +26,7 @@ ap.add_argument("--rank", type=int, default=0)
 args = ap.parse_args()
 
 t = time.time()
-meshes = synthetic.urban_block(args.side, args.face_grid, args.ground_grid)
+meshes = synthetic.terrain_with_objects() if args.terrain else synthetic.urban_block(args.side, args.face_grid, args.ground_grid)
 ps = PreparedSolver(meshes)
 print(f"meshes {len(meshes)} tris {ps.total_faces} gen {time.time()-t:.2f}s", flush=True)
 t = time.time()
