@@ -404,7 +404,12 @@ def run_ours(args):
     rays_per_step = int(sum(n_once))
     total_iters = max(args.warmup, 3) + 2 * args.steps + 2
     table = M._rotation_table(args.seed, n, max(total_iters, 64))
-    plans = M.plan_shards(list(range(n)), n_once, world)
+    # the plan the public call would make: emitters weighted by rays x measured cost per ray (N > 1)
+    cost = None
+    if world > 1:
+        ids_all = np.arange(n, dtype=np.int32)
+        cost = M._emitter_cost_per_ray(ctx, sc, em, list(range(n)), n_once, active, table, ids_all, np.zeros(n, np.int32), rank, world)
+    plans = M.plan_shards(list(range(n)), n_once, world, cost_per_ray=cost)
     plan = plans[rank]
     ids = np.asarray([j[0] for j in plan], np.int32)
     ranges = np.asarray([[j[1], j[2]] for j in plan], np.int64).reshape(-1, 2)
@@ -513,7 +518,7 @@ def run_ours(args):
             "dtype": "f32 (f64 ray generation)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "step": "one Monte-Carlo iteration of all 2001 emitters", "rays_per_step": rays_per_step,
                        "bvh": f"GPU LBVH -> 8-wide quantised, {info['n_nodes']} nodes, depth {info['depth']}, built in {info['build_us']/1e3:.1f} ms",
-                       "l2": "evicted before every iteration: 160 MB scratch write on the trace stream, inside the timed region", "sharding": f"emitters over {world} GPU(s), {n_shared} ray-split",
+                       "l2": "evicted before every iteration: 160 MB scratch write on the trace stream, inside the timed region", "sharding": f"emitters over {world} GPU(s), {n_shared} ray-split" + ("" if cost is None else ", loads weighted by measured cost per ray"),
                        "collectives": None if comm is None else f"librsk_b200 rsk_comm (NCCL {comm['nccl_version']}, {comm['nranks']} ranks) on the kernel stream",
                        "upload_prepare_build_s": round(prep_s, 3), "upload_prepare_build_warm_s": round(prep_warm_s, 4)},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -165,6 +165,14 @@ int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, int32_t emi
                    int32_t mode, int64_t first_ray, int64_t n_rays,
                    float *orig, float *dirs, int32_t *hit_sid, uint8_t *hit_front);
 
+/* Relative cost per ray of a set of emitters (no reference counterpart; used to balance multi-GPU plans):
+ * one launch traces the first sample_rays rays of each emitter with the masks and skip rules of a matrix solve
+ * (surf_active / emit_sid / min_sid as in rsk_matrix_begin, cp = one rotation row) and every CTA adds the SM clock
+ * ticks it was resident to its emitter.  ticks: int64[n_local]; rays_out (may be NULL): the rays each entry covers. */
+int rsk_emitter_costs(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, const int32_t *emit_ids, int32_t n_local,
+                      const uint8_t *surf_active, const int32_t *emit_sid, const int32_t *min_sid, const float *cp,
+                      int64_t sample_rays, int64_t *ticks, int64_t *rays_out);
+
 /* ------------------------------------------------------------------------------------------- matrix solve
  * Replaces the emitter/iteration loops of view_factor_matrix (main.py:1757-1945): per iteration and emitter
  * build_rays -> trace -> reduce_first_hits -> Welford update -> convergence test, for a SET of emitters at once.

@@ -38,7 +38,7 @@ EXPORTS = (
     "rsk_solve_allreduce_iter_tallies",
     "rsk_tally_block_create", "rsk_tally_block_add_solve", "rsk_tally_block_allreduce", "rsk_tally_block_device",
     "rsk_tally_block_download", "rsk_tally_block_destroy",
-    "rsk_solve_csr", "rsk_tally_block_csr", "rsk_csr_fetch", "rsk_ctx_set_l2_flush",
+    "rsk_solve_csr", "rsk_tally_block_csr", "rsk_csr_fetch", "rsk_ctx_set_l2_flush", "rsk_emitter_costs",
 )
 COMM_ID_BYTES = 128
 
@@ -387,6 +387,21 @@ def trace_rays(ctx: Context, scene: DeviceScene, em: DeviceEmitters, emitter: in
                                  C.c_int32(min_sid), ptr(cpv), C.c_int32(mode), C.c_int64(first_ray), C.c_int64(n),
                                  ptr(orig), ptr(dirs), ptr(hit), ptr(front)), "rsk_trace_rays")
     return orig, dirs, hit, front
+
+
+def emitter_costs(ctx: Context, scene: "DeviceScene", em: "DeviceEmitters", emit_ids, surf_active, emit_sid, min_sid, cp,
+                  sample_rays: int = 2048):
+    """``rsk_emitter_costs``: (ticks int64 [n], rays int64 [n]) -- SM clock ticks spent on the first ``sample_rays`` rays of
+    every listed emitter (closest hit with the masks of a matrix solve)."""
+    ids = np.ascontiguousarray(emit_ids, np.int32)
+    n = int(ids.shape[0])
+    act = np.ascontiguousarray(surf_active, np.uint8).reshape(n, scene.n_surf)
+    es, ms = np.ascontiguousarray(emit_sid, np.int32), np.ascontiguousarray(min_sid, np.int32)
+    cpr = np.ascontiguousarray(cp, np.float32).reshape(7)
+    ticks, rays = np.zeros(n, np.int64), np.zeros(n, np.int64)
+    check(ctx.lib.rsk_emitter_costs(ctx.handle, scene.handle, em.handle, ptr(ids), C.c_int32(n), ptr(act), ptr(es), ptr(ms), ptr(cpr),
+                                    C.c_int64(sample_rays), ptr(ticks), ptr(rays)), "rsk_emitter_costs")
+    return ticks, rays
 
 
 class Solve:

@@ -474,6 +474,65 @@ extern "C" int rsk_trace_rays(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, 
     return RSK_OK;
 }
 
+// ----------------------------------------------------------------------------- cost of an emitter's rays
+
+// Relative cost per ray of a set of emitters: one launch traces the first `sample_rays` rays of each (closest hit, the
+// masks and skip rules of a matrix solve) and every CTA adds the SM clock ticks it was resident to its job.  Multi-GPU
+// plans weight emitters by rays x cost instead of rays alone.  ticks[k] covers rays_out[k] = min(sample_rays, rays of k).
+extern "C" int rsk_emitter_costs(rsk_ctx *ctx, rsk_scene *scene, rsk_emitters *em, const int32_t *emit_ids, int32_t n_local,
+                                 const uint8_t *surf_active, const int32_t *emit_sid, const int32_t *min_sid, const float *cp,
+                                 int64_t sample_rays, int64_t *ticks, int64_t *rays_out) {
+    RSK_REQUIRE(ctx && scene && em && ticks && cp && sample_rays > 0 && n_local >= 0, "rsk_emitter_costs: bad arguments");
+    RSK_REQUIRE(n_local == 0 || (emit_ids && surf_active && emit_sid && min_sid), "rsk_emitter_costs: null arrays");
+    if (n_local == 0) return RSK_OK;
+    RskScope scope(ctx);
+    const int nw = std::max((scene->n_surf + 31) / 32, 1);
+    std::vector<uint32_t> mask((size_t)n_local * nw);
+    std::vector<int64_t> rbeg(n_local, 0), rend(n_local);
+    std::vector<int32_t> zeros(n_local, 0);
+    for (int k = 0; k < n_local; ++k) {
+        RSK_REQUIRE(emit_ids[k] >= 0 && emit_ids[k] < em->n_emit, "rsk_emitter_costs: emitter id out of range");
+        rsk_pack_mask(surf_active + (size_t)k * scene->n_surf, scene->n_surf, emit_sid[k], min_sid[k], mask.data() + (size_t)k * nw);
+        rend[k] = std::min<int64_t>(sample_rays, em->h_desc[emit_ids[k]].n_rays_once);
+        if (rays_out) rays_out[k] = rend[k];
+    }
+    std::vector<TileDesc> tiles;
+    for (int k = 0; k < n_local; ++k)                     // one pass of equal tiles: every CTA sees the same neighbours
+        for (int64_t b = 0; b < rend[k]; b += 2048)
+            tiles.push_back(TileDesc{k, (int32_t)std::min<int64_t>(2048, rend[k] - b), b});
+    uint32_t *d_mask = nullptr; float *d_cp = nullptr; int32_t *d_ids = nullptr, *d_zero = nullptr, *d_msid = nullptr;
+    TileDesc *d_tiles = nullptr; int64_t *d_beg = nullptr, *d_end = nullptr; unsigned long long *d_ticks = nullptr;
+    auto cleanup = [&]() { rsk_dev_free(d_mask); rsk_dev_free(d_cp); rsk_dev_free(d_ids); rsk_dev_free(d_zero); rsk_dev_free(d_msid);
+                           rsk_dev_free(d_tiles); rsk_dev_free(d_beg); rsk_dev_free(d_end); rsk_dev_free(d_ticks); };
+    int rc = RSK_OK;
+#define E_TRY(expr) do { rc = (expr); if (rc != RSK_OK) { cleanup(); return rc; } } while (0)
+#define E_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rsk_set_error("%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); return RSK_ERR_CUDA; } } while (0)
+    E_TRY(rsk_upload(ctx, &d_mask, mask.data(), mask.size()));
+    E_TRY(rsk_upload(ctx, &d_cp, cp, 7));
+    E_TRY(rsk_upload(ctx, &d_ids, emit_ids, (size_t)n_local));
+    E_TRY(rsk_upload(ctx, &d_zero, zeros.data(), zeros.size()));
+    E_TRY(rsk_upload(ctx, &d_msid, min_sid, (size_t)n_local));
+    E_TRY(rsk_upload(ctx, &d_tiles, tiles.data(), tiles.size()));
+    E_TRY(rsk_upload(ctx, &d_beg, rbeg.data(), rbeg.size()));
+    E_TRY(rsk_upload(ctx, &d_end, rend.data(), rend.size()));
+    E_TRY(rsk_dev_alloc(&d_ticks, (size_t)n_local));
+    E_CUDA(cudaMemsetAsync(d_ticks, 0, (size_t)n_local * 8, ctx->stream));
+    TraceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sc = scene->view();
+    a.ev = em->view();
+    a.emit_ids = d_ids; a.tiles = d_tiles; a.n_local = n_local; a.tile_rays = 2048; a.surf_mask = d_mask;
+    a.cp_table = d_cp; a.rot_base = d_zero; a.iters_done = d_zero; a.iter_index = 0; a.done = nullptr; a.tally = nullptr;
+    a.n_hist = 2 * scene->n_surf; a.ray_begin = d_beg; a.ray_end = d_end; a.min_sid = d_msid; a.job_ticks = d_ticks;
+    E_TRY(rsk_launch_trace(ctx, a, MODE_MATRIX, (int64_t)tiles.size(), ctx->stream));
+    E_CUDA(cudaMemcpyAsync(ticks, d_ticks, (size_t)n_local * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    E_CUDA(cudaStreamSynchronize(ctx->stream));
+    cleanup();
+#undef E_TRY
+#undef E_CUDA
+    return RSK_OK;
+}
+
 // ----------------------------------------------------------------------------- solves
 
 

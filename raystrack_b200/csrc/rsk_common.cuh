@@ -230,6 +230,7 @@ struct TraceArgs {
     int32_t hist_in_smem;
     const int64_t *ray_begin;       // [n_local] first ray of each job's slice (null: 0)
     const int64_t *ray_end;         // [n_local] one past the last ray of each job's slice (null: n_rays_once)
+    unsigned long long *job_ticks;  // [n_local] optional: SM clock ticks the CTAs of each job were resident (rsk_emitter_costs)
     int64_t dbg_base;               // ray index stored at element 0 of the per-ray outputs
     float *dbg_orig, *dbg_dirs;     // optional per-ray outputs (test hook)
     int32_t *dbg_hit;

@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
 
     if (tid == 0) s_next = 0;
     const TileDesc td = a.tiles[blockIdx.x];
+    const long long t_begin = a.job_ticks ? clock64() : 0ll;
     __syncthreads();
     const int job = td.job;
     const bool side1_done = a.done && a.done[job];
@@ -417,6 +418,7 @@ __global__ void __launch_bounds__(RSK_TILE_THREADS, RSK_MIN_CTAS) rsk_trace_kern
         if (lane == 0 && v) atomicAdd(&rsk_work_counters[i], (unsigned long long)v);
     }
 #endif
+    if (a.job_ticks && tid == 0) atomicAdd(&a.job_ticks[job], (unsigned long long)(clock64() - t_begin));
     // ---- flush the CTA histogram: one global atomic per touched bin
     if (a.hist_in_smem) {
         __syncthreads();

@@ -12,6 +12,7 @@ serve the CPU tests (gloo, ``tests/test_dist_gloo.py``)."""
 from __future__ import annotations
 
 import os
+import sys
 import time
 from pathlib import Path
 from typing import Optional, Sequence
@@ -44,6 +45,8 @@ def init_from_env(backend: str | None = None) -> tuple[int, int]:
 
 
 def _torch_group() -> tuple[int, int]:
+    if "torch" not in sys.modules:          # a process group cannot exist unless the caller imported torch: do not pay for it
+        return 0, 1
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
@@ -55,11 +58,10 @@ def _torch_group() -> tuple[int, int]:
 
 def nccl_active() -> bool:
     """True when a torch.distributed NCCL group with more than one rank is running."""
-    try:
-        import torch.distributed as dist
-        return bool(dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl")
-    except Exception:
+    if _torch_group()[1] <= 1:
         return False
+    import torch.distributed as dist
+    return dist.get_backend() == "nccl"
 
 
 # --------------------------------------------------------------------------------------------- library communicator
@@ -171,8 +173,8 @@ def barrier() -> None:
     if _NATIVE is not None:
         _NATIVE["ctx"].allreduce_host(np.zeros(1, np.int64))
         return
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized():
+    if _torch_group()[1] > 1:
+        import torch.distributed as dist
         dist.barrier()
 
 
@@ -182,10 +184,10 @@ def max_over_ranks(value: float, device: int = 0) -> float:
         # the IEEE-754 bit pattern of a non-negative double is monotonic in its value: an int64 MAX does it
         bits = np.array([max(float(value), 0.0)], np.float64).view(np.int64).copy()
         return float(_NATIVE["ctx"].allreduce_host(bits, "max").view(np.float64)[0])
+    if _torch_group()[1] <= 1:
+        return float(value)
     import torch
     import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() <= 1:
-        return float(value)
     t = torch.tensor([float(value)], dtype=torch.float64)
     if dist.get_backend() == "nccl":
         t = t.cuda(device)
@@ -203,10 +205,10 @@ def allreduce_sum_(arrays: Sequence[np.ndarray], device: int = 0) -> None:
             flat[lo:lo + 4096] = _NATIVE["ctx"].allreduce_host(part)
         out = flat
     else:
+        if _torch_group()[1] <= 1:
+            return
         import torch
         import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() <= 1:
-            return
         flat = np.concatenate([np.ascontiguousarray(a, np.int64).reshape(-1) for a in arrays])
         t = torch.from_numpy(flat)
         if dist.get_backend() == "nccl":

@@ -164,21 +164,24 @@ def _rotation_rows(seed: int, rows: int) -> np.ndarray:
 TILE_RAYS = 4096               # ray slices of split emitters are cut on multiples of this (half the largest CTA tile)
 
 
-def plan_shards(todo: Sequence[int], n_rays_once: Sequence[int], world: int,
-                allow_split: bool = True) -> List[List[Tuple[int, int, int, bool]]]:
+def plan_shards(todo: Sequence[int], n_rays_once: Sequence[int], world: int, allow_split: bool = True,
+                cost_per_ray: Optional[Sequence[float]] = None) -> List[List[Tuple[int, int, int, bool]]]:
     """Partition the (emitter, ray range) work of one iteration over ``world`` GPUs.
 
     Returns, per rank, a list of jobs ``(emitter, ray_begin, ray_end, shared)``.  Emitters are independent units
-    (reference main.py:1758-1939) and are assigned whole, longest first, to the least loaded rank; an emitter that
+    (reference main.py:1758-1939) and are assigned whole, costliest first, to the least loaded rank; an emitter that
     alone exceeds an eighth of a rank's fair share is cut into ``world`` tile-aligned ray slices instead (``shared``):
     its per-iteration tallies are summed across ranks before the statistics update, so every rank takes the same
     convergence decision for it.  Shared jobs come first in every rank's list, in the same order.
-    ``allow_split=False`` assigns every emitter whole (no per-iteration exchange at all)."""
+    ``allow_split=False`` assigns every emitter whole (no per-iteration exchange at all).  ``cost_per_ray`` (indexed by
+    emitter, e.g. from ``_emitter_cost_per_ray``) weights the load of an emitter by rays x cost instead of rays alone;
+    every rank must pass the same values."""
     world = max(1, int(world))
     plans: List[List[Tuple[int, int, int, bool]]] = [[] for _ in range(world)]
     if world == 1:
         plans[0] = [(int(i), 0, int(n_rays_once[i]), False) for i in todo]
         return plans
+    cost = (lambda i: 1.0) if cost_per_ray is None else (lambda i: float(cost_per_ray[i]))
     total = float(sum(int(n_rays_once[i]) for i in todo))
     limit = total / (8.0 * world)
     shared = [int(i) for i in todo if allow_split and n_rays_once[i] > limit and n_rays_once[i] >= 2 * world * TILE_RAYS]
@@ -191,17 +194,46 @@ def plan_shards(todo: Sequence[int], n_rays_once: Sequence[int], world: int,
         cuts = [min(n, (tiles * r // world) * TILE_RAYS) for r in range(world)] + [n]
         for r in range(world):
             plans[r].append((i, cuts[r], cuts[r + 1], True))
-            loads[r] += cuts[r + 1] - cuts[r]
+            loads[r] += (cuts[r + 1] - cuts[r]) * cost(i)
     per_rank: List[List[int]] = [[] for _ in range(world)]
     heap = [(loads[q], q) for q in range(world)]                 # least loaded rank first, ties to the lower rank
     heapq.heapify(heap)
-    for i in sorted(whole, key=lambda k: (-int(n_rays_once[k]), k)):
+    for i in sorted(whole, key=lambda k: (-int(n_rays_once[k]) * cost(k), k)):
         load, r = heapq.heappop(heap)
-        heapq.heappush(heap, (load + int(n_rays_once[i]), r))
+        heapq.heappush(heap, (load + int(n_rays_once[i]) * cost(i), r))
         per_rank[r].append(i)
     for r in range(world):
         plans[r].extend((i, 0, int(n_rays_once[i]), False) for i in sorted(per_rank[r]))
     return plans
+
+
+COST_SAMPLE_RAYS = 2048        # rays per emitter of the cost measurement (a QMC prefix covers the emitter evenly)
+
+
+def _emitter_cost_per_ray(ctx, d_scene, d_em, todo, n_rays_once, active, table, emit_sid, min_sid, rank: int, world: int):
+    """Relative cost per ray of every emitter in ``todo`` (1.0 = the mean), for ``plan_shards``: rays are balanced to
+    1e-4 by construction, but a ray from a roof (mostly sky) costs less than one from a street-level wall, and the
+    spread between ranks at 8 GPUs is ~1.5 % of an iteration.  Every rank measures the emitters ``k % world == rank`` of
+    ``todo`` (``rsk_emitter_costs``: SM clock ticks of the first COST_SAMPLE_RAYS rays), the tick and ray counts are summed
+    over the ranks, so all ranks plan with identical numbers.  ~1 ms per call."""
+    from .dist import allreduce_sum_
+    n_emit = active.shape[0]
+    ticks = np.zeros(n_emit, np.int64)
+    rays = np.zeros(n_emit, np.int64)
+    mine = np.asarray([i for k, i in enumerate(todo) if k % world == rank], np.int32)
+    if mine.size:
+        t, r = _native.emitter_costs(ctx, d_scene.native, d_em.native, mine, active[mine], np.asarray(emit_sid)[mine],
+                                     np.asarray(min_sid)[mine], table[0], COST_SAMPLE_RAYS)
+        ticks[mine], rays[mine] = t, r
+    allreduce_sum_([ticks, rays])
+    cost = np.ones(n_emit, np.float64)
+    seen = rays > 0
+    if seen.any():
+        per_ray = ticks[seen] / rays[seen].astype(np.float64)
+        mean = float(np.sum(per_ray * np.asarray(n_rays_once, np.float64)[seen]) / max(1.0, float(np.asarray(n_rays_once, np.float64)[seen].sum())))
+        if mean > 0.0:
+            cost[seen] = np.clip(per_ray / mean, 0.25, 4.0)
+    return cost
 
 
 def _run_solve(solve: _native.Solve, min_iters: int, max_iters: int) -> None:
@@ -319,7 +351,11 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
     n_surf = active.shape[1]
     rank, world = _dist_env()
     exchange = _exchange_kind(ctx, world)
-    all_plans = plan_shards(todo, n_rays_once, world, allow_split=exchange is not None)
+    cost = None
+    if exchange == "native" and not sky and len(todo) >= 4 * world and os.environ.get("RSK_COST_PLAN", "1") != "0":
+        with _Phase("cost_plan"):
+            cost = _emitter_cost_per_ray(ctx, d_scene, d_em, todo, n_rays_once, active, table, emit_sid, min_sid, rank, world)
+    all_plans = plan_shards(todo, n_rays_once, world, allow_split=exchange is not None, cost_per_ray=cost)
     plan = all_plans[rank]
     any_shared = world > 1 and any(j[3] for shard in all_plans for j in shard)
     n_hist = (145 if discrete else 1) if sky else 2 * n_surf

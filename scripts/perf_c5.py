@@ -23,6 +23,7 @@ ap.add_argument("--face-grid", type=int, default=16, help="quads per side of eve
 ap.add_argument("--recip", action="store_true", help="reciprocity schedule: emitter i ignores meshes j <= i")
 ap.add_argument("--world", type=int, default=1, help="time the shard rank --rank of plan_shards(world) would get (no collectives)")
 ap.add_argument("--rank", type=int, default=0)
+ap.add_argument("--cost", action="store_true", help="weight the shard plan by the measured cost per ray (as the public call does)")
 args = ap.parse_args()
 
 t = time.time()
@@ -44,7 +45,17 @@ n = len(meshes)
 centers, extents = ps.get_mesh_bounds()
 active = _surface_masks(ems, centers, extents)
 from raystrack_b200.main import plan_shards                       # noqa: E402
-plan = plan_shards(list(range(n)), [int(e.n_cells * args.rays) for e in ems], args.world)[args.rank]
+n_once_all = [int(e.n_cells * args.rays) for e in ems]
+cost = None
+if args.cost:
+    from raystrack_b200.main import _emitter_cost_per_ray
+    class _W:                     # the device objects as PreparedSolver wraps them
+        def __init__(self, native): self.native = native
+    t = time.time()
+    cost = _emitter_cost_per_ray(ctx, _W(sc), _W(em), list(range(n)), n_once_all, active, _rotation_table(1, n, 4), np.arange(n, dtype=np.int32),
+                                 np.zeros(n, np.int32), 0, 1)
+    print(f"cost per ray: min {cost.min():.2f} max {cost.max():.2f} ({1e3 * (time.time() - t):.1f} ms)", flush=True)
+plan = plan_shards(list(range(n)), n_once_all, args.world, cost_per_ray=cost)[args.rank]
 ids = np.asarray([j[0] for j in plan], np.int32)
 ranges = np.asarray([[j[1], j[2]] for j in plan], np.int64)
 table = _rotation_table(1, n, args.iters + 2)

@@ -116,3 +116,22 @@ def test_allreduce_helpers_single_process():
     D.allreduce_sum_([a])                                          # no group: identity
     assert np.array_equal(a, np.arange(6).reshape(2, 3))
     assert D.max_over_ranks(3.5) == 3.5
+
+
+def test_nccl_id_file_rendezvous(tmp_path, monkeypatch):
+    """dist._exchange_id_file: rank 0 publishes the 128-byte id atomically, the other ranks wait for the complete file."""
+    import threading
+    from raystrack_b200 import _native, dist as D
+    uid = bytes(range(128))
+    monkeypatch.setattr(_native.Context, "comm_unique_id", staticmethod(lambda: uid))
+    path = tmp_path / "id.bin"
+    got = {}
+    t = threading.Thread(target=lambda: got.setdefault("r1", D._exchange_id_file(path, 1, 10.0)))
+    t.start()
+    assert D._exchange_id_file(path, 0, 10.0) == uid
+    t.join(15)
+    assert got["r1"] == uid and not path.with_suffix(".bin.tmp").exists()
+    import pytest
+    with pytest.raises(TimeoutError):
+        D._exchange_id_file(tmp_path / "never.bin", 1, 0.05)
+    assert D.native_comm_active() is False and D.native_comm_env() == (0, 1)

@@ -350,3 +350,38 @@ def test_zero_area_and_empty_emitters(rb):
     assert with_empty["A"] == rb.view_factor_matrix(sq, p)["A"]
     sky = rb.view_factor_to_tregenza_sky([sq[0], empty, sq[1]], rb.SkyParams(samples=16, rays=32, seed=3, bvh="off", max_iters=6, min_iters=6))
     assert sky["nothing"] == {"Sky": 0.0}
+
+
+def test_pipelined_and_sequential_stepping_agree(rb, tmp_path):
+    """Iterations are pipelined over two streams (a job may be traced once more before its stop decision is known; the
+    statistics kernel drops those tallies).  RSK_PIPELINE=0 (read once per process, hence a child process) steps strictly
+    one iteration after the other: results and iteration counts must be identical, for all three solve kinds."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    code = (
+        "import json, sys\n"
+        f"sys.path.insert(0, {str(root)!r})\n"
+        "import raystrack_b200 as rb\n"
+        "from raystrack_b200 import main as M, synthetic\n"
+        "logs = []\n"
+        "M._log = logs.append\n"
+        "meshes = synthetic.urban_block(3, 4, 8, 0)\n"
+        "p = rb.MatrixParams(samples=2, rays=16, seed=3, bvh='builtin', max_iters=40, min_iters=3, tol=2e-3, reciprocity=True)\n"
+        "sp = rb.SkyParams(samples=2, rays=16, seed=3, bvh='builtin', max_iters=25, min_iters=3, tol=1e-3, discrete=True)\n"
+        "out = {'m': rb.view_factor_matrix(meshes, p), 's': rb.view_factor_to_tregenza_sky(meshes, sp),\n"
+        "       'd': M.view_factor_matrix_and_sky(meshes, matrix_params=p, sky_params=sp), 'logs': [l.split('->')[0] for l in logs]}\n"
+        "print('RESULT' + json.dumps(out, sort_keys=True, default=float))\n")
+    outs = {}
+    for mode in ("1", "0"):
+        import os
+        env = dict(os.environ, RSK_PIPELINE=mode)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[mode] = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][-1]
+    assert outs["1"] == outs["0"]
+    logs = json.loads(outs["1"][6:])["logs"]
+    iters = {int(ln.split("]")[1].split("iter")[0]) for ln in logs if "iter" in ln and "traced" not in ln}
+    assert len(iters) > 3, iters          # emitters stop at different iterations: the stop path is exercised
