@@ -369,8 +369,8 @@ def test_pipelined_and_sequential_stepping_agree(rb, tmp_path):
         "logs = []\n"
         "M._log = logs.append\n"
         "meshes = synthetic.urban_block(3, 4, 8, 0)\n"
-        "p = rb.MatrixParams(samples=2, rays=16, seed=3, bvh='builtin', max_iters=40, min_iters=3, tol=2e-3, reciprocity=True)\n"
-        "sp = rb.SkyParams(samples=2, rays=16, seed=3, bvh='builtin', max_iters=25, min_iters=3, tol=1e-3, discrete=True)\n"
+        "p = rb.MatrixParams(samples=2, rays=16, seed=3, bvh='builtin', max_iters=80, min_iters=3, tol=4e-4, reciprocity=True)\n"
+        "sp = rb.SkyParams(samples=2, rays=16, seed=3, bvh='builtin', max_iters=60, min_iters=3, tol=3e-4, discrete=True)\n"
         "out = {'m': rb.view_factor_matrix(meshes, p), 's': rb.view_factor_to_tregenza_sky(meshes, sp),\n"
         "       'd': M.view_factor_matrix_and_sky(meshes, matrix_params=p, sky_params=sp), 'logs': [l.split('->')[0] for l in logs]}\n"
         "print('RESULT' + json.dumps(out, sort_keys=True, default=float))\n")
@@ -384,4 +384,4 @@ def test_pipelined_and_sequential_stepping_agree(rb, tmp_path):
     assert outs["1"] == outs["0"]
     logs = json.loads(outs["1"][6:])["logs"]
     iters = {int(ln.split("]")[1].split("iter")[0]) for ln in logs if "iter" in ln and "traced" not in ln}
-    assert len(iters) > 3, iters          # emitters stop at different iterations: the stop path is exercised
+    assert len(iters) >= 4 and max(iters) >= 8, iters          # emitters stop at different iterations: the stop path is exercised
