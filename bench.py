@@ -392,9 +392,17 @@ def run_ours(args):
     ps2.get_device_emitters(samples=args.samples, rays=args.rays, flip_faces=False, ctx=ctx)
     ps2.get_emitter_summaries(samples=args.samples, rays=args.rays, flip_faces=False, ctx=ctx)
     ctx.synchronize()
-    prep_warm_s = time.time() - t
     ps2.clear_device_cache()
     del ps2
+    t = time.time()                                             # ... and a third time, into the blocks the second pass freed
+    ps3 = PreparedSolver(meshes)
+    ps3.get_device_scene(use_bvh=True, ctx=ctx)
+    ps3.get_device_emitters(samples=args.samples, rays=args.rays, flip_faces=False, ctx=ctx)
+    ps3.get_emitter_summaries(samples=args.samples, rays=args.rays, flip_faces=False, ctx=ctx)
+    ctx.synchronize()
+    prep_warm_s = time.time() - t
+    ps3.clear_device_cache()
+    del ps3
     geometry_bytes = ps._geometry(ctx).h2d_bytes
     info = sc.info()
     n = len(meshes)
