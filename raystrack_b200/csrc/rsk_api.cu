@@ -789,6 +789,7 @@ extern "C" int rsk_matrix_step(rsk_solve *s, int32_t n_iters, int32_t *n_active)
 }
 
 static int rsk_read_common(rsk_solve *s, int32_t *iters, int64_t *total_rays) {
+    RSK_TRY(rsk_ctx_join(s->ctx));         // reads are ordered after the iterations of a pipelined solve on the second stream
     if (iters && s->n_local) RSK_CUDA(cudaMemcpyAsync(iters, s->iters_done, s->n_local * sizeof(int32_t), cudaMemcpyDeviceToHost, s->ctx->stream));
     if (total_rays && s->n_local) RSK_CUDA(cudaMemcpyAsync(total_rays, s->total_rays, s->n_local * sizeof(int64_t), cudaMemcpyDeviceToHost, s->ctx->stream));
     return RSK_OK;
@@ -962,6 +963,7 @@ extern "C" int rsk_sky_read(rsk_solve *s, int64_t *counts, int32_t *iters, int64
 extern "C" int rsk_solve_rays_traced(rsk_solve *s, int64_t *rays) {
     RSK_REQUIRE(s && rays, "rsk_solve_rays_traced: bad arguments");
     RskScope scope(s->ctx);
+    RSK_TRY(rsk_ctx_join(s->ctx));
     unsigned long long v = 0;
     RSK_CUDA(cudaMemcpyAsync(&v, s->rays_traced, 8, cudaMemcpyDeviceToHost, s->ctx->stream));
     RSK_CUDA(cudaStreamSynchronize(s->ctx->stream));

@@ -200,6 +200,7 @@ extern "C" int rsk_tally_block_add_solve(rsk_tally_block *b, rsk_solve *s, const
     if (s->n_local == 0) return RSK_OK;
     rsk_ctx *ctx = b->ctx;
     RskScope scope(ctx);
+    RSK_TRY(rsk_ctx_join(ctx));
     // destination rows = the solve's emitter ids (already on the device); jobs not kept get row -1
     std::vector<int32_t> rows(s->n_local);
     RSK_CUDA(cudaMemcpyAsync(rows.data(), s->emit_ids, s->n_local * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));

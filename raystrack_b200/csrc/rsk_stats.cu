@@ -321,6 +321,7 @@ static int rsk_csr_build_impl(rsk_ctx *ctx, const long long *block, int64_t n_ro
 extern "C" int rsk_solve_csr(rsk_solve *s, int64_t *row_ptr) {
     RSK_REQUIRE(s && row_ptr, "rsk_solve_csr: null argument");
     RskScope scope(s->ctx);
+    RSK_TRY(rsk_ctx_join(s->ctx));
     return rsk_csr_build_impl(s->ctx, s->total, s->n_local, s->n_hist, (const long long *)s->total_rays, nullptr, row_ptr);
 }
 
