@@ -132,9 +132,12 @@ def _cached_masks(solver: PreparedSolver, emitters, centers, extents, flip_faces
     if got is None:
         if ctx is not None and len(emitters) and centers.shape[0]:
             ne = len(emitters)
-            got = ctx.surface_masks(np.fromiter((em.plane_is_planar for em in emitters), bool, ne),
-                                    np.stack([em.plane_origin for em in emitters]), np.stack([em.plane_normal for em in emitters]),
-                                    np.fromiter((em.plane_tol for em in emitters), np.float64, ne).astype(np.float32), centers, extents)
+            soa = getattr(emitters, "soa", None)           # summaries that came from the device already hold the arrays
+            if soa is None:
+                soa = (np.fromiter((em.plane_is_planar for em in emitters), bool, ne), np.stack([em.plane_origin for em in emitters]),
+                       np.stack([em.plane_normal for em in emitters]),
+                       np.fromiter((em.plane_tol for em in emitters), np.float64, ne).astype(np.float32))
+            got = ctx.surface_masks(*soa, centers, extents)
         else:
             got = _surface_masks(emitters, centers, extents)
         got.setflags(write=False)

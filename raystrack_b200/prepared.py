@@ -247,6 +247,11 @@ class EmitterSummary:
         return int(self.g) * int(self.g)
 
 
+class SummaryList(list):
+    """List of EmitterSummary that also carries the plane records as arrays: ``soa`` = (planar, origin, normal, tol)."""
+    soa = None
+
+
 def flatten_meshes(meshes: List[Mesh]):
     """All meshes back to back: (verts float32[nv,3], vert_offset int64[n+1], faces int32[nt,3], tri_offset int64[n+1])
     -- the input of the device-side preparation (csrc/rsk_prepare.cu)."""
@@ -306,14 +311,13 @@ def summaries_from_device(summary: np.ndarray, g: np.ndarray, meshes: List[Mesh]
     band = 1.0e-6 * summary["worst_mag"]
     no = (summary["min_dot"] < lo - 2.0e-6) | (summary["worst"] - band > tol)
     yes = ~no & (summary["min_dot"] >= lo + 2.0e-6) & (summary["worst"] + band <= tol)
-    out: List[EmitterSummary] = []
-    for i in range(n):
-        planar = False
-        if unit[i]:
-            planar = bool(yes[i])
-            if not yes[i] and not no[i]:          # within rounding distance of a threshold: the reference arithmetic decides
-                planar = prepare_emitters([meshes[i]], samples=samples, rays=rays, flip_faces=flip_faces)[0].plane_is_planar
-        out.append(EmitterSummary(origin[i], normal[i], float(tol[i]), bool(planar), float(summary["total_area"][i]), int(g[i]), int(rays)))
+    planar = (unit & yes).tolist()
+    for i in np.nonzero(unit & ~yes & ~no)[0].tolist():      # within rounding distance of a threshold: the reference arithmetic decides
+        planar[i] = bool(prepare_emitters([meshes[i]], samples=samples, rays=rays, flip_faces=flip_faces)[0].plane_is_planar)
+    rays = int(rays)
+    out = SummaryList(EmitterSummary(o, nv, t, p, a, gi, rays)
+                      for o, nv, t, p, a, gi in zip(origin, normal, tol.tolist(), planar, summary["total_area"].tolist(), np.asarray(g).tolist()))
+    out.soa = (np.asarray(planar, bool), origin, normal, tol.astype(np.float32))      # the same fields as arrays (surface masks)
     return out
 
 
