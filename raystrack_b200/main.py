@@ -358,12 +358,12 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
     if exchange == "native" and not sky and len(todo) >= 4 * world and os.environ.get("RSK_COST_PLAN", "1") != "0":
         with _Phase("cost_plan"):
             cost = _emitter_cost_per_ray(ctx, d_scene, d_em, todo, n_rays_once, active, table, emit_sid, min_sid, rank, world)
-    all_plans = plan_shards(todo, n_rays_once, world, allow_split=exchange is not None, cost_per_ray=cost)
-    plan = all_plans[rank]
-    any_shared = world > 1 and any(j[3] for shard in all_plans for j in shard)
-    n_hist = (145 if discrete else 1) if sky else 2 * n_surf
-
-    chunks = _plan_chunks(plan, n_hist)
+    with _Phase("plan"):
+        all_plans = plan_shards(todo, n_rays_once, world, allow_split=exchange is not None, cost_per_ray=cost)
+        plan = all_plans[rank]
+        any_shared = world > 1 and any(j[3] for shard in all_plans for j in shard)
+        n_hist = (145 if discrete else 1) if sky else 2 * n_surf
+        chunks = _plan_chunks(plan, n_hist)
 
     single = world == 1 and len(chunks) == 1 and len(plan) == n_emit          # every emitter, in order: no scatter needed
     # one GPU, one solve, emitters in ascending order (some may be missing: emitters without receivers are never
@@ -436,7 +436,8 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
                 else:
                     allreduce_sum_([tallies, iters, totals], device=getattr(ctx, "device", 0))
         if block is not None:
-            tallies = block.read_csr(totals) if want_csr else block.download()
+            with _Phase("rows"):
+                tallies = block.read_csr(totals) if want_csr else block.download()
     finally:
         if block is not None:
             block.close()
@@ -455,6 +456,7 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
     tallies all-reduced, every rank returns the full result."""
     if not isinstance(params, MatrixParams):
         raise TypeError("params must be a MatrixParams instance")
+    t_call = time.perf_counter()
     p = params.as_dict()
     samples, rays, seed = p["samples"], p["rays"], p["seed"]
     max_iters, tol, tol_mode, min_iters = p["max_iters"], p["tol"], p["tol_mode"], p["min_iters"]
@@ -482,6 +484,7 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
     t0 = time.time()
     with _Phase("masks"):
         active = _cached_masks(solver, emitters, centers, extents, flip_faces, ctx)
+    t_recv = time.perf_counter()
     # receivers of emitter i (main.py:161-164, 207-214): active meshes j > i (reciprocity) or j != i
     emit_sid = np.arange(n_surf, dtype=np.int32)
     min_sid = (emit_sid + 1) if reciprocity else np.zeros(n_surf, np.int32)
@@ -496,6 +499,7 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
 
     weights = [float(em.n_cells * rays) for em in emitters]
     n_once = [int(em.n_cells * rays) for em in emitters]
+    LAST_TIMING["receivers"] = time.perf_counter() - t_recv
     if _hook is not None and "precomputed" in _hook:
         tallies, iters, totals = _hook["precomputed"]            # shared-ray solve already ran (view_factor_matrix_and_sky)
     else:
@@ -541,6 +545,7 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
             _log(f"({i+1}/{n_surf}) [{name_e}] {iters_l[i]} iter, {totals_l[i]:,} rays -> {share_l[i]:0.3f}s  {tail}")
 
     LAST_TIMING["assemble"] = time.perf_counter() - t_asm
+    LAST_TIMING["other"] = (time.perf_counter() - t_call) - sum(LAST_TIMING.values())      # everything no phase above covers
     if _hook is not None:
         _hook.update(iters=iters, totals=totals, n_once=n_once, label=label, elapsed=elapsed, device=schedule)
         return result
