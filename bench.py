@@ -73,41 +73,93 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    NVML in-process (nvidia_ml_py): the first sample is taken the moment the region starts and then every 5 ms, so even
+    the 40 ms region of the 8-GPU run is covered; `nvidia-smi -lms` (the recipe's command) is the fall-back -- it needs
+    ~1 s to print its first row, which is why it saw nothing at N=8 in the first round-2 lines."""
+
+    REASONS = (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"))
 
     def __init__(self, device: int):
         self.device = device
-        self.rows = []
-        self.proc = None
+        self.sm, self.mx, self.reasons = [], 0, set()
+        self.proc = self.nv = self.handle = self.thread = None
+        self.running = False
+        self.source = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(device).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.mx = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.source = "nvml"
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        nv = self.nv
+        if nv is None:
+            return
+        try:
+            self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+            bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            for name, const in self.REASONS:
+                if bits & getattr(nv, const):
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _loop(self):
+        while self.running:
+            self.sample()
+            time.sleep(0.005)
 
     def start(self):
+        if self.nv is not None:
+            self.running = True
+            self.sample()
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 100"
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+            r = [c.strip() for c in line.split(",")]
             try:
-                sm.append(int(r[0]))
-                mx = max(mx, int(r[1]))
+                self.sm.append(int(r[0]))
+                self.mx = max(self.mx, int(r[1]))
             except Exception:
                 continue
-            for name, col in (("hw_slowdown", 2), ("hw_thermal_slowdown", 3), ("sw_thermal_slowdown", 4), ("sw_power_cap", 5)):
+            for col, (name, _) in enumerate(self.REASONS, start=2):
                 if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(name)
+
+    def stop(self):
+        if self.thread is not None:
+            self.sample()
+            self.running = False
+            self.thread.join(timeout=1.0)
+        if self.proc:
+            self.proc.terminate()
+        sm = self.sm
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": self.mx or None, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": self.source}
 
 
 def build_scene(side: int):
