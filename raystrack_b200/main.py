@@ -446,6 +446,30 @@ def _solve_sharded(ctx, d_scene, d_em, todo, n_rays_once, active, table, *, max_
     return tallies, iters, totals
 
 
+OVERLAP_MIN_EMITTERS = 256            # a solve is cut in two only with at least this many emitters to solve ...
+OVERLAP_MIN_RAYS = 1.0e9              # ... and this many rays certain to be traced (rays per iteration x min_iters)
+OVERLAP_TAIL_FRACTION = 0.15          # share of the rays left for the second part
+
+
+def _overlap_split(todo: Sequence[int], n_rays_once: Sequence[int], iters_floor: int) -> int:
+    """Where to cut a large matrix solve in two so that the result rows of the first part are assembled (600 k Python
+    floats at C5: ~23 ms, a fixed cost that does not shrink with the GPU count) while the GPUs trace the second part.
+    Returns k: ``todo[:k]`` is solved first, ``todo[k:]`` second; 0 = solve in one piece.  The cut keeps emitter order
+    (rows and reciprocity fill-ins are then written in the reference's order, main.py:1918-1934) and leaves the second
+    part the shortest suffix holding OVERLAP_TAIL_FRACTION of the rays -- enough GPU time to hide the first part's rows,
+    few rows of its own.  Depends only on values every rank holds, so all ranks cut at the same place."""
+    if os.environ.get("RSK_OVERLAP_ASSEMBLY", "1") == "0" or len(todo) < max(2, OVERLAP_MIN_EMITTERS):
+        return 0
+    rays = np.asarray([int(n_rays_once[i]) for i in todo], np.float64)
+    total = float(rays.sum())
+    if total * max(1, int(iters_floor)) < OVERLAP_MIN_RAYS:
+        return 0
+    suffix = np.cumsum(rays[::-1])[::-1]                   # rays of todo[k:]
+    ks = np.nonzero(suffix >= OVERLAP_TAIL_FRACTION * total)[0]
+    k = int(ks[-1]) if ks.size else 0
+    return k if 2 * k >= len(todo) else 0                  # the hidden part must be the larger one in rows
+
+
 def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Optional[PreparedSolver] = None,
                        _hook: Optional[dict] = None):
     """View factors between all meshes (reference main.py:1689-1945).
@@ -500,49 +524,93 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
     weights = [float(em.n_cells * rays) for em in emitters]
     n_once = [int(em.n_cells * rays) for em in emitters]
     LAST_TIMING["receivers"] = time.perf_counter() - t_recv
-    if _hook is not None and "precomputed" in _hook:
-        tallies, iters, totals = _hook["precomputed"]            # shared-ray solve already ran (view_factor_matrix_and_sky)
-    else:
-        with _Phase("rotations"):
-            table = _rotation_table(seed, n_surf, max_iters)
-        tallies, iters, totals = _solve_sharded(ctx, d_scene, d_em, todo, n_once, active, table, max_iters=max_iters,
-                                                min_iters=min_iters, interval=interval if schedule == "gpu" else 1,
-                                                tol_mode=tol_mode, tol=tol, emit_sid=emit_sid, min_sid=min_sid, want_csr=True)
-    elapsed = time.time() - t0
-    t_asm = time.perf_counter()
-
     # result rows (main.py:1918-1934).  The tally block is [emitter][receiver][front, back], i.e. already in the
     # reference's key order "<r0>_front, <r0>_back, <r1>_front, ..."; only non-zero bins become keys.
     label = "builtin" if use_bvh else "off"
     keys = [f"{name}{suffix}" for name, _, _ in meshes for suffix in ("_front", "_back")]
-    work = np.asarray(weights) * np.maximum(iters, 1)
-    work_sum = max(1.0, float(work.sum()))
-    # non-zero bins per emitter: column indices (row-major, i.e. keys in order) and F = hits / total rays (main.py:1922-1923)
-    row_ptr, nz_cols, nz_vals = tallies if isinstance(tallies, tuple) else _csr_from_dense(tallies, totals)
-    bounds = row_ptr.tolist()
-    vals_all = nz_vals.tolist()
-    cols_all = nz_cols.tolist() if reciprocity else None
-    keys_nz = np.asarray(keys, dtype=object)[nz_cols].tolist() if len(keys) else []
-    iters_l, totals_l = iters.tolist(), totals.tolist()                  # plain Python numbers for the log lines
-    share_l = (elapsed * work / work_sum).tolist()
-    has_recv = has_recv.tolist()
+    keys_obj = np.asarray(keys, dtype=object) if keys else None
+    has_recv_l = has_recv.tolist()
     tail = f"(BVH={label}, device={schedule})"
-    for i, (name_e, _, _) in enumerate(meshes):
-        if not has_recv[i]:
+    weights_a = np.asarray(weights)
+
+    def assemble(i_lo: int, i_hi: int, tallies, iters, totals, elapsed: float) -> None:
+        """Rows of emitters i_lo <= i < i_hi from the compressed (or dense) tallies of a finished solve."""
+        work = weights_a[i_lo:i_hi] * np.maximum(iters[i_lo:i_hi], 1)
+        work_sum = max(1.0, float(work.sum()))
+        # non-zero bins per emitter: column indices (row-major, i.e. keys in order) and F = hits / total rays (main.py:1922-1923)
+        row_ptr, nz_cols, nz_vals = tallies if isinstance(tallies, tuple) else _csr_from_dense(tallies, totals)
+        bounds = row_ptr.tolist()
+        lo_all, hi_all = bounds[i_lo], bounds[i_hi]
+        vals_all = nz_vals[lo_all:hi_all].tolist()
+        cols_all = nz_cols[lo_all:hi_all].tolist() if reciprocity else None
+        keys_nz = keys_obj[nz_cols[lo_all:hi_all]].tolist() if keys_obj is not None else []
+        iters_l, totals_l = iters[i_lo:i_hi].tolist(), totals[i_lo:i_hi].tolist()     # plain Python numbers for the log lines
+        share_l = (elapsed * work / work_sum).tolist()
+        for i in range(i_lo, i_hi):
+            name_e = meshes[i][0]
+            if not has_recv_l[i]:
+                if _hook is None:
+                    _log(f"({i+1}/{n_surf}) [{name_e}] 0 iter, 0 rays -> 0.000s  (BVH={label}, device={schedule})")
+                continue
+            lo, hi = bounds[i] - lo_all, bounds[i + 1] - lo_all
+            vals = vals_all[lo:hi]
+            row = dict(zip(keys_nz[lo:hi], vals))
+            if reciprocity and areas is not None:
+                for c, f in zip(cols_all[lo:hi], vals):
+                    j = c >> 1
+                    if not (c & 1) and areas[j] > 0.0:
+                        result[meshes[j][0]][f"{name_e}_front"] = f * (areas[i] / areas[j])     # main.py:1926-1927
+            result[name_e].update(row)
             if _hook is None:
-                _log(f"({i+1}/{n_surf}) [{name_e}] 0 iter, 0 rays -> 0.000s  (BVH={label}, device={schedule})")
-            continue
-        lo, hi = bounds[i], bounds[i + 1]
-        vals = vals_all[lo:hi]
-        row = dict(zip(keys_nz[lo:hi], vals))
-        if reciprocity and areas is not None:
-            for c, f in zip(cols_all[lo:hi], vals):
-                j = c >> 1
-                if not (c & 1) and areas[j] > 0.0:
-                    result[meshes[j][0]][f"{name_e}_front"] = f * (areas[i] / areas[j])     # main.py:1926-1927
-        result[name_e].update(row)
-        if _hook is None:
-            _log(f"({i+1}/{n_surf}) [{name_e}] {iters_l[i]} iter, {totals_l[i]:,} rays -> {share_l[i]:0.3f}s  {tail}")
+                _log(f"({i+1}/{n_surf}) [{name_e}] {iters_l[i - i_lo]} iter, {totals_l[i - i_lo]:,} rays -> {share_l[i - i_lo]:0.3f}s  {tail}")
+
+    if _hook is not None and "precomputed" in _hook:
+        tallies, iters, totals = _hook["precomputed"]            # shared-ray solve already ran (view_factor_matrix_and_sky)
+        elapsed = time.time() - t0
+        t_asm = time.perf_counter()
+        assemble(0, n_surf, tallies, iters, totals, elapsed)
+    else:
+        with _Phase("rotations"):
+            table = _rotation_table(seed, n_surf, max_iters)
+        solve_kw = dict(max_iters=max_iters, min_iters=min_iters, interval=interval if schedule == "gpu" else 1,
+                        tol_mode=tol_mode, tol=tol, emit_sid=emit_sid, min_sid=min_sid, want_csr=True)
+        cut = _overlap_split(todo, n_once, min_iters)
+        if cut:
+            # two solves: the rows of the first are built on a worker thread while the GPUs trace the second (the
+            # main thread spends that time inside the library with the GIL released)
+            import sys
+            import threading
+            first_of_second = todo[cut]
+            res_a = _solve_sharded(ctx, d_scene, d_em, todo[:cut], n_once, active, table, **solve_kw)
+            err: List[BaseException] = []
+
+            def work_a(elapsed_a=time.time() - t0):
+                try:
+                    assemble(0, first_of_second, *res_a, elapsed_a)
+                except BaseException as exc:                     # re-raised on the calling thread
+                    err.append(exc)
+
+            worker = threading.Thread(target=work_a, name="rsk-rows")
+            switch = sys.getswitchinterval()
+            sys.setswitchinterval(1e-4)                          # the enqueueing thread must get the GIL back at once
+            t1 = time.time()
+            worker.start()
+            try:
+                res_b = _solve_sharded(ctx, d_scene, d_em, todo[cut:], n_once, active, table, **solve_kw)
+            finally:
+                t_asm = time.perf_counter()
+                worker.join()
+                sys.setswitchinterval(switch)
+            if err:
+                raise err[0]
+            iters, totals = res_a[1] + res_b[1], res_a[2] + res_b[2]
+            elapsed = time.time() - t0
+            assemble(first_of_second, n_surf, res_b[0], res_b[1], res_b[2], time.time() - t1)
+        else:
+            tallies, iters, totals = _solve_sharded(ctx, d_scene, d_em, todo, n_once, active, table, **solve_kw)
+            elapsed = time.time() - t0
+            t_asm = time.perf_counter()
+            assemble(0, n_surf, tallies, iters, totals, elapsed)
 
     LAST_TIMING["assemble"] = time.perf_counter() - t_asm
     LAST_TIMING["other"] = (time.perf_counter() - t_call) - sum(LAST_TIMING.values())      # everything no phase above covers

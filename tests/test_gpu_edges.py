@@ -385,3 +385,40 @@ def test_pipelined_and_sequential_stepping_agree(rb, tmp_path):
     logs = json.loads(outs["1"][6:])["logs"]
     iters = {int(ln.split("]")[1].split("iter")[0]) for ln in logs if "iter" in ln and "traced" not in ln}
     assert len(iters) >= 4 and max(iters) >= 8, iters          # emitters stop at different iterations: the stop path is exercised
+
+
+@pytest.mark.parametrize("reciprocity", [False, True])
+def test_two_part_solve_with_overlapped_rows_equals_one_solve(rb, monkeypatch, reciprocity):
+    """Large solves are cut in two (main._overlap_split) so that the rows of the first part are assembled on a worker
+    thread while the second part is traced: same dictionaries, same key order (rows and reciprocity fill-ins are
+    written in emitter order either way), same progress lines apart from the time shares, and a converging solve stops
+    every emitter at the same iteration."""
+    import raystrack_b200.main as M
+    from raystrack_b200 import synthetic
+    meshes = synthetic.urban_block(3, face_grid=4, ground_grid=8)              # 46 meshes; the ground holds the most rays
+    prm = rb.MatrixParams(samples=8, rays=16, seed=5, bvh="builtin", reciprocity=reciprocity, max_iters=12, min_iters=3, tol=2e-3)
+    lines = {}
+
+    def run(on: bool):
+        monkeypatch.setenv("RSK_OVERLAP_ASSEMBLY", "1" if on else "0")
+        got = []
+        monkeypatch.setattr(M, "_log", got.append)
+        out = rb.view_factor_matrix(meshes, prm)
+        lines[on] = [ln.split(" -> ")[0] for ln in got]
+        return out
+
+    one = run(False)
+    monkeypatch.setattr(M, "OVERLAP_MIN_EMITTERS", 8)
+    monkeypatch.setattr(M, "OVERLAP_MIN_RAYS", 0.0)
+    monkeypatch.setenv("RSK_OVERLAP_ASSEMBLY", "1")
+    todo = list(range(len(meshes)))
+    n_once = [1000] * (len(meshes) - 1) + [20000]
+    cut = M._overlap_split(todo, n_once, 1)
+    assert 0 < cut < len(meshes) and sum(n_once[cut:]) >= 0.15 * sum(n_once) > sum(n_once[cut + 1:])
+    two = run(True)
+    assert "assemble" in M.LAST_TIMING
+    assert one == two
+    for name in one:
+        assert list(one[name]) == list(two[name])
+    assert lines[False] == lines[True] and len(lines[True]) == len(meshes)
+    monkeypatch.setattr(M, "_log", lambda m: None)

@@ -271,3 +271,21 @@ def test_csr_from_dense_matches_the_dense_row_loop():
         assert vals[row_ptr[i]:row_ptr[i + 1]].tolist() == [int(t[i, j]) / float(totals[i]) for j in nz]
     empty = M._csr_from_dense(np.zeros((0, 4), np.int64), np.zeros(0, np.int64))
     assert empty[0].tolist() == [0] and empty[1].size == 0
+
+
+def test_overlap_split_rule(monkeypatch):
+    """main._overlap_split: large solves are cut where the suffix still holds 15 % of the rays; small ones never."""
+    from raystrack_b200 import main as M
+    n = 2001
+    n_once = [97_000] * (n - 1) + [45_000_000]                    # C5: 2000 facades and roofs + the ground
+    todo = list(range(n))
+    assert M._overlap_split(todo, n_once, 40) == n - 1            # the ground alone is 19 % of the rays
+    assert M._overlap_split(todo, n_once, 1) == 0                 # 0.24 G rays certain: not worth a second solve
+    assert M._overlap_split(todo[:100], n_once, 1000) == 0        # few emitters
+    even = [1_000_000] * 1000
+    k = M._overlap_split(list(range(1000)), even, 5)
+    assert k == 850                                               # uniform scene: the last 15 % of the emitters
+    head_heavy = [50_000_000] + [10_000] * 999
+    assert M._overlap_split(list(range(1000)), head_heavy, 40) == 0   # the suffix would hold most rows: no cut
+    monkeypatch.setenv("RSK_OVERLAP_ASSEMBLY", "0")
+    assert M._overlap_split(todo, n_once, 40) == 0
