@@ -235,6 +235,22 @@ __global__ void k_refit(const unsigned *ids, const float4 *tlo, const float4 *th
     }
 }
 
+// Conservative padding (world units) and the lower bound of the (unbiased) quantisation exponent, from the largest
+// coordinate of the scene: computed by one thread on the device so that the build never waits for the bounds.
+struct BuildParams {
+    float pad;
+    int min_exp;
+};
+__global__ void k_build_params(const unsigned *bounds, BuildParams *bp) {
+    float max_abs = 0.f;
+    for (int c = 0; c < 6; ++c) max_abs = fmaxf(max_abs, fabsf(float_from_ord(bounds[c])));
+    if (!(max_abs > 0.f)) max_abs = 1.f;
+    bp->pad = max_abs * 4.76837158e-7f;                 // 2^-21 of the largest coordinate: several ulps
+    int me;
+    frexpf(max_abs, &me);
+    bp->min_exp = me - 20;                              // grid step never below ~2^-20 of the coordinates
+}
+
 // ---- 5. collapse one level of wide nodes
 struct CollapseArgs {
     const int *left, *right;
@@ -244,15 +260,16 @@ struct CollapseArgs {
     const unsigned *ids;          // sorted position -> input triangle
     int n;                        // triangles
     const int2 *queue_in;         // (binary node, wide index)
-    int n_in;
+    const int *n_in;              // entries of queue_in: written by the previous level's launch, never read by the host
     int2 *queue_out;
     int *n_out;
+    int *depth;                   // deepest level that held a node (atomicMax)
+    int level;
     int *node_counter;            // next free wide-node index
     int *tri_counter;             // next free traversal-order triangle slot
     WideNode *nodes;
     int *tri_order;               // traversal slot -> input triangle
-    float pad;                    // conservative padding in world units
-    int min_exp;                  // lower bound of the (unbiased) quantisation exponent
+    const BuildParams *bp;        // padding and exponent floor, derived from the scene bounds on the device
 };
 
 __device__ __forceinline__ int sub_count(const CollapseArgs &a, int node) {
@@ -284,9 +301,20 @@ __device__ __forceinline__ int quant_exp(float ext, int min_exp) {
     return min(max(e, -126), 112);      // + 14 on RSK_PRMT_AXES axes must stay a finite float
 }
 
+// One wide node of the level: grid-stride over the level's queue, whose length only the device knows (the host
+// launches a fixed sequence of levels; a launch past the last level finds an empty queue and returns).
+__device__ void collapse_one(const CollapseArgs &a, int q, float a_pad, int a_min_exp);
+
 __global__ void k_collapse(const CollapseArgs a) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= a.n_in) return;
+    const int n_in = *a.n_in;
+    if (n_in <= 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(a.depth, a.level + 1);
+    const float pad = a.bp->pad;
+    const int min_exp = a.bp->min_exp;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_in; q += gridDim.x * blockDim.x) collapse_one(a, q, pad, min_exp);
+}
+
+__device__ void collapse_one(const CollapseArgs &a, int q, float a_pad, int a_min_exp) {
     const int bnode = a.queue_in[q].x, widx = a.queue_in[q].y;
 
     // Which binary sub-trees become the (up to) 8 children.  Sub-trees of <= RSK_LEAF_MAX triangles are leaf
@@ -319,8 +347,8 @@ __global__ void k_collapse(const CollapseArgs a) {
     float3 lo = make_float3(3e38f, 3e38f, 3e38f), hi = make_float3(-3e38f, -3e38f, -3e38f);
     for (int c = 0; c < nc; ++c) {
         const float4 l = a.nlo[cand[c]], h = a.nhi[cand[c]];
-        clo[c] = make_float3(l.x - a.pad, l.y - a.pad, l.z - a.pad);
-        chi[c] = make_float3(h.x + a.pad, h.y + a.pad, h.z + a.pad);
+        clo[c] = make_float3(l.x - a_pad, l.y - a_pad, l.z - a_pad);
+        chi[c] = make_float3(h.x + a_pad, h.y + a_pad, h.z + a_pad);
         lo = make_float3(fminf(lo.x, clo[c].x), fminf(lo.y, clo[c].y), fminf(lo.z, clo[c].z));
         hi = make_float3(fmaxf(hi.x, chi[c].x), fmaxf(hi.y, chi[c].y), fmaxf(hi.z, chi[c].z));
     }
@@ -360,7 +388,7 @@ __global__ void k_collapse(const CollapseArgs a) {
     node.sid_max = __float_as_int(a.nhi[bnode].w);
     node.reserved = 0u;
     node.ox = lo.x; node.oy = lo.y; node.oz = lo.z;
-    const int ex = quant_exp(hi.x - lo.x, a.min_exp), ey = quant_exp(hi.y - lo.y, a.min_exp), ez = quant_exp(hi.z - lo.z, a.min_exp);
+    const int ex = quant_exp(hi.x - lo.x, a_min_exp), ey = quant_exp(hi.y - lo.y, a_min_exp), ez = quant_exp(hi.z - lo.z, a_min_exp);
     node.scale[0] = exp2f((float)(ex + ((RSK_PRMT_AXES & 1) ? 14 : 0)));
     node.scale[1] = exp2f((float)(ey + ((RSK_PRMT_AXES & 2) ? 14 : 0)));
     node.scale[2] = exp2f((float)(ez + ((RSK_PRMT_AXES & 4) ? 14 : 0)));
@@ -416,7 +444,9 @@ __global__ void k_iota(int *p, int n) {
 }
 
 // tiny scenes (<= RSK_LEAF_MAX triangles): a root whose only child is a leaf with every triangle
-__global__ void k_tiny_root(const float4 *tlo, const float4 *thi, int n, WideNode *nodes, float pad, int min_exp) {
+__global__ void k_tiny_root(const float4 *tlo, const float4 *thi, int n, WideNode *nodes, const BuildParams *bp) {
+    const float pad = bp->pad;
+    const int min_exp = bp->min_exp;
     float3 lo = make_float3(3e38f, 3e38f, 3e38f), hi = make_float3(-3e38f, -3e38f, -3e38f);
     int smin = 0x7fffffff, smax = -1;
     for (int i = 0; i < n; ++i) {
@@ -460,7 +490,8 @@ int rsk_bvh_build(rsk_scene *sc, const float4 *tri_in, const float4 *nrm_in) {
     int *pl_cluster[2] = {nullptr, nullptr}, *pl_nearest = nullptr, *pl_merged = nullptr, *pl_keep = nullptr, *pl_pos = nullptr;
     void *scan_tmp = nullptr;
     int2 *queue[2] = {nullptr, nullptr};
-    int *counters = nullptr;      // [0] node counter, [1] tri counter, [2] queue out count
+    int *counters = nullptr;      // [0] node counter, [1] tri counter, [2] depth, [4 + L] queue length of level L
+    BuildParams *bparams = nullptr;
     void *sort_tmp = nullptr;
     WideNode *nodes = nullptr;
     int rc = RSK_OK;
@@ -468,7 +499,7 @@ int rsk_bvh_build(rsk_scene *sc, const float4 *tri_in, const float4 *nrm_in) {
         rsk_dev_free(tlo); rsk_dev_free(thi); rsk_dev_free(nlo); rsk_dev_free(nhi); rsk_dev_free(bounds); rsk_dev_free(ids); rsk_dev_free(ids_sorted);
         rsk_dev_free(codes); rsk_dev_free(codes_sorted); rsk_dev_free(left); rsk_dev_free(right); rsk_dev_free(parent); rsk_dev_free(count);
         rsk_dev_free(pl_cluster[0]); rsk_dev_free(pl_cluster[1]); rsk_dev_free(pl_nearest); rsk_dev_free(pl_merged); rsk_dev_free(pl_keep); rsk_dev_free(pl_pos); rsk_dev_free(scan_tmp);
-        rsk_dev_free(arrivals); rsk_dev_free(queue[0]); rsk_dev_free(queue[1]); rsk_dev_free(counters); rsk_dev_free(sort_tmp);
+        rsk_dev_free(arrivals); rsk_dev_free(queue[0]); rsk_dev_free(queue[1]); rsk_dev_free(counters); rsk_dev_free(sort_tmp); rsk_dev_free(bparams);
         cudaEventDestroy(t0); cudaEventDestroy(t1);
     };
 #define B_TRY(expr) do { rc = (expr); if (rc != RSK_OK) { cleanup(); rsk_dev_free(nodes); return rc; } } while (0)
@@ -482,22 +513,10 @@ int rsk_bvh_build(rsk_scene *sc, const float4 *tri_in, const float4 *nrm_in) {
     }
     k_tri_boxes<<<rsk_blocks(n, 256), 256, 0, s>>>(tri_in, n, tlo, thi, bounds);
     ctx->launches++;
-    unsigned hb[6];
-    B_CUDA(cudaMemcpyAsync(hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost, s));
-    B_CUDA(cudaStreamSynchronize(s));
-    float max_abs = 0.f;
-    for (int c = 0; c < 6; ++c) {
-        unsigned u = hb[c];
-        unsigned bits = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
-        float f;
-        memcpy(&f, &bits, 4);
-        max_abs = fmaxf(max_abs, fabsf(f));
-    }
-    if (!(max_abs > 0.f)) max_abs = 1.f;
-    const float pad = max_abs * 4.76837158e-7f;                 // 2^-21 of the largest coordinate: several ulps
-    int me;
-    frexpf(max_abs, &me);
-    const int min_exp = me - 20;                                // grid step never below ~2^-20 of the coordinates
+    // padding / exponent floor from the scene bounds, on the device (no read-back: the build waits for the GPU once, at its end)
+    B_TRY(rsk_dev_alloc(&bparams, 1));
+    k_build_params<<<1, 1, 0, s>>>(bounds, bparams);
+    ctx->launches++;
 
     B_TRY(rsk_dev_alloc(&sc->tri_index, n));
     const int max_nodes = n > RSK_LEAF_MAX ? n : 1;
@@ -505,7 +524,7 @@ int rsk_bvh_build(rsk_scene *sc, const float4 *tri_in, const float4 *nrm_in) {
 
     int depth = 1, n_nodes = 1;
     if (n <= RSK_LEAF_MAX) {
-        k_tiny_root<<<1, 1, 0, s>>>(tlo, thi, n, nodes, pad, min_exp);
+        k_tiny_root<<<1, 1, 0, s>>>(tlo, thi, n, nodes, bparams);
         k_iota<<<1, 32, 0, s>>>(sc->tri_index, n);
         ctx->launches += 2;
     } else {
@@ -560,31 +579,47 @@ int rsk_bvh_build(rsk_scene *sc, const float4 *tri_in, const float4 *nrm_in) {
         ctx->launches += 2;
 #endif
 
+        // Level-by-level collapse without host round trips: level L reads its queue length from counters[4 + L] and
+        // appends to counters[5 + L]; the host launches a fixed run of levels (grids sized by the bound min(8^L, n),
+        // grid-stride inside) and reads the counters back once.  Trees deeper than the first run (rare: the collapse
+        // opens the largest child first, 1M triangles give 9-10 levels) get further runs of four levels.
         B_TRY(rsk_dev_alloc(&queue[0], n)); B_TRY(rsk_dev_alloc(&queue[1], n));
-        B_TRY(rsk_dev_alloc(&counters, 4));
-        const int init_counters[4] = {1, 0, 0, 0};
-        B_CUDA(cudaMemcpyAsync(counters, init_counters, sizeof(init_counters), cudaMemcpyHostToDevice, s));
+        constexpr int LEVEL_SLOTS = 4 * RSK_MAX_DEPTH_HOST + 8;
+        B_TRY(rsk_dev_alloc(&counters, 4 + LEVEL_SLOTS));
+        {
+            int init_counters[4 + LEVEL_SLOTS];
+            memset(init_counters, 0, sizeof(init_counters));
+            init_counters[0] = 1;                              // wide node 0 = the root
+            init_counters[4] = 1;                              // level 0 holds the root
+            B_CUDA(cudaMemcpyAsync(counters, init_counters, sizeof(init_counters), cudaMemcpyHostToDevice, s));
+        }
         const int2 root = make_int2(root_id, 0);
         B_CUDA(cudaMemcpyAsync(queue[0], &root, sizeof(root), cudaMemcpyHostToDevice, s));
-        int n_in = 1, cur = 0;
-        depth = 0;
-        while (n_in > 0) {
-            depth++;
-            B_CUDA(cudaMemsetAsync(counters + 2, 0, sizeof(int), s));
-            CollapseArgs a;
-            a.left = left; a.right = right; a.count = count; a.root = root_id; a.nlo = nlo; a.nhi = nhi; a.ids = ids_sorted; a.n = n;
-            a.queue_in = queue[cur]; a.n_in = n_in; a.queue_out = queue[cur ^ 1]; a.n_out = counters + 2;
-            a.node_counter = counters; a.tri_counter = counters + 1; a.nodes = nodes; a.tri_order = sc->tri_index;
-            a.pad = pad; a.min_exp = min_exp;
-            k_collapse<<<rsk_blocks(n_in, 128), 128, 0, s>>>(a);
-            ctx->launches++;
-            int h[3];
+        int level = 0, cur = 0, pending = 1;
+        int run = 12;
+        while (pending > 0 && level < 4 * RSK_MAX_DEPTH_HOST) {
+            for (int k = 0; k < run; ++k, ++level) {
+                CollapseArgs a;
+                a.left = left; a.right = right; a.count = count; a.root = root_id; a.nlo = nlo; a.nhi = nhi; a.ids = ids_sorted; a.n = n;
+                a.queue_in = queue[cur]; a.n_in = counters + 4 + level; a.queue_out = queue[cur ^ 1]; a.n_out = counters + 5 + level;
+                a.depth = counters + 2; a.level = level;
+                a.node_counter = counters; a.tri_counter = counters + 1; a.nodes = nodes; a.tri_order = sc->tri_index;
+                a.bp = bparams;
+                double bound = 1.0;
+                for (int l = 0; l < level && bound < (double)n; ++l) bound *= RSK_WIDE;
+                const int64_t width = (int64_t)(bound < (double)n ? bound : (double)n);
+                const int64_t blocks = rsk_blocks(width, 128);
+                k_collapse<<<(unsigned)(blocks < 4096 ? blocks : 4096), 128, 0, s>>>(a);
+                ctx->launches++;
+                cur ^= 1;
+            }
+            int h[4 + LEVEL_SLOTS];
             B_CUDA(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, s));
             B_CUDA(cudaStreamSynchronize(s));
             n_nodes = h[0];
-            n_in = h[2];
-            cur ^= 1;
-            if (depth > 4 * RSK_MAX_DEPTH_HOST) break;
+            depth = h[2];
+            pending = h[4 + level];
+            run = 4;
         }
         if (depth > RSK_MAX_DEPTH_HOST) {
             rsk_set_error("rsk_bvh_build: wide tree depth %d exceeds the traversal stack (%d)", depth, RSK_MAX_DEPTH_HOST);
