@@ -545,11 +545,19 @@ def run_ours(args):
         return D.max_over_ranks(dt)
 
     e2e_times, e2e_single, phases = [], [], []
+    plan_note = None
     parity = secondary = None
     try:
         if args.e2e_steps > 0:
-            timed_call(1)                                       # warm-up of the public path
+            # warm-up of the public path: one call of each kind.  The first calls of a process grow the context's
+            # memory pool (blocks freed on one stream are not reusable on another until the streams meet), which
+            # costs 50-150 ms once (scripts/overlap_ab.py prints the per-call phases)
+            timed_call(1)
+            timed_call(args.e2e_iters)
             e2e_times = [timed_call(args.e2e_iters) for _ in range(args.e2e_steps)]
+            cut, n_todo = M.LAST_PLAN.get("first_part", 0), M.LAST_PLAN.get("emitters", 0)
+            plan_note = (f"emitters [0, {cut}) of {n_todo} solved first, their result rows built on a worker thread while the "
+                         f"remaining {n_todo - cut} are traced (main._overlap_split)") if cut else None
             e2e_single = [timed_call(1) for _ in range(3)]
         if not args.no_parity:
             parity = parity_block(ctx, rank, world, sc, em, active, n_once, table, args)
@@ -588,7 +596,10 @@ def run_ours(args):
                             f"min_iters=max_iters={args.e2e_iters}, tol=0)) from the mesh list alone: upload of vertices+faces, "
                             f"device-side preparation, GPU BVH build, {args.e2e_iters} iterations, tally download, result dict",
                     "ms_per_step": 1e3 * float(np.mean(e2e_times)) if e2e_times else None,
-                    "phases_ms_last_call": phases[args.e2e_steps] if len(phases) > args.e2e_steps else None,
+                    "ms_each_call": [round(1e3 * t, 1) for t in e2e_times],
+                    "phases_ms_last_call": phases[args.e2e_steps + 1] if len(phases) > args.e2e_steps + 1 else None,
+                    "warmup_calls": 2,
+                    "two_part_solve": plan_note,
                     "single_iteration_call": {"value": e2e_single_value, "unit": UNIT,
                                               "ms": 1e3 * float(np.mean(e2e_single)) if e2e_single else None}}}
     if parity is not None:

@@ -27,6 +27,7 @@ _BVH_AUTO_THRESHOLD = 512      # reference main.py:48
 
 
 LAST_TIMING: Dict[str, float] = {}     # wall-clock seconds per phase of the most recent solve (diagnostics / bench.py)
+LAST_PLAN: Dict[str, int] = {}         # how the most recent matrix solve was cut: {"emitters", "first_part"} (0 = one piece)
 
 
 class _Phase:
@@ -575,6 +576,7 @@ def view_factor_matrix(meshes: List[Mesh], params: MatrixParams, *, prepared: Op
         solve_kw = dict(max_iters=max_iters, min_iters=min_iters, interval=interval if schedule == "gpu" else 1,
                         tol_mode=tol_mode, tol=tol, emit_sid=emit_sid, min_sid=min_sid, want_csr=True)
         cut = _overlap_split(todo, n_once, min_iters)
+        LAST_PLAN.update(emitters=len(todo), first_part=cut)
         if cut:
             # two solves: the rows of the first are built on a worker thread while the GPUs trace the second (the
             # main thread spends that time inside the library with the GIL released)
@@ -679,15 +681,16 @@ def view_factor_to_tregenza_sky(meshes: List[Mesh], params: SkyParams, *, prepar
     label = "builtin" if use_bvh else "off"
     work = np.asarray(weights) * np.maximum(iters, 1)
     work_sum = max(1.0, float(work.sum()))
+    # counts / max(1, total rays) per mesh (main.py:2160-2178): one float64 division per bin, as the reference's
+    # ``counts.astype(np.float64) / denom``; rows become dictionaries over the pre-built key list
+    denom = np.maximum(1, np.asarray(totals, np.int64)).astype(np.float64)
+    rows = (np.asarray(counts)[:, :len(keys)].astype(np.float64) / denom[:, None]).tolist()
+    iters_l, totals_l = np.asarray(iters).tolist(), np.asarray(totals).tolist()
+    share_l = (elapsed * work / work_sum).tolist()
     for i, (name_e, _, _) in enumerate(meshes):
-        denom = float(max(1, int(totals[i])))
-        if discrete:
-            frac = counts[i].astype(np.float64) / denom
-            result[name_e].update({f"Sky_Patch_{k+1}": float(frac[k]) for k in range(145)})
-        else:
-            result[name_e]["Sky"] = float(int(counts[i, 0]) / denom)
+        result[name_e] = dict(zip(keys, rows[i]))
         if _hook is None:
-            _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters[i])} iter, {int(totals[i]):,} rays -> {elapsed * work[i] / work_sum:0.3f}s  "
+            _log(f"({i+1}/{n_surf}) [{name_e}] {int(iters_l[i])} iter, {int(totals_l[i]):,} rays -> {share_l[i]:0.3f}s  "
                  f"(BVH={label}, device={schedule})")
     if _hook is not None:
         _hook.update(iters=iters, totals=totals, n_once=n_once, label=label, elapsed=elapsed, device=schedule)
@@ -737,8 +740,12 @@ def _shared_ray_solve(meshes, matrix_params: MatrixParams, sky_params: SkyParams
     first = max(1, min(limit, max(1, min(int(mp["min_iters"]), int(sp["min_iters"])))))
     all_plans = plan_shards(list(range(n_surf)), n_once, world, allow_split=exchange == "native")
     any_shared = world > 1 and any(j[3] for shard in all_plans for j in shard)
+    chunks = _plan_chunks(all_plans[rank], 2 * n_surf + n_sky)
+    # one GPU, one chunk: every emitter is a job, in order -- the matrix rows leave the device compressed (non-zero bins
+    # only) instead of as the dense [n, 2n] int64 block (64 MB at C5), exactly as in the matrix-only solve
+    csr_single = blocks is None and world == 1 and len(chunks) == 1 and len(chunks[0]) == n_surf and hasattr(_native.Solve, "read_csr")
     try:
-        for c, plan in enumerate(_plan_chunks(all_plans[rank], 2 * n_surf + n_sky)):
+        for c, plan in enumerate(chunks):
             mine = np.asarray([j[0] for j in plan], np.int32)
             ranges = np.asarray([[j[1], j[2]] for j in plan], np.int64).reshape(-1, 2)
             n_shared = sum(1 for j in plan if j[3])
@@ -776,6 +783,9 @@ def _shared_ray_solve(meshes, matrix_params: MatrixParams, sky_params: SkyParams
                         if blocks:
                             i, r = part.read_counters()
                             blocks[k].add_solve(part, keep)
+                        elif csr_single and k == 0:
+                            i, r = part.read_counters()
+                            out[0] = part.read_csr()
                         else:
                             t, i, r = part.read_block()
                             out[0][mine[keep]] = t[keep]
@@ -783,15 +793,19 @@ def _shared_ray_solve(meshes, matrix_params: MatrixParams, sky_params: SkyParams
             finally:
                 solve.close()
         if blocks:
-            for k, out in enumerate((out_m, out_s)):
-                blocks[k].allreduce()
-                out[0] = blocks[k].download(copy=True)          # two blocks share the context's staging area: copy
+            for blk in blocks:
+                blk.allreduce()
         if world > 1:
             from .dist import allreduce_sum_
             if blocks:
                 allreduce_sum_([out_m[1], out_m[2], out_s[1], out_s[2]])
             else:
                 allreduce_sum_([*out_m, *out_s], device=getattr(ctx, "device", 0))
+        if blocks:
+            # matrix rows compressed on the device from the rank-summed block (needs the rank-summed ray totals); the sky
+            # block is small and comes back dense (two blocks share the context's staging area: copy)
+            out_m[0] = blocks[0].read_csr(out_m[2]) if hasattr(blocks[0], "read_csr") else blocks[0].download(copy=True)
+            out_s[0] = blocks[1].download(copy=True)
     finally:
         for blk in blocks or ():
             blk.close()

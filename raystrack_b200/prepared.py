@@ -381,8 +381,9 @@ class PreparedSolver:
             extents = np.zeros((n, 3), np.float32)
             verts, vo, _, _ = self._flat()
             if n and np.all(vo[1:] > vo[:-1]):              # every mesh has vertices: one segmented min/max
-                lo = np.minimum.reduceat(verts, vo[:-1], axis=0)
-                hi = np.maximum.reduceat(verts, vo[:-1], axis=0)
+                cols = np.ascontiguousarray(verts.T)        # per coordinate: reduceat over a contiguous row is ~2x faster
+                lo = np.stack([np.minimum.reduceat(cols[k], vo[:-1]) for k in range(3)], axis=1)
+                hi = np.stack([np.maximum.reduceat(cols[k], vo[:-1]) for k in range(3)], axis=1)
                 centers[:] = 0.5 * (lo + hi)
                 extents[:] = 0.5 * (hi - lo)
             else:
