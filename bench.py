@@ -73,21 +73,34 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region.
+    """SM clock and throttle reasons of this rank's GPU, sampled under load through NVML in-process (nvidia_ml_py).
 
-    NVML in-process (nvidia_ml_py): the first sample is taken the moment the region starts and then every 5 ms, so even
-    the 40 ms region of the 8-GPU run is covered; `nvidia-smi -lms` (the recipe's command) is the fall-back -- it needs
-    ~1 s to print its first row, which is why it saw nothing at N=8 in the first round-2 lines."""
+    One GPU: clock and throttle reasons every 50 ms DURING the timed region, first sample as soon as the K steps are
+    enqueued (measured harmless: 134 samples at 5 ms spacing leave the C5 step at 66.2 ms).
+
+    Several GPUs: NVML queries during an NCCL-coupled step sequence stall the job.  Measured at 2 GPUs (5 steps of
+    33.2 ms, gpurun_out/r2w*): clock + reasons every 5 ms -> 40.8 ms per step, reasons alone -> 35.8, clock alone -> 34.2,
+    no sampling -> 33.2; at 8 GPUs 20 samples turned 8.56 ms steps into 9.81 ms.  So inside a multi-GPU timed region only
+    the cheap query runs -- the SM clock, at its start and every 100 ms -- and the throttle reasons (with another clock
+    reading) are taken under the same load immediately before it, while the warm-up steps execute (``adjacent``).  ``RSK_BENCH_SAMPLE_MS`` overrides the interval ("off": no
+    sampling); ``nvidia-smi -lms`` (the recipe's command) is the fall-back when NVML cannot be loaded -- it needs ~1 s
+    to print its first row and saw nothing of the 43 ms region of the first round-2 lines at 8 GPUs."""
 
     REASONS = (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
                ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"))
 
-    def __init__(self, device: int):
+    def __init__(self, device: int, world: int = 1):
         self.device = device
-        self.sm, self.mx, self.reasons = [], 0, set()
+        self.multi = world > 1
+        self.sm, self.sm_adjacent, self.mx, self.reasons = [], [], 0, set()
         self.proc = self.nv = self.handle = self.thread = None
         self.running = False
         self.source = None
+        mode = os.environ.get("RSK_BENCH_SAMPLE_MS", "100" if self.multi else "50")
+        self.off = mode == "off"
+        self.interval = 0.05 if self.off else max(0.001, float(mode) * 1e-3)
+        if self.off:
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -103,28 +116,37 @@ class ClockSampler:
         except Exception:
             self.nv = None
 
-    def sample(self):
+    def sample(self, reasons: bool = True, adjacent: bool = False):
         nv = self.nv
         if nv is None:
             return
         try:
-            self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
-            bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-            for name, const in self.REASONS:
-                if bits & getattr(nv, const):
-                    self.reasons.add(name)
+            (self.sm_adjacent if adjacent else self.sm).append(int(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+            if reasons:
+                bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                for name, const in self.REASONS:
+                    if bits & getattr(nv, const):
+                        self.reasons.add(name)
         except Exception:
             pass
 
+    def sample_adjacent(self):
+        """Multi-GPU only: clock + reasons while work enqueued just outside the timed region executes."""
+        if self.multi and not self.off:
+            self.sample(reasons=True, adjacent=True)
+
     def _loop(self):
         while self.running:
-            self.sample()
-            time.sleep(0.005)
+            time.sleep(self.interval)
+            if self.running:
+                self.sample(reasons=not self.multi)
 
     def start(self):
+        if self.off:
+            return
         if self.nv is not None:
             self.running = True
-            self.sample()
+            self.sample(reasons=not self.multi)
             self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
             return
@@ -150,16 +172,25 @@ class ClockSampler:
                 if len(r) > col and r[col].lower().startswith("active"):
                     self.reasons.add(name)
 
-    def stop(self):
+    def pause(self):
+        """End of the timed region: stop the thread, keep what was collected (no sample here: the GPU is idle again)."""
         if self.thread is not None:
-            self.sample()
             self.running = False
             self.thread.join(timeout=1.0)
+            self.thread = None
+
+    def stop(self):
+        self.pause()
         if self.proc:
             self.proc.terminate()
         sm = self.sm
-        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": self.mx or None, "reasons": sorted(self.reasons),
-                "samples": len(sm), "source": self.source}
+        out = {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": self.mx or None, "reasons": sorted(self.reasons),
+               "samples": len(sm), "source": self.source}
+        if self.multi and self.nv is not None:
+            out["adjacent"] = {"sm_mhz": self.sm_adjacent, "when": "while the warm-up steps right before the timed region execute (same "
+                               "load); the throttle reasons come from this sample -- NVML's reasons query stalls NCCL-coupled "
+                               "steps (bench.py ClockSampler), inside the region only the SM clock is read"}
+        return out
 
 
 def build_scene(side: int):
@@ -489,22 +520,28 @@ def run_ours(args):
             solve.allreduce_iter_tallies(n_shared)              # NCCL on the iteration's stream, between trace and fold
         solve.enqueue_fold()
 
+    sampler = ClockSampler(local, world) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         one_step()
+    if sampler:
+        sampler.sample_adjacent()                # multi-GPU: clock + throttle reasons while the warm-up steps execute
     ctx.synchronize()
     if world > 1:
         D.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = ctx.launch_count()
     # the timed region: exactly K steps, enqueued back to back (iterations are pipelined over two streams inside the
-    # library; statistics still fold in iteration order), CUDA events on the context's streams around all of them
+    # library; statistics still fold in iteration order), CUDA events on the context's streams around all of them.
+    # The clock sampler starts once everything is enqueued and runs while this thread waits for the GPU (ClockSampler
+    # explains what it may query inside a multi-GPU region).
     ctx.timer_start()
     for _ in range(args.steps):
         one_step()
+    if sampler:
+        sampler.start()
     local_ms = ctx.timer_stop()
+    if sampler:
+        sampler.pause()
     launches = ctx.launch_count() - launches0
     torch.cuda.synchronize()
     if world > 1:
@@ -518,7 +555,7 @@ def run_ours(args):
         ctx.synchronize()
         one_step(trace_ms)
     ctx.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler else None
     my_rays = int(sum(j[2] - j[1] for j in plan))
     trace_avg_ms = float(np.mean(trace_ms))
     solve.close()
