@@ -793,19 +793,15 @@ def _shared_ray_solve(meshes, matrix_params: MatrixParams, sky_params: SkyParams
             finally:
                 solve.close()
         if blocks:
-            for blk in blocks:
-                blk.allreduce()
+            for k, out in enumerate((out_m, out_s)):
+                blocks[k].allreduce()
+                out[0] = blocks[k].download(copy=True)          # two blocks share the context's staging area: copy
         if world > 1:
             from .dist import allreduce_sum_
             if blocks:
                 allreduce_sum_([out_m[1], out_m[2], out_s[1], out_s[2]])
             else:
                 allreduce_sum_([*out_m, *out_s], device=getattr(ctx, "device", 0))
-        if blocks:
-            # matrix rows compressed on the device from the rank-summed block (needs the rank-summed ray totals); the sky
-            # block is small and comes back dense (two blocks share the context's staging area: copy)
-            out_m[0] = blocks[0].read_csr(out_m[2]) if hasattr(blocks[0], "read_csr") else blocks[0].download(copy=True)
-            out_s[0] = blocks[1].download(copy=True)
     finally:
         for blk in blocks or ():
             blk.close()
