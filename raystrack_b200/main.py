@@ -156,12 +156,25 @@ def _rotation_table(seed: int, n_emit: int, max_iters: int) -> np.ndarray:
 
 @functools.lru_cache(maxsize=8)
 def _rotation_rows(seed: int, rows: int) -> np.ndarray:
+    if 0 <= seed and seed + rows <= (1 << 32):
+        # every row at once: SeedSequence + PCG64 + the float32 draw restated on integer arrays, bit-identical to the
+        # generators (``_pcg.py``; 2041 rows: 1.2 ms instead of 39 ms of generator constructions)
+        from ._pcg import rotation_rows
+        table = rotation_rows(seed, rows)
+    else:
+        table = _rotation_rows_generators(seed, rows)
+    table.setflags(write=False)
+    return table
+
+
+def _rotation_rows_generators(seed: int, rows: int) -> np.ndarray:
+    """The reference's own draws, one generator per row (main.py:1810-1812); also raises what NumPy raises for a
+    negative seed."""
     table = np.zeros((rows, 7), np.float32)
     for s in range(rows):
         rng = np.random.default_rng(seed + s)
         table[s, :2] = rng.random(2, dtype=np.float32)
         table[s, 2:] = rng.random(5, dtype=np.float32)
-    table.setflags(write=False)
     return table
 
 

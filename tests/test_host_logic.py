@@ -289,3 +289,27 @@ def test_overlap_split_rule(monkeypatch):
     assert M._overlap_split(list(range(1000)), head_heavy, 40) == 0   # the suffix would hold most rows: no cut
     monkeypatch.setenv("RSK_OVERLAP_ASSEMBLY", "0")
     assert M._overlap_split(todo, n_once, 40) == 0
+
+
+def test_rotation_rows_equal_numpy_generators():
+    """main._rotation_rows: the vectorised SeedSequence + PCG64 restatement (_pcg.py) gives the rows of
+    ``default_rng(seed + s)`` bit for bit; seeds outside its range use the generators themselves."""
+    import pytest
+    from raystrack_b200 import main as M, _pcg
+    rng = np.random.default_rng(2024)
+    seeds = [0, 1, 11, 31, 2**31 - 3, 2**32 - 40] + rng.integers(0, 2**32 - 64, 60).tolist()
+    total = 0
+    for seed in seeds:
+        rows = 40 if seed else 2600
+        got = _pcg.rotation_rows(int(seed), rows)
+        want = M._rotation_rows_generators(int(seed), rows)
+        assert got.dtype == np.float32 and np.array_equal(got, want), seed
+        total += rows
+    assert total >= 5000
+    M._rotation_rows.cache_clear()
+    big = M._rotation_rows(2**32 - 3, 8)                          # crosses 2**32: two-word entropy -> generator loop
+    assert np.array_equal(big, M._rotation_rows_generators(2**32 - 3, 8)) and not big.flags.writeable
+    assert np.array_equal(M._rotation_table(7, 11, 100), M._rotation_rows_generators(7, 111))
+    with pytest.raises(ValueError):
+        M._rotation_rows(-5, 4)
+    M._rotation_rows.cache_clear()
