@@ -260,10 +260,12 @@ def flatten_meshes(meshes: List[Mesh]):
     to = np.zeros(n + 1, np.int64)
     if n == 0:
         return np.empty((0, 3), np.float32), vo, np.empty((0, 3), np.int32), to
-    np.cumsum([np.shape(V)[0] for _, V, _ in meshes], out=vo[1:])
-    np.cumsum([np.shape(F)[0] for _, _, F in meshes], out=to[1:])
-    verts = np.concatenate([np.asarray(V, dtype=np.float32).reshape(-1, 3) for _, V, _ in meshes], axis=0)
-    faces64 = np.concatenate([np.asarray(F).reshape(-1, 3) for _, _, F in meshes], axis=0)
+    vs = [np.asarray(V, dtype=np.float32).reshape(-1, 3) for _, V, _ in meshes]
+    fs = [np.asarray(F).reshape(-1, 3) for _, _, F in meshes]
+    np.cumsum([v.shape[0] for v in vs], out=vo[1:])
+    np.cumsum([f.shape[0] for f in fs], out=to[1:])
+    verts = np.concatenate(vs, axis=0)
+    faces64 = np.concatenate(fs, axis=0)
     narrow = faces64.dtype == np.int32 or (faces64.dtype.kind in "iu" and faces64.dtype.itemsize < 4)     # cannot overflow
     if not narrow and faces64.size and (faces64.max() > 0x7fffffff or faces64.min() < -0x80000000):
         raise IndexError("face index does not fit in int32")
