@@ -81,7 +81,7 @@ class ClockSampler:
     Several GPUs: NVML queries during an NCCL-coupled step sequence stall the job.  Measured at 2 GPUs (5 steps of
     33.2 ms, gpurun_out/r2w*): clock + reasons every 5 ms -> 40.8 ms per step, reasons alone -> 35.8, clock alone -> 34.2,
     no sampling -> 33.2; at 8 GPUs 20 samples turned 8.56 ms steps into 9.81 ms.  So inside a multi-GPU timed region only
-    the cheap query runs -- the SM clock, at its start and every 100 ms -- and the throttle reasons (with another clock
+    the cheap query runs -- the SM clock, once at its start (again after every full second) -- and the throttle reasons (with another clock
     reading) are taken under the same load immediately before it, while the warm-up steps execute (``adjacent``).  ``RSK_BENCH_SAMPLE_MS`` overrides the interval ("off": no
     sampling); ``nvidia-smi -lms`` (the recipe's command) is the fall-back when NVML cannot be loaded -- it needs ~1 s
     to print its first row and saw nothing of the 43 ms region of the first round-2 lines at 8 GPUs."""
@@ -96,7 +96,7 @@ class ClockSampler:
         self.proc = self.nv = self.handle = self.thread = None
         self.running = False
         self.source = None
-        mode = os.environ.get("RSK_BENCH_SAMPLE_MS", "100" if self.multi else "50")
+        mode = os.environ.get("RSK_BENCH_SAMPLE_MS", "1000" if self.multi else "50")
         self.off = mode == "off"
         self.interval = 0.05 if self.off else max(0.001, float(mode) * 1e-3)
         if self.off:
